@@ -1,0 +1,338 @@
+/* oracle/biot_oracle.c - plain-C restatement of Omega3D's direct Biot-Savart path (see biot_oracle.h).
+ *
+ * TEST INFRASTRUCTURE ONLY - the checker, never the product. Compile with -ffp-contract=off so
+ * every float operation rounds exactly as the reference's scalar build does with the same flag.
+ * Each function cites the reference file:line it follows (paths relative to /root/reference).
+ */
+#include "biot_oracle.h"
+#include <math.h>
+#include <omp.h>
+#include <stddef.h>
+
+#define O3D_MAXLEV 3 /* RECURSIVE_LEVELS, src/Influence.h:23 and src/Coefficients.h:23 */
+
+/* ---- src/MathHelper.h:122-135 (scalar specialisations): x^-2.5 by one sqrt and one divide ---- */
+static inline float inv_pow_2p5(float x) { return 1.0f / (x * x * sqrtf(x)); }
+
+/* ---- Winckelmans-Leonard core, src/CoreFunc.h:245-288 ---- */
+/* velocity only; blob target (:245-250) and singular target (:255-259) */
+static inline float wl_core_blob(float distsq, float sr, float tr) {
+  const float r2 = sr * sr + tr * tr;
+  const float d2 = distsq + r2;
+  return (distsq + 2.5f * r2) * inv_pow_2p5(d2);
+}
+static inline float wl_core_point(float distsq, float sr) {
+  const float r2 = sr * sr;
+  const float d2 = distsq + r2;
+  return (distsq + 2.5f * r2) * inv_pow_2p5(d2);
+}
+/* with the gradient factor; blob (:265-274) and singular (:279-287) */
+static inline void wl_core_grad_r2(float distsq, float r2, float* r3, float* bbb) {
+  const float d2 = distsq + r2;
+  const float d2top = distsq + 2.5f * r2;
+  const float dn5 = inv_pow_2p5(d2);
+  *r3 = d2top * dn5;
+  *bbb = 2.0f * dn5 - 5.0f * d2top * dn5 / d2;
+}
+static inline void wl_core_blob_grad(float distsq, float sr, float tr, float* r3, float* bbb) {
+  wl_core_grad_r2(distsq, sr * sr + tr * tr, r3, bbb);
+}
+static inline void wl_core_point_grad(float distsq, float sr, float* r3, float* bbb) {
+  wl_core_grad_r2(distsq, sr * sr, r3, bbb);
+}
+
+/* ---- pairwise kernels, src/Kernels.h ---- */
+typedef struct { float x, y, z, r, wx, wy, wz, q; } src_t; /* q = scalar source strength (vs kernels) */
+
+/* velocity: common tail of kernel_0v_0b (:50-69), kernel_0v_0p (:94-112), kernel_0vs_0p (:115-133) */
+#define VEL_BODY(ACC_T, CORE, WITH_Q)                                           \
+  const float dx = tx - s->x, dy = ty - s->y, dz = tz - s->z;                  \
+  const float k = CORE;                                                        \
+  float cx = dz * s->wy - dy * s->wz;                                          \
+  float cy = dx * s->wz - dz * s->wx;                                          \
+  float cz = dy * s->wx - dx * s->wy;                                          \
+  if (WITH_Q) { cx = cx + dx * s->q; cy = cy + dy * s->q; cz = cz + dz * s->q; } \
+  acc[0] += (ACC_T)(k * cx);                                                   \
+  acc[1] += (ACC_T)(k * cy);                                                   \
+  acc[2] += (ACC_T)(k * cz);
+
+static inline void k_0v_0b(const src_t* s, float tx, float ty, float tz, float tr, double* acc) {
+  VEL_BODY(double, wl_core_blob(dx * dx + dy * dy + dz * dz, s->r, tr), 0)
+}
+static inline void k_0v_0p(const src_t* s, float tx, float ty, float tz, double* acc) {
+  VEL_BODY(double, wl_core_point(dx * dx + dy * dy + dz * dz, s->r), 0)
+}
+static inline void k_0vs_0p(const src_t* s, float tx, float ty, float tz, double* acc) {
+  VEL_BODY(double, wl_core_point(dx * dx + dy * dy + dz * dz, s->r), 1)
+}
+static inline void k_0vs_0p_f(const src_t* s, float tx, float ty, float tz, float* acc) {
+  VEL_BODY(float, wl_core_point(dx * dx + dy * dy + dz * dz, s->r), 1)
+}
+
+/* velocity + 9 gradients: kernel_0v_0bg (:155-193), kernel_0v_0pg (:253-290), kernel_0vs_0pg (:294-345).
+ * acc layout: u v w | ux vx wx | uy vy wy | uz vz wz  (gradient slot 3*j+i = d u_i / d x_j). */
+static inline void grad_body(const src_t* s, float dx, float dy, float dz, float r3, float bbb,
+                             int with_q, double* acc) {
+  float cx = dz * s->wy - dy * s->wz;
+  float cy = dx * s->wz - dz * s->wx;
+  float cz = dy * s->wx - dx * s->wy;
+  if (with_q) {
+    acc[0] += (double)(r3 * (cx + dx * s->q));
+    acc[1] += (double)(r3 * (cy + dy * s->q));
+    acc[2] += (double)(r3 * (cz + dz * s->q));
+  } else {
+    acc[0] += (double)(r3 * cx);
+    acc[1] += (double)(r3 * cy);
+    acc[2] += (double)(r3 * cz);
+  }
+  cx *= bbb; cy *= bbb; cz *= bbb;
+  acc[3]  += (double)(dx * cx);
+  acc[4]  += (double)(dx * cy + s->wz * r3);
+  acc[5]  += (double)(dx * cz - s->wy * r3);
+  acc[6]  += (double)(dy * cx - s->wz * r3);
+  acc[7]  += (double)(dy * cy);
+  acc[8]  += (double)(dy * cz + s->wx * r3);
+  acc[9]  += (double)(dz * cx + s->wy * r3);
+  acc[10] += (double)(dz * cy - s->wx * r3);
+  acc[11] += (double)(dz * cz);
+  if (with_q) { /* gradient of the source-strength part, :327-344 */
+    const float gx = dx * bbb * s->q, gy = dy * bbb * s->q, gz = dz * bbb * s->q;
+    const float iso = s->q * r3;
+    acc[3]  += (double)(dx * gx + iso);
+    acc[4]  += (double)(dx * gy);
+    acc[5]  += (double)(dx * gz);
+    acc[6]  += (double)(dy * gx);
+    acc[7]  += (double)(dy * gy + iso);
+    acc[8]  += (double)(dy * gz);
+    acc[9]  += (double)(dz * gx);
+    acc[10] += (double)(dz * gy);
+    acc[11] += (double)(dz * gz + iso);
+  }
+}
+static inline void k_0v_0bg(const src_t* s, float tx, float ty, float tz, float tr, double* acc) {
+  const float dx = tx - s->x, dy = ty - s->y, dz = tz - s->z;
+  float r3, bbb;
+  wl_core_blob_grad(dx * dx + dy * dy + dz * dz, s->r, tr, &r3, &bbb);
+  grad_body(s, dx, dy, dz, r3, bbb, 0, acc);
+}
+static inline void k_0v_0pg(const src_t* s, float tx, float ty, float tz, double* acc) {
+  const float dx = tx - s->x, dy = ty - s->y, dz = tz - s->z;
+  float r3, bbb;
+  wl_core_point_grad(dx * dx + dy * dy + dz * dz, s->r, &r3, &bbb);
+  grad_body(s, dx, dy, dz, r3, bbb, 0, acc);
+}
+static inline void k_0vs_0pg(const src_t* s, float tx, float ty, float tz, double* acc) {
+  const float dx = tx - s->x, dy = ty - s->y, dz = tz - s->z;
+  float r3, bbb;
+  wl_core_point_grad(dx * dx + dy * dy + dz * dz, s->r, &r3, &bbb);
+  grad_body(s, dx, dy, dz, r3, bbb, 1, acc);
+}
+
+/* ---- recursive panel kernels, src/Kernels.h:1028-1315 ---- */
+typedef struct { float x[3], y[3], z[3]; } tri_t;
+
+/* the 4 children of a flat triangle from its 3 corners + 3 edge midpoints (:1081-1089) */
+static void tri_split(const tri_t* p, tri_t c[4]) {
+  const float nx[6] = {p->x[0], 0.5f * (p->x[0] + p->x[1]), p->x[1], 0.5f * (p->x[0] + p->x[2]), 0.5f * (p->x[1] + p->x[2]), p->x[2]};
+  const float ny[6] = {p->y[0], 0.5f * (p->y[0] + p->y[1]), p->y[1], 0.5f * (p->y[0] + p->y[2]), 0.5f * (p->y[1] + p->y[2]), p->y[2]};
+  const float nz[6] = {p->z[0], 0.5f * (p->z[0] + p->z[1]), p->z[1], 0.5f * (p->z[0] + p->z[2]), 0.5f * (p->z[1] + p->z[2]), p->z[2]};
+  static const int child[4][3] = {{0, 1, 3}, {1, 2, 4}, {1, 4, 3}, {3, 4, 5}};
+  for (int k = 0; k < 4; ++k)
+    for (int v = 0; v < 3; ++v) {
+      c[k].x[v] = nx[child[k][v]];
+      c[k].y[v] = ny[child[k][v]];
+      c[k].z[v] = nz[child[k][v]];
+    }
+}
+static inline void tri_centroid(const tri_t* p, float* cx, float* cy, float* cz) {
+  *cx = (p->x[0] + p->x[1] + p->x[2]) / 3.0f;
+  *cy = (p->y[0] + p->y[1] + p->y[2]) / 3.0f;
+  *cz = (p->z[0] + p->z[1] + p->z[2]) / 3.0f;
+}
+static inline float dist3(float dx, float dy, float dz) { return sqrtf(dx * dx + dy * dy + dz * dz); }
+
+/* panel -> point. grads != 0 selects rkernel_2vs_0pg (:1120-1211), else rkernel_2vs_0p (:1028-1115).
+ * Flop bookkeeping mirrors the reference so the returned count can be compared too. */
+static int rk_2vs_0(const tri_t* p, float gx, float gy, float gz, float gs, float tx, float ty, float tz,
+                    float sa, int lev, int grads, double* acc) {
+  int flops = 0;
+  if (lev == 0) { gx *= sa; gy *= sa; gz *= sa; gs *= sa; flops += 4; }
+  float cx, cy, cz;
+  tri_centroid(p, &cx, &cy, &cz);
+  flops += 9;
+  const float trisize = sqrtf(sa);
+  const float dist = dist3(tx - cx, ty - cy, tz - cz);
+  flops += 10;
+  const int wellsep = dist > trisize * 4.0f; /* my_well_sep, :1000-1002 */
+  flops += 1;
+  if (wellsep || lev == O3D_MAXLEV) {
+    const src_t leaf = {cx, cy, cz, 0.0f, gx, gy, gz, gs};
+    if (grads) { k_0vs_0pg(&leaf, tx, ty, tz, acc); flops += 79 + 14; }
+    else       { k_0vs_0p(&leaf, tx, ty, tz, acc);  flops += 29 + 8; }
+  } else {
+    gx *= 0.25f; gy *= 0.25f; gz *= 0.25f; gs *= 0.25f;
+    const float ca = 0.25f * sa;
+    flops += 5 + 18;
+    tri_t c[4];
+    tri_split(p, c);
+    for (int k = 0; k < 4; ++k) flops += rk_2vs_0(&c[k], gx, gy, gz, gs, tx, ty, tz, ca, lev + 1, grads, acc);
+  }
+  return flops;
+}
+
+/* panel -> panel, float accumulators (:1217-1315) */
+static void rk_2vs_2(const tri_t* p, float gx, float gy, float gz, float gs, const tri_t* q, float sa, float ta,
+                     int lev, float* acc) {
+  if (lev == 0) { gx *= sa; gy *= sa; gz *= sa; gs *= sa; }
+  float sx, sy, sz, tx, ty, tz;
+  tri_centroid(p, &sx, &sy, &sz);
+  tri_centroid(q, &tx, &ty, &tz);
+  const float trisize = sqrtf(sa) + sqrtf(ta);
+  const float dist = dist3(tx - sx, ty - sy, tz - sz);
+  if (dist > trisize * 4.0f || lev == O3D_MAXLEV) {
+    const src_t leaf = {sx, sy, sz, 0.0f, gx, gy, gz, gs};
+    k_0vs_0p_f(&leaf, tx, ty, tz, acc);
+  } else {
+    gx *= 0.0625f; gy *= 0.0625f; gz *= 0.0625f; gs *= 0.0625f;
+    const float sca = 0.25f * sa, tca = 0.25f * ta;
+    tri_t sc[4], tc[4];
+    tri_split(p, sc);
+    tri_split(q, tc);
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) rk_2vs_2(&sc[i], gx, gy, gz, gs, &tc[j], sca, tca, lev + 1, acc);
+  }
+}
+
+static inline void load_tri(tri_t* t, const float* nx, const float* ny, const float* nz, const uint32_t* idx, int64_t p) {
+  for (int v = 0; v < 3; ++v) {
+    const uint32_t n = idx[3 * p + v];
+    t->x[v] = nx[n]; t->y[v] = ny[n]; t->z[v] = nz[n];
+  }
+}
+
+/* ---- exported single-interaction hooks ---- */
+static src_t src_from7(const float s[7]) { src_t r = {s[0], s[1], s[2], s[3], s[4], s[5], s[6], 0.0f}; return r; }
+void o3d_oracle_kernel_0v_0b(const float s[7], const float t[4], double u[3]) {
+  const src_t a = src_from7(s); u[0] = u[1] = u[2] = 0.0; k_0v_0b(&a, t[0], t[1], t[2], t[3], u);
+}
+void o3d_oracle_kernel_0v_0p(const float s[7], const float t[3], double u[3]) {
+  const src_t a = src_from7(s); u[0] = u[1] = u[2] = 0.0; k_0v_0p(&a, t[0], t[1], t[2], u);
+}
+void o3d_oracle_kernel_0v_0bg(const float s[7], const float t[4], double out[12]) {
+  const src_t a = src_from7(s); for (int i = 0; i < 12; ++i) out[i] = 0.0; k_0v_0bg(&a, t[0], t[1], t[2], t[3], out);
+}
+void o3d_oracle_kernel_0v_0pg(const float s[7], const float t[3], double out[12]) {
+  const src_t a = src_from7(s); for (int i = 0; i < 12; ++i) out[i] = 0.0; k_0v_0pg(&a, t[0], t[1], t[2], out);
+}
+static tri_t tri_from9(const float v[9]) {
+  tri_t t; for (int k = 0; k < 3; ++k) { t.x[k] = v[3 * k]; t.y[k] = v[3 * k + 1]; t.z[k] = v[3 * k + 2]; } return t;
+}
+int o3d_oracle_rkernel_2vs_0p(const float tri[9], const float str[4], const float t[3], float sa, double u[3]) {
+  const tri_t p = tri_from9(tri); u[0] = u[1] = u[2] = 0.0;
+  return rk_2vs_0(&p, str[0], str[1], str[2], str[3], t[0], t[1], t[2], sa, 0, 0, u);
+}
+int o3d_oracle_rkernel_2vs_0pg(const float tri[9], const float str[4], const float t[3], float sa, double out[12]) {
+  const tri_t p = tri_from9(tri); for (int i = 0; i < 12; ++i) out[i] = 0.0;
+  return rk_2vs_0(&p, str[0], str[1], str[2], str[3], t[0], t[1], t[2], sa, 0, 1, out);
+}
+
+/* ---- loop nests ---- */
+static inline void flush_acc(int nacc, const double* acc, int64_t nt, int64_t i, float* tu, float* tug, double sign) {
+  for (int d = 0; d < 3; ++d) tu[d * nt + i] = (float)((double)tu[d * nt + i] + sign * acc[d]);
+  if (nacc == 12) for (int d = 0; d < 9; ++d) tug[d * nt + i] = (float)((double)tug[d * nt + i] + acc[3 + d]);
+}
+
+/* src/Influence.h:278-309 (0pg), :351-365 (0p), :443-474 (0bg), :518-533 (0b): OpenMP over targets,
+ * sources innermost in index order, one double accumulator set per target, then tu[d][i] += acc. */
+void o3d_oracle_pts_on_pts(int64_t ns, const float* sx, const float* sy, const float* sz, const float* sr,
+                           const float* ssx, const float* ssy, const float* ssz,
+                           int64_t nt, const float* tx, const float* ty, const float* tz, const float* tr,
+                           float* tu, float* tug) {
+  const int nacc = tug ? 12 : 3;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nt; ++i) {
+    double acc[12] = {0};
+    for (int64_t j = 0; j < ns; ++j) {
+      const src_t s = {sx[j], sy[j], sz[j], sr[j], ssx[j], ssy[j], ssz[j], 0.0f};
+      if (tug) { if (tr) k_0v_0bg(&s, tx[i], ty[i], tz[i], tr[i], acc); else k_0v_0pg(&s, tx[i], ty[i], tz[i], acc); }
+      else     { if (tr) k_0v_0b(&s, tx[i], ty[i], tz[i], tr[i], acc);  else k_0v_0p(&s, tx[i], ty[i], tz[i], acc); }
+    }
+    flush_acc(nacc, acc, nt, i, tu, tug, 1.0);
+  }
+}
+
+/* src/Influence.h:728-775 (grads) and :826-864 (vel only); blob-target branches :989-1094 are the
+ * same arithmetic (target radius is never used by panel kernels). Sheet strength = ts/area. */
+void o3d_oracle_pan_on_pts(int64_t np, const float* nx, const float* ny, const float* nz, const uint32_t* idx,
+                           const float* ts, const float* area, const float* sss,
+                           int64_t nt, const float* tx, const float* ty, const float* tz,
+                           float* tu, float* tug) {
+  const int nacc = tug ? 12 : 3;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int64_t i = 0; i < nt; ++i) {
+    double acc[12] = {0};
+    for (int64_t j = 0; j < np; ++j) {
+      tri_t p; load_tri(&p, nx, ny, nz, idx, j);
+      rk_2vs_0(&p, ts[j] / area[j], ts[np + j] / area[j], ts[2 * np + j] / area[j], sss ? sss[j] : 0.0f,
+               tx[i], ty[i], tz[i], area[j], 0, tug != NULL, acc);
+    }
+    flush_acc(nacc, acc, nt, i, tu, tug, 1.0);
+  }
+}
+
+/* src/Influence.h:1186-1214: panel geometry plays "source", particle position plays "target",
+ * particle strength / panel area is the sheet strength, result subtracted from pu. */
+void o3d_oracle_pts_on_pan(int64_t ns, const float* sx, const float* sy, const float* sz,
+                           const float* ssx, const float* ssy, const float* ssz,
+                           int64_t np, const float* nx, const float* ny, const float* nz, const uint32_t* idx,
+                           const float* area, float* pu) {
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t i = 0; i < np; ++i) {
+    double acc[3] = {0};
+    tri_t p; load_tri(&p, nx, ny, nz, idx, i);
+    for (int64_t j = 0; j < ns; ++j)
+      rk_2vs_0(&p, ssx[j] / area[i], ssy[j] / area[i], ssz[j] / area[i], 0.0f, sx[j], sy[j], sz[j], area[i], 0, 0, acc);
+    flush_acc(3, acc, np, i, pu, NULL, -1.0);
+  }
+}
+
+/* src/Coefficients.h:214-446 (scalar arm :327-411). Column block j = source panel: unit sheet strength
+ * along its x1, x2, then unit source; rows = target panel i projected on (t1, t2, n). */
+void o3d_oracle_pan_on_pan_coeff(int64_t nsp, const float* snx, const float* sny, const float* snz,
+                                 const uint32_t* sidx, const float* sb1, const float* sb2, const float* sarea,
+                                 int64_t ntp, const float* tnx, const float* tny, const float* tnz,
+                                 const uint32_t* tidx, const float* tb1, const float* tb2, const float* tnrm,
+                                 const float* tarea, int self, float* coeffs) {
+  const int64_t nrows = 3 * ntp;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t j = 0; j < nsp; ++j) {
+    tri_t p; load_tri(&p, snx, sny, snz, sidx, j);
+    const float dir[3][4] = {{sb1[j], sb1[nsp + j], sb1[2 * nsp + j], 0.0f},
+                             {sb2[j], sb2[nsp + j], sb2[2 * nsp + j], 0.0f},
+                             {0.0f, 0.0f, 0.0f, 1.0f}};
+    for (int64_t i = 0; i < ntp; ++i) {
+      tri_t q; load_tri(&q, tnx, tny, tnz, tidx, i);
+      for (int k = 0; k < 3; ++k) {
+        float r[3] = {0.0f, 0.0f, 0.0f};
+        rk_2vs_2(&p, dir[k][0], dir[k][1], dir[k][2], dir[k][3], &q, sarea[j], tarea[i], 0, r);
+        float* col = coeffs + (3 * j + k) * nrows + 3 * i;
+        col[0] = r[0] * tb1[i] + r[1] * tb1[ntp + i] + r[2] * tb1[2 * ntp + i];
+        col[1] = r[0] * tb2[i] + r[1] * tb2[ntp + i] + r[2] * tb2[2 * ntp + i];
+        col[2] = r[0] * tnrm[i] + r[1] * tnrm[ntp + i] + r[2] * tnrm[2 * ntp + i];
+      }
+    }
+    if (self) { /* :414-436 */
+      float* d0 = coeffs + (3 * j) * nrows + 3 * j;
+      d0[0] = 0.0f; d0[1] = (float)(2.0 * M_PI); d0[2] = 0.0f;
+      float* d1 = d0 + nrows;
+      d1[0] = (float)(-2.0 * M_PI); d1[1] = 0.0f; d1[2] = 0.0f;
+      float* d2 = d1 + nrows;
+      d2[0] = 0.0f; d2[1] = 0.0f; d2[2] = (float)(2.0 * M_PI);
+    }
+  }
+  const float fac = (float)(1.0 / (4.0 * M_PI)); /* :448-451 */
+  for (int64_t k = 0; k < nrows * 3 * nsp; ++k) coeffs[k] = coeffs[k] * fac;
+}
+
+void o3d_oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int o3d_oracle_max_threads(void) { return omp_get_max_threads(); }

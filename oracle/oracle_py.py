@@ -1,0 +1,196 @@
+"""ctypes front end to the parity oracles. TEST INFRASTRUCTURE ONLY.
+
+Two libraries live under ``oracle/_ref/`` (git-ignored build outputs, see ``oracle/Makefile``):
+
+* ``libo3d_oracle.so`` - the plain-C restatement (``biot_oracle.c``); builds anywhere.
+* ``libo3d_ref.so`` / ``libo3d_ref_fast.so`` - the REFERENCE's own templates
+  (``/root/reference/src/Influence.h``, ``Coefficients.h``) behind ``ref_driver.cpp``; built only in
+  the container that has ``/root/reference`` and shipped prebuilt to the GPU box.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs may import this module. Nothing under ``omega3d_b200/`` does.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_float, c_int, c_int64, c_long, c_void_p
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(HERE, "_ref")
+REFERENCE_ROOT = "/root/reference"
+
+
+def build(want_ref: bool = True) -> None:
+    """Compile the restatement (always) and the reference build (when /root/reference exists)."""
+    subprocess.run(["make", "-s", "-C", HERE, "restate"], check=True)
+    if want_ref and os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
+        subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+def _f32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Restatement:
+    """biot_oracle.c - every entry point takes SoA float32 arrays and accumulates in place."""
+
+    def __init__(self):
+        path = os.path.join(OUT, "libo3d_oracle.so")
+        if not os.path.exists(path):
+            build(want_ref=False)
+        self.lib = ctypes.CDLL(path)
+        L = self.lib
+        L.o3d_oracle_pts_on_pts.argtypes = [c_int64] + [c_void_p] * 7 + [c_int64] + [c_void_p] * 6
+        L.o3d_oracle_pan_on_pts.argtypes = [c_int64] + [c_void_p] * 7 + [c_int64] + [c_void_p] * 5
+        L.o3d_oracle_pts_on_pan.argtypes = [c_int64] + [c_void_p] * 6 + [c_int64] + [c_void_p] * 6
+        L.o3d_oracle_pan_on_pan_coeff.argtypes = (
+            [c_int64] + [c_void_p] * 7 + [c_int64] + [c_void_p] * 8 + [c_int, c_void_p])
+        L.o3d_oracle_rkernel_2vs_0p.argtypes = [c_void_p] * 3 + [c_float, c_void_p]
+        L.o3d_oracle_rkernel_2vs_0pg.argtypes = [c_void_p] * 3 + [c_float, c_void_p]
+        L.o3d_oracle_set_threads.argtypes = [c_int]
+
+    def set_threads(self, n):
+        self.lib.o3d_oracle_set_threads(int(n))
+
+    def max_threads(self):
+        return int(self.lib.o3d_oracle_max_threads())
+
+    def pts_on_pts(self, sx, sr, ss, tx, tr, tu, tug):
+        """sx (3,ns), sr (ns,), ss (3,ns); tx (3,nt), tr (nt,)|None; tu (3,nt) and tug (9,nt)|None in/out."""
+        ns, nt = sx.shape[1], tx.shape[1]
+        self.lib.o3d_oracle_pts_on_pts(ns, _p(sx[0]), _p(sx[1]), _p(sx[2]), _p(sr), _p(ss[0]), _p(ss[1]), _p(ss[2]),
+                                       nt, _p(tx[0]), _p(tx[1]), _p(tx[2]), _p(tr), _p(tu), _p(tug))
+
+    def pan_on_pts(self, nodes, idx, ts, area, sss, tx, tu, tug):
+        """nodes (3,nn) SoA, idx (np,3) uint32, ts (3,np), area (np,), sss (np,)|None."""
+        np_, nt = idx.shape[0], tx.shape[1]
+        self.lib.o3d_oracle_pan_on_pts(np_, _p(nodes[0]), _p(nodes[1]), _p(nodes[2]), _p(idx), _p(ts), _p(area),
+                                       _p(sss), nt, _p(tx[0]), _p(tx[1]), _p(tx[2]), _p(tu), _p(tug))
+
+    def pts_on_pan(self, sx, ss, nodes, idx, area, pu):
+        ns, np_ = sx.shape[1], idx.shape[0]
+        self.lib.o3d_oracle_pts_on_pan(ns, _p(sx[0]), _p(sx[1]), _p(sx[2]), _p(ss[0]), _p(ss[1]), _p(ss[2]),
+                                       np_, _p(nodes[0]), _p(nodes[1]), _p(nodes[2]), _p(idx), _p(area), _p(pu))
+
+    def pan_on_pan_coeff(self, snodes, sidx, sb1, sb2, sarea, tnodes, tidx, tb1, tb2, tnrm, tarea, self_block):
+        nsp, ntp = sidx.shape[0], tidx.shape[0]
+        out = np.zeros(9 * nsp * ntp, np.float32)
+        self.lib.o3d_oracle_pan_on_pan_coeff(
+            nsp, _p(snodes[0]), _p(snodes[1]), _p(snodes[2]), _p(sidx), _p(sb1), _p(sb2), _p(sarea),
+            ntp, _p(tnodes[0]), _p(tnodes[1]), _p(tnodes[2]), _p(tidx), _p(tb1), _p(tb2), _p(tnrm), _p(tarea),
+            int(bool(self_block)), _p(out))
+        return out
+
+    def kernel(self, name, s7, t):
+        n = 12 if name.endswith("g") else 3
+        out = np.zeros(n, np.float64)
+        getattr(self.lib, "o3d_oracle_kernel_" + name)(_p(_f32(s7)), _p(_f32(t)), _p(out))
+        return out
+
+    def rkernel(self, grads, tri9, str4, t3, sa):
+        out = np.zeros(12 if grads else 3, np.float64)
+        fn = self.lib.o3d_oracle_rkernel_2vs_0pg if grads else self.lib.o3d_oracle_rkernel_2vs_0p
+        flops = fn(_p(_f32(tri9)), _p(_f32(str4)), _p(_f32(t3)), c_float(sa), _p(out))
+        return out, flops
+
+
+class Reference:
+    """ref_driver.cpp - the reference's real code. ``fast=True`` loads the stock-flags build (timing)."""
+
+    TARG_FIELD, TARG_TRACER, TARG_BLOB = 0, 1, 2
+
+    def __init__(self, fast: bool = False):
+        path = os.path.join(OUT, "libo3d_ref_fast.so" if fast else "libo3d_ref.so")
+        if not os.path.exists(path):
+            build(want_ref=True)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (needs /root/reference to build; ships prebuilt to the GPU box)")
+        self.lib = ctypes.CDLL(path)
+        L = self.lib
+        L.o3d_ref_pts_on_pts.argtypes = [c_int] + [c_void_p] * 5 + [c_int, c_int] + [c_void_p] * 4 + [c_int] + [c_void_p] * 2
+        L.o3d_ref_surface_props.argtypes = [c_int, c_void_p, c_int] + [c_void_p] * 7
+        L.o3d_ref_pan_on_pts.argtypes = [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int] + [c_void_p] * 6
+        L.o3d_ref_pts_on_pan.argtypes = [c_int] + [c_void_p] * 5 + [c_int, c_void_p, c_int] + [c_void_p] * 3
+        L.o3d_ref_pan_on_pan.argtypes = [c_int, c_void_p, c_int, c_void_p, c_void_p] * 2 + [c_void_p]
+        L.o3d_ref_pan_on_pan_coeff.argtypes = [c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                               c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+        L.o3d_ref_pan_on_pan_coeff.restype = c_long
+        L.o3d_ref_rkernel_2vs_0p.argtypes = [c_void_p] * 3 + [c_float, c_void_p]
+        L.o3d_ref_rkernel_2vs_0pg.argtypes = [c_void_p] * 3 + [c_float, c_void_p]
+
+    def set_threads(self, n):
+        self.lib.o3d_ref_set_threads(int(n))
+
+    def max_threads(self):
+        return int(self.lib.o3d_ref_max_threads())
+
+    def pts_on_pts(self, sx, sr, ss, tx, tr, tu, tug, targ_kind=None):
+        ns, nt = sx.shape[1], tx.shape[1]
+        if targ_kind is None:
+            targ_kind = self.TARG_BLOB if tr is not None else (self.TARG_FIELD if tug is not None else self.TARG_TRACER)
+        rc = self.lib.o3d_ref_pts_on_pts(ns, _p(sx[0]), _p(sx[1]), _p(sx[2]), _p(sr), _p(ss), targ_kind, nt,
+                                         _p(tx[0]), _p(tx[1]), _p(tx[2]), _p(tr), int(tug is not None), _p(tu), _p(tug))
+        if rc != 0:
+            raise RuntimeError("reference asserts on this target-kind/result-type combination")
+
+    def surface_props(self, nodes_i, idx, val):
+        """nodes_i (nn,3) interleaved, idx (np,3), val (np,3) -> area, ts(3,np), b1, b2, nrm (3,np)."""
+        nn, np_ = nodes_i.shape[0], idx.shape[0]
+        area = np.zeros(np_, np.float32)
+        ts, b1, b2, nrm = (np.zeros((3, np_), np.float32) for _ in range(4))
+        self.lib.o3d_ref_surface_props(nn, _p(nodes_i), np_, _p(idx), _p(val), _p(area), _p(ts), _p(b1), _p(b2), _p(nrm))
+        return area, ts, b1, b2, nrm
+
+    def pan_on_pts(self, nodes_i, idx, val, tx, tr, tu, tug, targ_kind=None):
+        nn, np_, nt = nodes_i.shape[0], idx.shape[0], tx.shape[1]
+        if targ_kind is None:
+            targ_kind = self.TARG_BLOB if tr is not None else (self.TARG_FIELD if tug is not None else self.TARG_TRACER)
+        self.lib.o3d_ref_pan_on_pts(nn, _p(nodes_i), np_, _p(idx), _p(val), targ_kind, nt,
+                                    _p(tx[0]), _p(tx[1]), _p(tx[2]), _p(tr), _p(tu), _p(tug))
+
+    def pts_on_pan(self, sx, sr, ss, nodes_i, idx, val, pu):
+        ns, nn, np_ = sx.shape[1], nodes_i.shape[0], idx.shape[0]
+        self.lib.o3d_ref_pts_on_pan(ns, _p(sx[0]), _p(sx[1]), _p(sx[2]), _p(sr), _p(ss), nn, _p(nodes_i), np_,
+                                    _p(idx), _p(val), _p(pu))
+
+    def pan_on_pan(self, nodes_i, idx, val, tnodes_i, tidx, tval):
+        pu = np.zeros((3, tidx.shape[0]), np.float32)
+        self.lib.o3d_ref_pan_on_pan(nodes_i.shape[0], _p(nodes_i), idx.shape[0], _p(idx), _p(val),
+                                    tnodes_i.shape[0], _p(tnodes_i), tidx.shape[0], _p(tidx), _p(tval), _p(pu))
+        return pu
+
+    def pan_on_pan_coeff(self, nodes_i, idx, bc, target=None):
+        if target is None:
+            n = 9 * idx.shape[0] ** 2
+            out = np.zeros(n, np.float32)
+            self.lib.o3d_ref_pan_on_pan_coeff(nodes_i.shape[0], _p(nodes_i), idx.shape[0], _p(idx), _p(bc), 1,
+                                              0, None, 0, None, None, _p(out))
+            return out
+        tn, ti, tb = target
+        out = np.zeros(9 * idx.shape[0] * ti.shape[0], np.float32)
+        self.lib.o3d_ref_pan_on_pan_coeff(nodes_i.shape[0], _p(nodes_i), idx.shape[0], _p(idx), _p(bc), 0,
+                                          tn.shape[0], _p(tn), ti.shape[0], _p(ti), _p(tb), _p(out))
+        return out
+
+    def kernel_0v_0bg(self, s7, t4):
+        out = np.zeros(12, np.float64)
+        self.lib.o3d_ref_kernel_0v_0bg(_p(_f32(s7)), _p(_f32(t4)), _p(out))
+        return out
+
+    def rkernel(self, grads, tri9, str4, t3, sa):
+        out = np.zeros(12 if grads else 3, np.float64)
+        fn = self.lib.o3d_ref_rkernel_2vs_0pg if grads else self.lib.o3d_ref_rkernel_2vs_0p
+        flops = fn(_p(_f32(tri9)), _p(_f32(str4)), _p(_f32(t3)), c_float(sa), _p(out))
+        return out, flops
+
+
+def have_reference() -> bool:
+    return os.path.exists(os.path.join(OUT, "libo3d_ref.so")) or os.path.isdir(os.path.join(REFERENCE_ROOT, "src"))

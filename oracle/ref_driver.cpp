@@ -1,0 +1,236 @@
+// oracle/ref_driver.cpp - C-callable wrapper around the REFERENCE's own hot-path templates.
+//
+// TEST INFRASTRUCTURE ONLY. This file contains no Biot-Savart arithmetic of its own: it
+// builds the reference's containers (Points<float>, Surfaces<float>) from flat arrays and
+// calls the reference's loop nests, compiled from the sources where they lie under
+// /root/reference/src (never copied into this repo):
+//     points_affect_points<float,double>   src/Influence.h:67-551
+//     panels_affect_points<float,double>   src/Influence.h:557-1099
+//     points_affect_panels<float,double>   src/Influence.h:1107-1221
+//     panels_on_panels_coeff<float>        src/Coefficients.h:169-483
+// with ExecEnv(true,true,direct,cpu_x86), i.e. the scalar "float kernel, double accumulator"
+// arm (src/Simulation.h:41-47 without USE_VC). The result, oracle/_ref/libo3d_ref.so, is the
+// parity oracle for tests/ and the CPU baseline for bench.py. Nothing in omega3d_b200/
+// may link or load it.
+//
+// Build: see oracle/Makefile (target _ref/libo3d_ref.so).
+
+#ifndef VERBOSE
+#define VERBOSE false  // CMake normally passes -DVERBOSE (CMakeLists.txt:31-35)
+#endif
+#include "Collection.h"  // must precede Influence.h (ElementBase.h -> GlComputeState.h -> Collection.h cycle)
+#include "Influence.h"
+#include "Coefficients.h"
+
+#include <omp.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+// The reference chats on stdout/stderr from every routine and ctor; mute fds 1 and 2 for
+// the duration of a call so harness output (one JSON line) stays clean.
+struct Mute {
+  int so = -1, se = -1;
+  bool on;
+  explicit Mute(bool enable) : on(enable) {
+    if (!on) return;
+    fflush(stdout); fflush(stderr); std::cout.flush(); std::cerr.flush();
+    so = dup(1); se = dup(2);
+    int nul = open("/dev/null", O_WRONLY);
+    dup2(nul, 1); dup2(nul, 2); close(nul);
+  }
+  ~Mute() {
+    if (!on) return;
+    fflush(stdout); fflush(stderr); std::cout.flush(); std::cerr.flush();
+    dup2(so, 1); dup2(se, 2); close(so); close(se);
+  }
+};
+
+bool g_mute = true;
+
+Points<float> make_points(int n, const float* x, const float* y, const float* z,
+                          const float* str3 /*SoA 3 x n or NULL*/, const float* rad /*or NULL*/,
+                          elem_t e, move_t m) {
+  std::vector<float> px(3 * (size_t)n), val;
+  for (int i = 0; i < n; ++i) { px[3*i] = x[i]; px[3*i+1] = y[i]; px[3*i+2] = z[i]; }
+  if (e != inert) {
+    val.resize(3 * (size_t)n);
+    for (int i = 0; i < n; ++i) for (int d = 0; d < 3; ++d) val[3*i+d] = str3[(size_t)d*n + i];
+  }
+  ElementPacket<float> pk(px, std::vector<Int>(), val, (size_t)n, 0);
+  Points<float> p(pk, e, m, nullptr, 0.0f);
+  if (e != inert && rad) {
+    Vector<float>& r = p.get_rad();
+    for (int i = 0; i < n; ++i) r[i] = rad[i];
+  }
+  return p;
+}
+
+Surfaces<float> make_surfaces(int nn, const float* nodes /*3*nn interleaved*/, int np,
+                              const uint32_t* idx /*3*np*/, const float* val /*3*np interleaved*/,
+                              elem_t e) {
+  std::vector<float> x(nodes, nodes + 3 * (size_t)nn);
+  std::vector<Int> id(idx, idx + 3 * (size_t)np);
+  std::vector<float> v(val, val + 3 * (size_t)np);
+  ElementPacket<float> pk(x, id, v, (size_t)np, 2);
+  return Surfaces<float>(pk, e, fixed, nullptr);
+}
+
+// target kinds understood by the *_pts entry points
+//   0: inert + fixed      -> no radius, HAS velgrad storage   (field points)
+//   1: inert + lagrangian -> no radius, NO velgrad storage    (tracers)
+//   2: active + lagrangian-> radius and velgrad storage       (vortex particles)
+Points<float> make_targets(int kind, int nt, const float* tx, const float* ty, const float* tz,
+                           const float* tr) {
+  if (kind == 2) {
+    std::vector<float> zero(3 * (size_t)nt, 0.0f);
+    return make_points(nt, tx, ty, tz, zero.data(), tr, active, lagrangian);
+  }
+  return make_points(nt, tx, ty, tz, nullptr, nullptr, inert, kind == 0 ? fixed : lagrangian);
+}
+
+void load_results(Points<float>& t, int nt, const float* tu, const float* tug) {
+  auto& u = t.get_vel();
+  for (int d = 0; d < 3; ++d) std::memcpy(u[d].data(), tu + (size_t)d*nt, sizeof(float)*nt);
+  auto& og = t.get_velgrad();
+  if (og && tug) for (int d = 0; d < 9; ++d) std::memcpy((*og)[d].data(), tug + (size_t)d*nt, sizeof(float)*nt);
+}
+void store_results(Points<float>& t, int nt, float* tu, float* tug) {
+  auto& u = t.get_vel();
+  for (int d = 0; d < 3; ++d) std::memcpy(tu + (size_t)d*nt, u[d].data(), sizeof(float)*nt);
+  auto& og = t.get_velgrad();
+  if (og && tug) for (int d = 0; d < 9; ++d) std::memcpy(tug + (size_t)d*nt, (*og)[d].data(), sizeof(float)*nt);
+}
+
+}  // namespace
+
+extern "C" {
+
+void o3d_ref_set_mute(int on) { g_mute = on != 0; }
+int o3d_ref_max_threads() { return omp_get_max_threads(); }
+void o3d_ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
+// src (ns particles, SoA) -> targets; results ACCUMULATE into tu (3 x nt SoA) and tug (9 x nt SoA).
+// want_grad selects ResultsType velandgrad / velonly. Returns 0, or -1 on a combination the
+// reference itself asserts on (src/Influence.h:368-370).
+int o3d_ref_pts_on_pts(int ns, const float* sx, const float* sy, const float* sz, const float* sr,
+                       const float* ss3, int targ_kind, int nt, const float* tx, const float* ty,
+                       const float* tz, const float* tr, int want_grad, float* tu, float* tug) {
+  if (targ_kind == 1 && want_grad) return -1;
+  Mute m(g_mute);
+  Points<float> src = make_points(ns, sx, sy, sz, ss3, sr, active, lagrangian);
+  Points<float> targ = make_targets(targ_kind, nt, tx, ty, tz, tr);
+  load_results(targ, nt, tu, tug);
+  ExecEnv env(true, true, direct, cpu_x86);
+  points_affect_points<float, double>(src, targ, ResultsType(want_grad ? velandgrad : velonly), env);
+  store_results(targ, nt, tu, tug);
+  return 0;
+}
+
+// Derived panel quantities exactly as the reference's Surfaces ctor computes them
+// (compute_bases, vortex_sheet_to_panel_strength: src/Surfaces.h:309-335).
+// val = (vortex-sheet strength along x1, along x2, source-sheet strength) per panel.
+// Outputs (all SoA): area[np], ts[3*np] total vortex strength, b1/b2/nrm[3*np] basis vectors.
+int o3d_ref_surface_props(int nn, const float* nodes, int np, const uint32_t* idx, const float* val,
+                          float* area, float* ts, float* b1, float* b2, float* nrm) {
+  Mute m(g_mute);
+  Surfaces<float> s = make_surfaces(nn, nodes, np, idx, val, active);
+  for (int i = 0; i < np; ++i) area[i] = s.get_area()[i];
+  for (int d = 0; d < 3; ++d) for (int i = 0; i < np; ++i) {
+    ts[(size_t)d*np + i]  = s.get_str()[d][i];
+    b1[(size_t)d*np + i]  = s.get_x1()[d][i];
+    b2[(size_t)d*np + i]  = s.get_x2()[d][i];
+    nrm[(size_t)d*np + i] = s.get_norm()[d][i];
+  }
+  return 0;
+}
+
+// panels -> points. Gradients are produced iff the target kind has velgrad storage
+// (src/Influence.h:652,875), independent of restype.
+int o3d_ref_pan_on_pts(int nn, const float* nodes, int np, const uint32_t* idx, const float* val,
+                       int targ_kind, int nt, const float* tx, const float* ty, const float* tz,
+                       const float* tr, float* tu, float* tug) {
+  Mute m(g_mute);
+  Surfaces<float> src = make_surfaces(nn, nodes, np, idx, val, active);
+  Points<float> targ = make_targets(targ_kind, nt, tx, ty, tz, tr);
+  load_results(targ, nt, tu, tug);
+  ExecEnv env(true, true, direct, cpu_x86);
+  panels_affect_points<float, double>(src, targ, ResultsType(velonly), env);
+  store_results(targ, nt, tu, tug);
+  return 0;
+}
+
+// particles -> panel centres (BEM right-hand side). pu (3 x np SoA) is DECREMENTED
+// (src/Influence.h:1210-1212).
+int o3d_ref_pts_on_pan(int ns, const float* sx, const float* sy, const float* sz, const float* sr,
+                       const float* ss3, int nn, const float* nodes, int np, const uint32_t* idx,
+                       const float* val, float* pu) {
+  Mute m(g_mute);
+  Points<float> src = make_points(ns, sx, sy, sz, ss3, sr, active, lagrangian);
+  Surfaces<float> targ = make_surfaces(nn, nodes, np, idx, val, active);
+  auto& u = targ.get_vel();
+  for (int d = 0; d < 3; ++d) std::memcpy(u[d].data(), pu + (size_t)d*np, sizeof(float)*np);
+  ExecEnv env(true, true, direct, cpu_x86);
+  points_affect_panels<float, double>(src, targ, ResultsType(velonly), env);
+  for (int d = 0; d < 3; ++d) std::memcpy(pu + (size_t)d*np, u[d].data(), sizeof(float)*np);
+  return 0;
+}
+
+// panels -> panels velocity via the reference's colocation-point trick (src/Influence.h:1224-1245).
+int o3d_ref_pan_on_pan(int nn, const float* nodes, int np, const uint32_t* idx, const float* val,
+                       int tnn, const float* tnodes, int tnp, const uint32_t* tidx, const float* tval,
+                       float* pu) {
+  Mute m(g_mute);
+  Surfaces<float> src = make_surfaces(nn, nodes, np, idx, val, active);
+  Surfaces<float> targ = make_surfaces(tnn, tnodes, tnp, tidx, tval, reactive);
+  ExecEnv env(true, true, direct, cpu_x86);
+  panels_affect_panels<float, double>(src, targ, ResultsType(velonly), env);
+  auto& u = targ.get_vel();
+  for (int d = 0; d < 3; ++d) std::memcpy(pu + (size_t)d*tnp, u[d].data(), sizeof(float)*tnp);
+  return 0;
+}
+
+// BEM influence block of a reactive surface on itself (self != 0) or on a second surface.
+// Returns the number of floats written to coeffs (column-major, (nunk*ntarg) x (nunk*nsrc)),
+// or the required size when coeffs == NULL.
+long o3d_ref_pan_on_pan_coeff(int nn, const float* nodes, int np, const uint32_t* idx, const float* bc,
+                              int self, int tnn, const float* tnodes, int tnp, const uint32_t* tidx,
+                              const float* tbc, float* coeffs) {
+  Mute m(g_mute);
+  Surfaces<float> src = make_surfaces(nn, nodes, np, idx, bc, reactive);
+  if (self) {
+    Vector<float> c = panels_on_panels_coeff<float>(src, src);
+    if (coeffs) std::memcpy(coeffs, c.data(), sizeof(float)*c.size());
+    return (long)c.size();
+  }
+  Surfaces<float> targ = make_surfaces(tnn, tnodes, tnp, tidx, tbc, reactive);
+  Vector<float> c = panels_on_panels_coeff<float>(src, targ);
+  if (coeffs) std::memcpy(coeffs, c.data(), sizeof(float)*c.size());
+  return (long)c.size();
+}
+
+// Single-interaction known-answer hooks straight into src/Kernels.h (double accumulators).
+void o3d_ref_kernel_0v_0bg(const float* s7 /*x y z r wx wy wz*/, const float* t4 /*x y z r*/, double* out12) {
+  for (int i = 0; i < 12; ++i) out12[i] = 0.0;
+  kernel_0v_0bg<float, double>(s7[0], s7[1], s7[2], s7[3], s7[4], s7[5], s7[6], t4[0], t4[1], t4[2], t4[3],
+      out12+0, out12+1, out12+2, out12+3, out12+4, out12+5, out12+6, out12+7, out12+8, out12+9, out12+10, out12+11);
+}
+int o3d_ref_rkernel_2vs_0p(const float* tri9 /*x0 y0 z0 x1 ..*/, const float* str4, const float* t3,
+                           float sa, double* out3) {
+  out3[0] = out3[1] = out3[2] = 0.0;
+  return rkernel_2vs_0p<float, double>(tri9[0], tri9[1], tri9[2], tri9[3], tri9[4], tri9[5], tri9[6], tri9[7],
+      tri9[8], str4[0], str4[1], str4[2], str4[3], t3[0], t3[1], t3[2], sa, 0, RECURSIVE_LEVELS,
+      out3, out3+1, out3+2);
+}
+int o3d_ref_rkernel_2vs_0pg(const float* tri9, const float* str4, const float* t3, float sa, double* out12) {
+  for (int i = 0; i < 12; ++i) out12[i] = 0.0;
+  return rkernel_2vs_0pg<float, double>(tri9[0], tri9[1], tri9[2], tri9[3], tri9[4], tri9[5], tri9[6], tri9[7],
+      tri9[8], str4[0], str4[1], str4[2], str4[3], t3[0], t3[1], t3[2], sa, 0, RECURSIVE_LEVELS,
+      out12+0, out12+1, out12+2, out12+3, out12+4, out12+5, out12+6, out12+7, out12+8, out12+9, out12+10, out12+11);
+}
+
+}  // extern "C"
