@@ -1,0 +1,401 @@
+// biot_pp.cuh - particles -> points direct Biot-Savart sums for sm_100a (B200).
+//
+// Replaces the loop nests of points_affect_points<S,A> (reference src/Influence.h:278-309,
+// :351-365, :443-474, :518-533) and the pairwise kernels they call (src/Kernels.h:50-69 kernel_0v_0b,
+// :94-112 kernel_0v_0p, :155-193 kernel_0v_0bg, :253-290 kernel_0v_0pg) with the Winckelmans-Leonard
+// core (src/CoreFunc.h:245-288). Written from the formulas, not from those loops:
+//
+//   d = t - s,  r2 = sr^2 + tr^2,  d2 = |d|^2 + r2,  top = |d|^2 + 2.5 r2 = d2 + 1.5 r2
+//   dn5 = d2^(-5/2) = rs^5 with rs = MUFU.RSQ(d2)          (reference: 1/(d2*d2*sqrt(d2)))
+//   r3  = top * dn5,   bbb = dn5 * (2 - 5 top / d2) = dn5 * (2 - 5 top rs^2)
+//   c   = (dz wy - dy wz, dx wz - dz wx, dy wx - dx wy)
+//   u  += r3 c ;   G[3j+i] += d_j (bbb c_i)  (+/- w_k r3 on the six off-diagonals)
+//
+// Design:
+//   * each thread owns T targets in registers; every source record is read once from shared memory
+//     (one broadcast LDS.128 pair per warp) and applied to all T targets: 40 FP32-pipe instructions
+//     + 1 MUFU.RSQ per interaction for velocity+gradient, 21 + 1 for velocity only;
+//   * the antisymmetric +/- w_k r3 part of the gradient is accumulated once as A = sum w r3 (3 FMA)
+//     and applied in the epilogue instead of 6 FMA per interaction;
+//   * source tiles (512 records = 16 KB, contiguous) arrive by cp.async.bulk (TMA, SASS UBLKCP)
+//     into a 2-deep mbarrier ring - no thread spends registers or issue slots on the copy;
+//   * sums are FP32 FMA chains inside one tile, promoted to FP64 once per tile (B200 keeps a full FP64
+//     pipe; 12 DADD per 512 interactions), mirroring the reference's float-kernel/double-accumulator
+//     scheme (src/Simulation.h:41-47) to ~1e-7 relative;
+//   * outputs are read-modify-write, un-normalised: tu[i] = float(double(tu[i]) + sum), exactly the
+//     reference's "tu[0][i] += accumu" (src/Influence.h:462-473).
+#pragma once
+#include "o3d_common.cuh"
+
+namespace o3d {
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <bool GRAD> struct PPAcc { static constexpr int N = GRAD ? 15 : 3; };
+
+// One source record (a = x y z sr^2, b = wx wy wz -) on one target. acc layout:
+//   [0..2] u v w | [3..11] G[3j+i] = sum d_j * bbb*c_i | [12..14] A = sum w * r3
+template <bool GRAD>
+__device__ __forceinline__ void pp_interact(const float4 a, const float4 b, const float tx, const float ty,
+                                            const float tz, const float tr2, float (&acc)[PPAcc<GRAD>::N]) {
+  const float dx = tx - a.x, dy = ty - a.y, dz = tz - a.z;
+  const float r2 = a.w + tr2;
+  const float d2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, r2)));
+  const float top = fmaf(1.5f, r2, d2);
+  const float rs = rsqrt_approx(d2);
+  const float rs2 = rs * rs;
+  const float rs4 = rs2 * rs2;
+  const float dn5 = rs4 * rs;
+  const float r3 = top * dn5;
+  float cx = fmaf(dz, b.y, -(dy * b.z));
+  float cy = fmaf(dx, b.z, -(dz * b.x));
+  float cz = fmaf(dy, b.x, -(dx * b.y));
+  acc[0] = fmaf(r3, cx, acc[0]);
+  acc[1] = fmaf(r3, cy, acc[1]);
+  acc[2] = fmaf(r3, cz, acc[2]);
+  if constexpr (GRAD) {
+    const float bbb = dn5 * fmaf(-5.0f, top * rs2, 2.0f);
+    cx *= bbb; cy *= bbb; cz *= bbb;
+    acc[3]  = fmaf(dx, cx, acc[3]);
+    acc[4]  = fmaf(dx, cy, acc[4]);
+    acc[5]  = fmaf(dx, cz, acc[5]);
+    acc[6]  = fmaf(dy, cx, acc[6]);
+    acc[7]  = fmaf(dy, cy, acc[7]);
+    acc[8]  = fmaf(dy, cz, acc[8]);
+    acc[9]  = fmaf(dz, cx, acc[9]);
+    acc[10] = fmaf(dz, cy, acc[10]);
+    acc[11] = fmaf(dz, cz, acc[11]);
+    acc[12] = fmaf(b.x, r3, acc[12]);
+    acc[13] = fmaf(b.y, r3, acc[13]);
+    acc[14] = fmaf(b.z, r3, acc[14]);
+  }
+}
+
+// Fold the per-tile FP32 partials into the 3 (or 12) FP64 running sums and clear them.
+template <bool GRAD>
+__device__ __forceinline__ void pp_promote(float (&acc)[PPAcc<GRAD>::N], double (&sum)[GRAD ? 12 : 3]) {
+  sum[0] += (double)acc[0]; sum[1] += (double)acc[1]; sum[2] += (double)acc[2];
+  if constexpr (GRAD) {
+    const float ax = acc[12], ay = acc[13], az = acc[14];
+    sum[3]  += (double)acc[3];            // ux
+    sum[4]  += (double)(acc[4] + az);     // vx = sum dx*cy + wz*r3
+    sum[5]  += (double)(acc[5] - ay);     // wx = sum dx*cz - wy*r3
+    sum[6]  += (double)(acc[6] - az);     // uy
+    sum[7]  += (double)acc[7];            // vy
+    sum[8]  += (double)(acc[8] + ax);     // wy
+    sum[9]  += (double)(acc[9] + ay);     // uz
+    sum[10] += (double)(acc[10] - ax);    // vz
+    sum[11] += (double)acc[11];           // wz
+  }
+#pragma unroll
+  for (int k = 0; k < PPAcc<GRAD>::N; ++k) acc[k] = 0.0f;
+}
+
+struct PPArgs {
+  const float4* src;      // packed source stream, 2 float4 per source, padded to whole tiles
+  int tile_begin;         // first tile of this launch's source range (per blockIdx.y slice: see split)
+  int ntiles;             // tiles in the whole stream
+  int nsplit;             // source slices = gridDim.y
+  int64_t nt;             // targets
+  const float* tx; const float* ty; const float* tz;
+  const float* tr;        // nullptr => singular targets (tr = 0)
+  float* tu; float* tv; float* tw;   // velocity, read-modify-write
+  float* tug;             // 9 rows of stride tug_stride, or nullptr
+  int64_t tug_stride;
+  double* partial;        // nsplit > 1: [12 or 3][nt] FP64 workspace receiving atomic partial sums
+  float sign;             // +1, or -1 for the points->panels convention
+};
+
+// Scalar-FFMA kernel: T register-blocked targets per thread.
+template <int T, bool GRAD, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pp_kernel(const PPArgs p) {
+  constexpr int NA = PPAcc<GRAD>::N;
+  constexpr int NS = GRAD ? 12 : 3;
+  __shared__ alignas(128) float4 tile[2][kTile * 2];
+  __shared__ alignas(8) uint64_t full[2];
+
+  // this CTA's slice of the source stream
+  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int k0 = blockIdx.y * per;
+  const int k1 = min(p.ntiles, k0 + per);
+  const int nk = k1 - k0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (s < nk) {
+        mbar_expect_tx(&full[s], kTileBytes);
+        bulk_g2s(tile[s], p.src + (size_t)(k0 + s) * (kTile * 2), kTileBytes, &full[s]);
+      }
+  }
+
+  float tx[T], ty[T], tz[T], tr2[T];
+  const int64_t base = (int64_t)blockIdx.x * (BLOCK * T) + threadIdx.x;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
+    tx[t] = p.tx[i]; ty[t] = p.ty[i]; tz[t] = p.tz[i];
+    const float r = p.tr ? p.tr[i] : 0.0f;
+    tr2[t] = r * r;
+  }
+
+  float acc[T][NA];
+  double sum[T][NS];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[t][k] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
+  }
+
+  for (int k = 0; k < nk; ++k) {
+    const int buf = k & 1;
+    mbar_wait(&full[buf], (k >> 1) & 1);
+    const float4* __restrict__ s = tile[buf];
+#pragma unroll 4
+    for (int j = 0; j < kTile; ++j) {
+      const float4 a = s[2 * j], b = s[2 * j + 1];
+#pragma unroll
+      for (int t = 0; t < T; ++t) pp_interact<GRAD>(a, b, tx[t], ty[t], tz[t], tr2[t], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) pp_promote<GRAD>(acc[t], sum[t]);
+    __syncthreads();  // every warp is done with tile[buf]; safe to refill
+    if (threadIdx.x == 0 && k + 2 < nk) {
+      mbar_expect_tx(&full[buf], kTileBytes);
+      bulk_g2s(tile[buf], p.src + (size_t)(k0 + k + 2) * (kTile * 2), kTileBytes, &full[buf]);
+    }
+  }
+
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int64_t i = base + (int64_t)t * BLOCK;
+    if (i >= p.nt) continue;
+    if (p.nsplit > 1) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) atomicAdd(p.partial + (size_t)k * p.nt + i, sum[t][k]);
+    } else {
+      const double sg = (double)p.sign;
+      p.tu[i] = (float)((double)p.tu[i] + sg * sum[t][0]);
+      p.tv[i] = (float)((double)p.tv[i] + sg * sum[t][1]);
+      p.tw[i] = (float)((double)p.tw[i] + sg * sum[t][2]);
+      if constexpr (GRAD) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          float* g = p.tug + (size_t)k * p.tug_stride + i;
+          *g = (float)((double)*g + sum[t][3 + k]);
+        }
+      }
+    }
+  }
+}
+
+// nsplit > 1 epilogue: out[i] = float(double(out[i]) + sign * partial[i]), then clear the workspace.
+__global__ void pp_finish_kernel(int nrows, int64_t nt, double* partial, float* tu, float* tv, float* tw, float* tug,
+                                 int64_t tug_stride, float sign) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  for (int k = 0; k < nrows; ++k) {
+    double* w = partial + (size_t)k * nt + i;
+    float* o = k == 0 ? tu + i : k == 1 ? tv + i : k == 2 ? tw + i : tug + (size_t)(k - 3) * tug_stride + i;
+    *o = (float)((double)*o + (double)sign * *w);
+    *w = 0.0;
+  }
+}
+
+// SoA (the reference's Points layout) -> packed record stream, with zero-strength padding records.
+__global__ void pp_pack_kernel(int64_t ns, int64_t ns_pad, const float* sx, const float* sy, const float* sz,
+                               const float* sr, const float* wx, const float* wy, const float* wz, float4* out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= ns_pad) return;
+  float4 a = make_float4(0.f, 0.f, 0.f, 1.0f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < ns) {
+    const float r = sr ? sr[j] : 0.0f;
+    a = make_float4(sx[j], sy[j], sz[j], r * r);
+    b = make_float4(wx[j], wy[j], wz[j], 0.f);
+  }
+  out[2 * j] = a;
+  out[2 * j + 1] = b;
+}
+
+// =============================================================================================
+// Packed-FP32 variant (sm_100 FFMA2 / FMUL2 / FADD2: fma.rn.f32x2): each instruction carries TWO
+// sources against one target. Tile layout is pair-interleaved (built by pp_pack2_kernel):
+//     q[4p+0] = { -x0, -x1, -y0, -y1 }   q[4p+1] = { -z0, -z1, r0^2, r1^2 }
+//     q[4p+2] = { wx0, wx1, wy0, wy1 }   q[4p+3] = { wz0, wz1, 0, 0 }
+// Positions are stored negated so d = t + (-s) is one FADD2 (the packed ops have no negate modifier
+// in PTX). Kept as a measured alternative - see DESIGN.md section 5 for the verdict.
+// =============================================================================================
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+template <bool GRAD>
+__device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
+                                             const float2 tx, const float2 ty, const float2 tz, const float2 tr2,
+                                             float2 (&acc)[PPAcc<GRAD>::N]) {
+  const float2 dx = __fadd2_rn(tx, f2(q0.x, q0.y));
+  const float2 dy = __fadd2_rn(ty, f2(q0.z, q0.w));
+  const float2 dz = __fadd2_rn(tz, f2(q1.x, q1.y));
+  const float2 r2 = __fadd2_rn(tr2, f2(q1.z, q1.w));
+  const float2 wx = f2(q2.x, q2.y), wy = f2(q2.z, q2.w), wz = f2(q3.x, q3.y);
+  const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, r2)));
+  const float2 top = __ffma2_rn(f2(1.5f, 1.5f), r2, d2);
+  const float2 rs = f2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+  const float2 rs2 = __fmul2_rn(rs, rs);
+  const float2 rs4 = __fmul2_rn(rs2, rs2);
+  const float2 dn5 = __fmul2_rn(rs4, rs);
+  const float2 r3 = __fmul2_rn(top, dn5);
+  // negated cross product n = -(c): n_x = dy wz - dz wy ... using only multiplies and FMAs with a
+  // negated first product folded into the sign of the accumulation (u -= r3 n  <=>  u += (-r3) n)
+  const float2 ndx = neg2(dx), ndy = neg2(dy), ndz = neg2(dz);
+  float2 cx = __ffma2_rn(dz, wy, __fmul2_rn(ndy, wz));
+  float2 cy = __ffma2_rn(dx, wz, __fmul2_rn(ndz, wx));
+  float2 cz = __ffma2_rn(dy, wx, __fmul2_rn(ndx, wy));
+  acc[0] = __ffma2_rn(r3, cx, acc[0]);
+  acc[1] = __ffma2_rn(r3, cy, acc[1]);
+  acc[2] = __ffma2_rn(r3, cz, acc[2]);
+  if constexpr (GRAD) {
+    const float2 bbb = __fmul2_rn(dn5, __ffma2_rn(f2(-5.0f, -5.0f), __fmul2_rn(top, rs2), f2(2.0f, 2.0f)));
+    cx = __fmul2_rn(cx, bbb); cy = __fmul2_rn(cy, bbb); cz = __fmul2_rn(cz, bbb);
+    acc[3]  = __ffma2_rn(dx, cx, acc[3]);
+    acc[4]  = __ffma2_rn(dx, cy, acc[4]);
+    acc[5]  = __ffma2_rn(dx, cz, acc[5]);
+    acc[6]  = __ffma2_rn(dy, cx, acc[6]);
+    acc[7]  = __ffma2_rn(dy, cy, acc[7]);
+    acc[8]  = __ffma2_rn(dy, cz, acc[8]);
+    acc[9]  = __ffma2_rn(dz, cx, acc[9]);
+    acc[10] = __ffma2_rn(dz, cy, acc[10]);
+    acc[11] = __ffma2_rn(dz, cz, acc[11]);
+    acc[12] = __ffma2_rn(wx, r3, acc[12]);
+    acc[13] = __ffma2_rn(wy, r3, acc[13]);
+    acc[14] = __ffma2_rn(wz, r3, acc[14]);
+  }
+}
+
+template <int T, bool GRAD, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pp2_kernel(const PPArgs p) {
+  constexpr int NA = PPAcc<GRAD>::N;
+  constexpr int NS = GRAD ? 12 : 3;
+  __shared__ alignas(128) float4 tile[2][kTile * 2];
+  __shared__ alignas(8) uint64_t full[2];
+
+  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int k0 = blockIdx.y * per;
+  const int k1 = min(p.ntiles, k0 + per);
+  const int nk = k1 - k0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (s < nk) {
+        mbar_expect_tx(&full[s], kTileBytes);
+        bulk_g2s(tile[s], p.src + (size_t)(k0 + s) * (kTile * 2), kTileBytes, &full[s]);
+      }
+  }
+
+  float2 tx[T], ty[T], tz[T], tr2[T];
+  const int64_t base = (int64_t)blockIdx.x * (BLOCK * T) + threadIdx.x;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
+    tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
+    const float r = p.tr ? p.tr[i] : 0.0f;
+    tr2[t] = f2(r * r, r * r);
+  }
+
+  float2 acc[T][NA];
+  double sum[T][NS];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[t][k] = f2(0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
+  }
+
+  for (int k = 0; k < nk; ++k) {
+    const int buf = k & 1;
+    mbar_wait(&full[buf], (k >> 1) & 1);
+    const float4* __restrict__ s = tile[buf];
+#pragma unroll 2
+    for (int j = 0; j < kTile / 2; ++j) {
+      const float4 q0 = s[4 * j], q1 = s[4 * j + 1], q2 = s[4 * j + 2], q3 = s[4 * j + 3];
+#pragma unroll
+      for (int t = 0; t < T; ++t) pp_interact2<GRAD>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tr2[t], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      float h[NA];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) { h[q] = acc[t][q].x + acc[t][q].y; acc[t][q] = f2(0.f, 0.f); }
+      pp_promote<GRAD>(h, sum[t]);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && k + 2 < nk) {
+      mbar_expect_tx(&full[buf], kTileBytes);
+      bulk_g2s(tile[buf], p.src + (size_t)(k0 + k + 2) * (kTile * 2), kTileBytes, &full[buf]);
+    }
+  }
+
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int64_t i = base + (int64_t)t * BLOCK;
+    if (i >= p.nt) continue;
+    if (p.nsplit > 1) {
+#pragma unroll
+      for (int k = 0; k < NS; ++k) atomicAdd(p.partial + (size_t)k * p.nt + i, sum[t][k]);
+    } else {
+      const double sg = (double)p.sign;
+      p.tu[i] = (float)((double)p.tu[i] + sg * sum[t][0]);
+      p.tv[i] = (float)((double)p.tv[i] + sg * sum[t][1]);
+      p.tw[i] = (float)((double)p.tw[i] + sg * sum[t][2]);
+      if constexpr (GRAD) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          float* g = p.tug + (size_t)k * p.tug_stride + i;
+          *g = (float)((double)*g + sum[t][3 + k]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void pp_pack2_kernel(int64_t ns, int64_t ns_pad, const float* sx, const float* sy, const float* sz,
+                                const float* sr, const float* wx, const float* wy, const float* wz, float4* out) {
+  const int64_t pr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+  if (2 * pr >= ns_pad) return;
+  float x[2], y[2], z[2], r2[2], a[2], b[2], c[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t j = 2 * pr + h;
+    x[h] = y[h] = z[h] = 0.f; r2[h] = 1.f; a[h] = b[h] = c[h] = 0.f;
+    if (j < ns) {
+      const float r = sr ? sr[j] : 0.0f;
+      x[h] = -sx[j]; y[h] = -sy[j]; z[h] = -sz[j]; r2[h] = r * r;
+      a[h] = wx[j]; b[h] = wy[j]; c[h] = wz[j];
+    }
+  }
+  out[4 * pr + 0] = make_float4(x[0], x[1], y[0], y[1]);
+  out[4 * pr + 1] = make_float4(z[0], z[1], r2[0], r2[1]);
+  out[4 * pr + 2] = make_float4(a[0], a[1], b[0], b[1]);
+  out[4 * pr + 3] = make_float4(c[0], c[1], 0.f, 0.f);
+}
+
+}  // namespace o3d

@@ -1,0 +1,115 @@
+// kbench.cu - times the points->points kernel variants against each other on one GPU and checks
+// them against a double-precision host loop on a few targets. Development harness only (the product
+// entry points are in ../capi.cu). Build: see ../Makefile (target kbench).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+#include "../biot_pp.cuh"
+
+using namespace o3d;
+#define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
+
+static void host_ref(int ns, const float* sx, const float* sy, const float* sz, const float* sr, const float* wx,
+                     const float* wy, const float* wz, float tx, float ty, float tz, float tr, double* o) {
+  for (int k = 0; k < 12; ++k) o[k] = 0;
+  for (int j = 0; j < ns; ++j) {
+    double dx = (double)tx - sx[j], dy = (double)ty - sy[j], dz = (double)tz - sz[j];
+    double r2 = (double)sr[j] * sr[j] + (double)tr * tr, ds = dx * dx + dy * dy + dz * dz, d2 = ds + r2;
+    double top = ds + 2.5 * r2, dn5 = 1.0 / (d2 * d2 * std::sqrt(d2)), r3 = top * dn5, bbb = 2 * dn5 - 5 * top * dn5 / d2;
+    double cx = dz * wy[j] - dy * wz[j], cy = dx * wz[j] - dz * wx[j], cz = dy * wx[j] - dx * wy[j];
+    o[0] += r3 * cx; o[1] += r3 * cy; o[2] += r3 * cz;
+    cx *= bbb; cy *= bbb; cz *= bbb;
+    o[3] += dx * cx; o[4] += dx * cy + wz[j] * r3; o[5] += dx * cz - wy[j] * r3;
+    o[6] += dy * cx - wz[j] * r3; o[7] += dy * cy; o[8] += dy * cz + wx[j] * r3;
+    o[9] += dz * cx + wy[j] * r3; o[10] += dz * cy - wx[j] * r3; o[11] += dz * cz;
+  }
+}
+
+int main(int argc, char** argv) {
+  const int n = argc > 1 ? atoi(argv[1]) : 262144;
+  const int reps = argc > 2 ? atoi(argv[2]) : 3;
+  cudaDeviceProp prop; CHECK(cudaGetDeviceProperties(&prop, 0));
+  printf("device %s SMs=%d  N=%d\n", prop.name, prop.multiProcessorCount, n);
+  std::mt19937_64 gen(20240517 + n);
+  std::uniform_real_distribution<float> U(-0.5f, 0.5f);
+  std::vector<float> h[7];
+  for (int c = 0; c < 7; ++c) h[c].resize(n);
+  for (int i = 0; i < n; ++i) { h[0][i] = U(gen); h[1][i] = U(gen); h[2][i] = U(gen); }
+  for (int i = 0; i < n; ++i) { h[4][i] = U(gen) / n; h[5][i] = U(gen) / n; h[6][i] = U(gen) / n; h[3][i] = 1.5f * std::pow((float)n, -1.f / 3.f); }
+  float* d[7];
+  for (int c = 0; c < 7; ++c) { CHECK(cudaMalloc(&d[c], n * 4)); CHECK(cudaMemcpy(d[c], h[c].data(), n * 4, cudaMemcpyHostToDevice)); }
+  const int64_t npad = padded_sources(n);
+  float4 *pk, *pk2;
+  CHECK(cudaMalloc(&pk, npad * 32)); CHECK(cudaMalloc(&pk2, npad * 32));
+  pp_pack_kernel<<<(npad + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk);
+  pp_pack2_kernel<<<(npad / 2 + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk2);
+  float* out; CHECK(cudaMalloc(&out, (size_t)n * 12 * 4));
+  double* partial; CHECK(cudaMalloc(&partial, (size_t)n * 12 * 8)); CHECK(cudaMemset(partial, 0, (size_t)n * 12 * 8));
+  CHECK(cudaDeviceSynchronize());
+
+  // host reference on 8 targets
+  const int nchk = 8;
+  std::vector<double> ref(nchk * 12);
+  double umax = 0, gmax = 0;
+  for (int c = 0; c < nchk; ++c) {
+    const int i = (int)((long long)c * n / nchk);
+    host_ref(n, h[0].data(), h[1].data(), h[2].data(), h[3].data(), h[4].data(), h[5].data(), h[6].data(), h[0][i], h[1][i], h[2][i], h[3][i], &ref[c * 12]);
+    for (int k = 0; k < 3; ++k) umax = std::fmax(umax, std::fabs(ref[c * 12 + k]));
+    for (int k = 3; k < 12; ++k) gmax = std::fmax(gmax, std::fabs(ref[c * 12 + k]));
+  }
+
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto run = [&](const char* name, auto kern, int T, int BLOCK, bool grad, const float4* src, int nsplit) {
+    PPArgs a{};
+    a.src = src; a.ntiles = (int)(npad / kTile); a.nsplit = nsplit; a.nt = n;
+    a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
+    a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = out + 3 * (size_t)n; a.tug_stride = n;
+    a.partial = partial; a.sign = 1.0f;
+    dim3 grid((n + BLOCK * T - 1) / (BLOCK * T), nsplit);
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; ++r) {
+      CHECK(cudaMemset(out, 0, (size_t)n * 12 * 4));
+      cudaEventRecord(e0);
+      kern<<<grid, BLOCK>>>(a);
+      if (nsplit > 1) pp_finish_kernel<<<(n + 255) / 256, 256>>>(grad ? 12 : 3, n, partial, a.tu, a.tv, a.tw, a.tug, n, 1.0f);
+      cudaEventRecord(e1);
+      CHECK(cudaDeviceSynchronize());
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (r > 0 && ms < best) best = ms;
+    }
+    std::vector<float> o((size_t)n * 12);
+    CHECK(cudaMemcpy(o.data(), out, (size_t)n * 12 * 4, cudaMemcpyDeviceToHost));
+    double eu = 0, eg = 0;
+    for (int c = 0; c < nchk; ++c) {
+      const int i = (int)((long long)c * n / nchk);
+      for (int k = 0; k < 3; ++k) eu = std::fmax(eu, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
+      if (grad) for (int k = 3; k < 12; ++k) eg = std::fmax(eg, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
+    }
+    const double ips = (double)n * n / (best * 1e-3);
+    printf("%-22s T=%d B=%3d split=%2d grid=%6d  %8.3f ms  %.3e int/s  %6.2f TFLOP/s@%d  err u %.2e g %.2e\n", name, T, BLOCK, nsplit,
+           grid.x * grid.y, best, ips, ips * (grad ? 70 : 33) * 1e-12, grad ? 70 : 33, eu / umax, eg / gmax);
+  };
+#define RUN_S(T, B, G, SPLIT) run("scalar" #G, pp_kernel<T, G, B>, T, B, G, pk, SPLIT)
+#define RUN_P(T, B, G, SPLIT) run("packed" #G, pp2_kernel<T, G, B>, T, B, G, pk2, SPLIT)
+  RUN_S(1, 256, true, 1);
+  RUN_S(2, 256, true, 1);
+  RUN_S(2, 128, true, 1);
+  RUN_S(4, 256, true, 1);
+  RUN_S(4, 128, true, 1);
+  RUN_S(3, 128, true, 1);
+  RUN_S(3, 256, true, 1);
+  RUN_P(1, 256, true, 1);
+  RUN_P(1, 128, true, 1);
+  RUN_P(2, 256, true, 1);
+  RUN_P(2, 128, true, 1);
+  RUN_P(3, 128, true, 1);
+  RUN_S(2, 256, true, 4);
+  RUN_P(2, 128, true, 4);
+  RUN_S(4, 256, false, 1);
+  RUN_S(8, 128, false, 1);
+  RUN_P(2, 256, false, 1);
+  RUN_P(4, 128, false, 1);
+  return 0;
+}
