@@ -1,0 +1,144 @@
+/* o3d_cuda.h - C ABI of the B200 (sm_100a) Biot-Savart back end for Omega3D.
+ *
+ * This is the drop-in boundary: the entry points below are what the reference's `gpu_cuda` arm
+ * (accel_t::gpu_cuda, /root/reference/src/ExecEnv.h:34-39 - declared, never dispatched) binds. The
+ * precedent for the shape of the interface is the reference's own external-solver hook
+ * `external_vel_solver_f_` (src/Influence.h:34-47,97-103): SoA float arrays by pointer, counts by value,
+ * results accumulated into caller-owned arrays. INTEGRATION.md shows the reference-side patch.
+ *
+ * Conventions shared by every entry point (they are the reference's):
+ *   - all arrays are float32 SoA in the layout of the reference's containers (Points: x[3], s[3], r -
+ *     src/Points.h; Surfaces: node x[3], idx[3*np], area, ts[3] - src/Surfaces.h);
+ *   - results ACCUMULATE into the caller's arrays (`tu[d][i] += sum`, src/Influence.h:296-307,462-473;
+ *     `-=` for particles->panels, :1210-1212), un-normalised (no 1/4pi, no freestream: the caller's
+ *     finalize_vels does that, src/Points.h:265-277);
+ *   - self interactions are NOT skipped (src/Kernels.h:184-192); sources may alias targets;
+ *   - pairwise arithmetic in float, per-target sums carried to double before the final `+=`
+ *     (the reference's non-Vc scheme, src/Simulation.h:41-47);
+ *   - every function returns 0 on success or an O3D_ERR_* code; nothing aborts or throws across
+ *     the boundary (the reference asserts; the integration arm asserts on non-zero);
+ *   - a context is single-caller (the reference calls the influence routines from one thread at a time,
+ *     src/Simulation.cpp:776,802); host pointers are never retained past the return;
+ *   - `flops_out` (may be NULL) receives the reference's own flop estimate for the call so the caller
+ *     can print its usual "[%.4f] seconds at %.3f GFlop/s" line (src/Influence.h:310,366,475,534).
+ *
+ * There is no CPU fallback: without a usable sm_100 device o3d_cuda_create fails with O3D_ERR_NODEVICE.
+ */
+#ifndef O3D_CUDA_H
+#define O3D_CUDA_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define O3D_CUDA_ABI_VERSION 1
+
+enum {
+  O3D_OK = 0,
+  O3D_ERR_INVALID = 1,     /* bad argument (NULL where an array is required, negative count, ...) */
+  O3D_ERR_CUDA = 2,        /* a CUDA runtime call failed; see o3d_cuda_last_error */
+  O3D_ERR_NOMEM = 3,       /* device or pinned-host allocation failed */
+  O3D_ERR_NODEVICE = 4,    /* no CUDA device / wrong architecture */
+  O3D_ERR_UNSUPPORTED = 5  /* combination the reference itself asserts on (src/Influence.h:368-370) */
+};
+
+typedef struct o3d_ctx o3d_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int o3d_cuda_abi_version(void);
+int o3d_cuda_device_count(void);
+/* One context drives `ndev` GPUs of this process (devices == NULL: 0..ndev-1). With ndev > 1 the host
+ * entry points partition the TARGETS across the devices and replicate the sources to each
+ * (SURVEY.md section 8e). One-process-per-GPU jobs create a 1-device context per rank and use the *_dev
+ * entry points with an NCCL all-gather of the packed source records in between. */
+int o3d_cuda_create(o3d_ctx** ctx, int ndev, const int* devices);
+void o3d_cuda_destroy(o3d_ctx* ctx);
+const char* o3d_cuda_last_error(const o3d_ctx* ctx);
+int o3d_cuda_num_devices(const o3d_ctx* ctx);
+/* SM count, SM clock (kHz) and FP32 FMA peak (flop/s at that clock: SMs x 128 x 2 x f) of device k. */
+int o3d_cuda_device_props(const o3d_ctx* ctx, int k, int* sm_count, int* clock_khz, double* fp32_peak);
+/* Device-side time of the LAST host entry point on this context, max over its devices, from CUDA events
+ * on the launching streams: influence kernels only / host->device / device->host, in milliseconds;
+ * `launches` = number of kernels this library launched for that call. Any pointer may be NULL. */
+int o3d_cuda_last_timing(const o3d_ctx* ctx, double* kernel_ms, double* h2d_ms, double* d2h_ms, int* launches);
+
+/* ---- host-pointer entry points: one per reference influence routine -------------------------------- */
+
+/* particles -> points. Replaces the CPU block of points_affect_points<S,A> (src/Influence.h:202-551).
+ *   sources: position sx,sy,sz, radius sr, strength ssx,ssy,ssz                       (ns each)
+ *   targets: position tx,ty,tz; tr = radius, or NULL for singular (inert) targets     (nt each)
+ *   tu,tv,tw: velocity, += ; tug: 9 arrays, slot 3*j+i = d u_i / d x_j, += ; NULL => velocity only
+ * Kernel selected as the reference does (src/Influence.h:213-533):
+ *   tr && tug -> kernel_0v_0bg   tr && !tug -> kernel_0v_0b   !tr && tug -> kernel_0v_0pg   else kernel_0v_0p */
+int o3d_cuda_pts_on_pts(o3d_ctx* ctx, int64_t ns, const float* sx, const float* sy, const float* sz,
+                        const float* sr, const float* ssx, const float* ssy, const float* ssz, int64_t nt,
+                        const float* tx, const float* ty, const float* tz, const float* tr, float* tu, float* tv,
+                        float* tw, float* const* tug, double* flops_out);
+
+/* triangular panels -> points. Replaces panels_affect_points<S,A> (src/Influence.h:557-1099): per
+ * (target, panel) the recursive rkernel_2vs_0p / rkernel_2vs_0pg (src/Kernels.h:1028-1211), maxlev 3.
+ *   nodes: nx,ny,nz (nn each); idx: 3 node indices per panel; ts: total vortex strength tsx,tsy,tsz (np each);
+ *   area (np); sss: source-sheet strength per panel or NULL (src/Influence.h:577-579)
+ *   tug != NULL selects the gradient kernel (the reference keys this on the target having gradient
+ *   storage, not on the results type: src/Influence.h:652,875). Target radius never enters (:873,893). */
+int o3d_cuda_pan_on_pts(o3d_ctx* ctx, int64_t nn, const float* nx, const float* ny, const float* nz, int64_t np,
+                        const uint32_t* idx, const float* tsx, const float* tsy, const float* tsz,
+                        const float* area, const float* sss, int64_t nt, const float* tx, const float* ty,
+                        const float* tz, float* tu, float* tv, float* tw, float* const* tug, double* flops_out);
+
+/* particles -> panel centres (the BEM right-hand side). Replaces points_affect_panels<S,A>
+ * (src/Influence.h:1107-1221): the same recursive kernel with the panel as geometry and the particle
+ * strength / panel area as sheet strength; the result is SUBTRACTED from pu,pv,pw (np each). */
+int o3d_cuda_pts_on_pan(o3d_ctx* ctx, int64_t ns, const float* sx, const float* sy, const float* sz,
+                        const float* ssx, const float* ssy, const float* ssz, int64_t nn, const float* nx,
+                        const float* ny, const float* nz, int64_t np, const uint32_t* idx, const float* area,
+                        float* pu, float* pv, float* pw, double* flops_out);
+
+/* panels -> panels BEM influence block. Replaces panels_on_panels_coeff<S> (src/Coefficients.h:169-483),
+ * 3 unknowns per panel (vortex x1, vortex x2, source), rkernel_2vs_2p (src/Kernels.h:1217-1315).
+ * Source panels: nodes + idx + basis sb1, sb2 (3 arrays of nsp each, SoA x|y|z) + area.
+ * Target panels: nodes + idx + basis tb1, tb2, tnrm + area. self != 0: source and target are the same
+ * surface, apply the diagonal override (:414-436). coeffs: column-major (3*ntp) x (3*nsp), OVERWRITTEN,
+ * already scaled by 1/4pi (:448-451). */
+int o3d_cuda_pan_on_pan_coeff(o3d_ctx* ctx, int64_t snn, const float* snx, const float* sny, const float* snz,
+                              int64_t nsp, const uint32_t* sidx, const float* sb1, const float* sb2,
+                              const float* sarea, int64_t tnn, const float* tnx, const float* tny,
+                              const float* tnz, int64_t ntp, const uint32_t* tidx, const float* tb1,
+                              const float* tb2, const float* tnrm, const float* tarea, int self, float* coeffs,
+                              double* flops_out);
+
+/* ---- device-pointer entry points (arrays already resident in HBM on the context's device 0) ------- */
+/* `stream` is a cudaStream_t passed as an opaque pointer (NULL = the legacy default stream). All calls
+ * are asynchronous with respect to the host. */
+
+/* Number of 32-byte records the packed source stream holds for ns sources (padded to whole tiles). */
+int64_t o3d_cuda_packed_records(int64_t ns);
+/* SoA sources -> packed record stream `packed` (device memory, nrec * 32 bytes). nrec = 0 means
+ * o3d_cuda_packed_records(ns); a larger whole number of tiles is filled up with zero-strength records
+ * (ranks of a sharded job all contribute equally sized streams to one all-gather). */
+int o3d_cuda_pack_sources_dev(o3d_ctx* ctx, void* stream, int64_t ns, const float* sx, const float* sy,
+                              const float* sz, const float* sr, const float* ssx, const float* ssy,
+                              const float* ssz, int64_t nrec, void* packed);
+/* Packed sources (nrec records, any whole number of tiles - e.g. an all-gathered concatenation of every
+ * rank's padded stream) -> targets. tug = base of a 9 x tug_stride float block or NULL. `workspace` is
+ * used when the library splits the source range across CTAs for small target counts: pass NULL to let
+ * the context own it. */
+int o3d_cuda_pts_on_pts_dev(o3d_ctx* ctx, void* stream, int64_t nrec, const void* packed, int64_t nt,
+                            const float* tx, const float* ty, const float* tz, const float* tr, float* tu,
+                            float* tv, float* tw, float* tug, int64_t tug_stride);
+
+
+/* ---- measurement helpers ----------------------------------------------------------------------------- */
+/* When on, o3d_cuda_pts_on_pts_dev brackets its dominant kernel with CUDA events on the launching stream;
+ * o3d_cuda_dev_kernel_ms waits for the last such launch and returns its device time in milliseconds. */
+int o3d_cuda_set_profiling(o3d_ctx* ctx, int on);
+int o3d_cuda_dev_kernel_ms(o3d_ctx* ctx, double* ms);
+/* Runs a dependency-free packed-FMA (fma.rn.f32x2) loop on every SM of device 0 for a few tens of
+ * milliseconds and reports the FP32 rate the GPU sustains at its real clocks, in TFLOP/s. */
+int o3d_cuda_probe_fp32_peak(o3d_ctx* ctx, double* tflops, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* O3D_CUDA_H */

@@ -1,0 +1,65 @@
+"""Loader for the C-ABI shared library (``include/o3d_cuda.h``).
+
+There is exactly one implementation behind this package - the sm_100a CUDA library
+``omega3d_b200/lib/libo3d_cuda.so`` built by ``omega3d_b200/csrc/Makefile``. If it is missing or cannot
+be loaded the import of any compute entry point raises: there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libo3d_cuda.so")
+CSRC = os.path.join(HERE, "csrc")
+
+# every symbol include/o3d_cuda.h declares: (restype, argtypes)
+_P = c_void_p
+SYMBOLS = {
+    "o3d_cuda_abi_version": (c_int, []),
+    "o3d_cuda_device_count": (c_int, []),
+    "o3d_cuda_create": (c_int, [POINTER(c_void_p), c_int, POINTER(c_int)]),
+    "o3d_cuda_destroy": (None, [c_void_p]),
+    "o3d_cuda_last_error": (c_char_p, [c_void_p]),
+    "o3d_cuda_num_devices": (c_int, [c_void_p]),
+    "o3d_cuda_device_props": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_double)]),
+    "o3d_cuda_last_timing": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_double), POINTER(c_int)]),
+    "o3d_cuda_pts_on_pts": (c_int, [c_void_p, c_int64] + [_P] * 7 + [c_int64] + [_P] * 4 + [_P] * 3 + [_P, POINTER(c_double)]),
+    "o3d_cuda_pan_on_pts": (c_int, [c_void_p, c_int64, _P, _P, _P, c_int64] + [_P] * 6 + [c_int64] + [_P] * 3 + [_P] * 3 + [_P, POINTER(c_double)]),
+    "o3d_cuda_pts_on_pan": (c_int, [c_void_p, c_int64] + [_P] * 6 + [c_int64, _P, _P, _P, c_int64, _P, _P] + [_P] * 3 + [POINTER(c_double)]),
+    "o3d_cuda_pan_on_pan_coeff": (c_int, [c_void_p, c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P,
+                                          c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, _P, POINTER(c_double)]),
+    "o3d_cuda_packed_records": (c_int64, [c_int64]),
+    "o3d_cuda_pack_sources_dev": (c_int, [c_void_p, c_void_p, c_int64] + [_P] * 7 + [c_int64, _P]),
+    "o3d_cuda_pts_on_pts_dev": (c_int, [c_void_p, c_void_p, c_int64, _P, c_int64] + [_P] * 4 + [_P] * 3 + [_P, c_int64]),
+    "o3d_cuda_set_profiling": (c_int, [c_void_p, c_int]),
+    "o3d_cuda_dev_kernel_ms": (c_int, [c_void_p, POINTER(c_double)]),
+    "o3d_cuda_probe_fp32_peak": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
+}
+
+_lib = None
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-C", CSRC] + ([] if verbose else ["-s"]), check=True)
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C {CSRC}` (or __graft_entry__.build()). "
+            "omega3d_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError here = header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib

@@ -1,0 +1,492 @@
+// biot_panel.cuh - flat triangular panels <-> points for sm_100a (B200).
+//
+// Replaces the loop nests of panels_affect_points<S,A> (reference src/Influence.h:728-775, :826-864 and
+// the identical blob-target arms :952-1094), points_affect_panels<S,A> (:1186-1214) and
+// panels_on_panels_coeff<S> (src/Coefficients.h:327-446), together with the recursive kernels they call:
+// rkernel_2vs_0p / rkernel_2vs_0pg (src/Kernels.h:1028-1211) and rkernel_2vs_2p (:1217-1315), whose
+// leaves are kernel_0vs_0p / kernel_0vs_0pg (:115-133, :294-345) with a zero source radius.
+//
+// What the reference computes per (panel, point) pair: an adaptive 4-way midpoint subdivision, to at
+// most 3 levels, that stops at a node when |point - centroid| > 4 sqrt(area); every stopped node adds
+// one singular point-vortex(+source) interaction from its centroid carrying area-fraction of the panel
+// strength. Panel-panel pairs subdivide both triangles (16 children), size = sqrt(sa) + sqrt(ta).
+//
+// Design:
+//   * The stop predicate is a hard branch that changes how many leaves are summed, so it is evaluated
+//     bit-for-bit as the reference's scalar build rounds it: unfused __fmul_rn/__fadd_rn in the
+//     reference's operand order, IEEE __fdiv_rn for the /3 and __fsqrt_rn for the distance. The
+//     threshold 4*sqrt(area*4^-l) equals 2^-l * 4*sqrt(area) exactly, so it is formed once per panel.
+//   * The recursion is unrolled into three statically nested loops (no stack, no local memory): the
+//     parent's three edge midpoints are formed once and a child is a register select.
+//   * Leaves run in FP32 with MUFU.RSQ: r3 = rs^3, bbb = -3 rs^5 (the WL core at zero radius, src/
+//     CoreFunc.h:255-259,279-287). Strengths enter as totals: the reference's (ts/area)*area round trip
+//     (src/Influence.h:736, Kernels.h:1043-1048) differs from ts by <= 1 ulp.
+//   * A thread owns one target (a point for panels->points, a panel for points->panels and for the
+//     coefficient block) and its sums: FP32 across one shared-memory tile of sources, FP64 across tiles,
+//     the reference's float-kernel/double-accumulator scheme. Small target counts split the source
+//     range over gridDim.y; each slice stores its FP64 partials in its own slab and pp_finish_kernel adds
+//     the slabs in slice order (deterministic), as in biot_pp.cuh.
+//   * Leaf/split counters (for the reference's flop report) are reduced per warp with
+//     __reduce_add_sync and added once per warp.
+#pragma once
+#include "biot_pp.cuh"
+
+namespace o3d {
+
+constexpr int kPanRec = 5;        // float4 per packed panel record (80 bytes)
+constexpr int kPanTile = 64;      // panels per shared-memory tile (5 KB)
+constexpr int kMaxLev = 3;        // RECURSIVE_LEVELS, src/Influence.h:23, src/Coefficients.h:23
+
+struct Tri {
+  float x0, y0, z0, x1, y1, z1, x2, y2, z2;
+};
+
+// reference operand order: (a + b + c) / 3  (src/Kernels.h:1052-1054)
+__device__ __forceinline__ float third_sum(float a, float b, float c) {
+  return __fdiv_rn(__fadd_rn(__fadd_rn(a, b), c), 3.0f);
+}
+__device__ __forceinline__ float mid(float a, float b) { return __fmul_rn(0.5f, __fadd_rn(a, b)); }
+// my_dist (src/Kernels.h:979-982): sqrt(dx*dx + dy*dy + dz*dz), unfused, left to right
+__device__ __forceinline__ float sumsq_rn(float dx, float dy, float dz) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+struct Mids {
+  float ax, ay, az;  // mid(v0,v1)
+  float bx, by, bz;  // mid(v0,v2)
+  float cx, cy, cz;  // mid(v1,v2)
+};
+__device__ __forceinline__ Mids tri_mids(const Tri& p) {
+  Mids m;
+  m.ax = mid(p.x0, p.x1); m.ay = mid(p.y0, p.y1); m.az = mid(p.z0, p.z1);
+  m.bx = mid(p.x0, p.x2); m.by = mid(p.y0, p.y2); m.bz = mid(p.z0, p.z2);
+  m.cx = mid(p.x1, p.x2); m.cy = mid(p.y1, p.y2); m.cz = mid(p.z1, p.z2);
+  return m;
+}
+// children {0,1,3},{1,2,4},{1,4,3},{3,4,5} of nodes [v0, m01, v1, m02, m12, v2] (src/Kernels.h:1081-1089)
+__device__ __forceinline__ Tri tri_child(const Tri& p, const Mids& m, int k) {
+  Tri c;
+  if (k == 0)      c = Tri{p.x0, p.y0, p.z0, m.ax, m.ay, m.az, m.bx, m.by, m.bz};
+  else if (k == 1) c = Tri{m.ax, m.ay, m.az, p.x1, p.y1, p.z1, m.cx, m.cy, m.cz};
+  else if (k == 2) c = Tri{m.ax, m.ay, m.az, m.cx, m.cy, m.cz, m.bx, m.by, m.bz};
+  else             c = Tri{m.bx, m.by, m.bz, m.cx, m.cy, m.cz, p.x2, p.y2, p.z2};
+  return c;
+}
+
+// Accumulator layout for panel -> point: [0..2] u v w | [3..11] d_j * (bbb e_i) | [12..14] sum w r3 |
+// [15] sum q r3 (the isotropic part of the source-sheet gradient, src/Kernels.h:327-344)
+template <bool GRAD> struct PanAcc { static constexpr int N = GRAD ? 16 : 3; };
+
+// one leaf: singular vortex (wx,wy,wz) + source q at (cx,cy,cz) acting on the point (tx,ty,tz)
+template <bool GRAD>
+__device__ __forceinline__ void pan_leaf(float dx, float dy, float dz, float distsq, float wx, float wy, float wz,
+                                         float q, float (&acc)[PanAcc<GRAD>::N]) {
+  const float rs = rsqrt_approx(distsq);
+  const float rs2 = rs * rs;
+  const float r3 = rs2 * rs;
+  float ex = fmaf(dz, wy, -(dy * wz));
+  float ey = fmaf(dx, wz, -(dz * wx));
+  float ez = fmaf(dy, wx, -(dx * wy));
+  ex = fmaf(dx, q, ex); ey = fmaf(dy, q, ey); ez = fmaf(dz, q, ez);
+  acc[0] = fmaf(r3, ex, acc[0]);
+  acc[1] = fmaf(r3, ey, acc[1]);
+  acc[2] = fmaf(r3, ez, acc[2]);
+  if constexpr (GRAD) {
+    const float bbb = -3.0f * (r3 * rs2);
+    ex *= bbb; ey *= bbb; ez *= bbb;
+    acc[3]  = fmaf(dx, ex, acc[3]);
+    acc[4]  = fmaf(dx, ey, acc[4]);
+    acc[5]  = fmaf(dx, ez, acc[5]);
+    acc[6]  = fmaf(dy, ex, acc[6]);
+    acc[7]  = fmaf(dy, ey, acc[7]);
+    acc[8]  = fmaf(dy, ez, acc[8]);
+    acc[9]  = fmaf(dz, ex, acc[9]);
+    acc[10] = fmaf(dz, ey, acc[10]);
+    acc[11] = fmaf(dz, ez, acc[11]);
+    acc[12] = fmaf(wx, r3, acc[12]);
+    acc[13] = fmaf(wy, r3, acc[13]);
+    acc[14] = fmaf(wz, r3, acc[14]);
+    acc[15] = fmaf(q, r3, acc[15]);
+  }
+}
+
+// Node test + leaf for a triangle whose centroid is (cx,cy,cz): returns true when the node was
+// consumed as a leaf (well separated, or deepest level).
+template <bool GRAD>
+__device__ __forceinline__ bool pan_node(float cx, float cy, float cz, float thr, bool deepest, float tx, float ty,
+                                         float tz, float wx, float wy, float wz, float q,
+                                         float (&acc)[PanAcc<GRAD>::N]) {
+  const float dx = __fsub_rn(tx, cx), dy = __fsub_rn(ty, cy), dz = __fsub_rn(tz, cz);
+  const float distsq = sumsq_rn(dx, dy, dz);
+  const float dist = __fsqrt_rn(distsq);
+  if (dist > thr || deepest) {
+    pan_leaf<GRAD>(dx, dy, dz, distsq, wx, wy, wz, q, acc);
+    return true;
+  }
+  return false;
+}
+
+// Whole (panel, point) pair. (wx,wy,wz,q) = total panel strengths; thr0 = 4 sqrt(area); c0 = centroid.
+// counts[0] += leaves, counts[1] += splits.
+template <bool GRAD>
+__device__ __forceinline__ void pan_on_point(const Tri& p0, float c0x, float c0y, float c0z, float thr0, float wx,
+                                             float wy, float wz, float q, float tx, float ty, float tz,
+                                             float (&acc)[PanAcc<GRAD>::N], unsigned (&counts)[2]) {
+  if (pan_node<GRAD>(c0x, c0y, c0z, thr0, false, tx, ty, tz, wx, wy, wz, q, acc)) {
+    counts[0] += 1;
+    return;
+  }
+  counts[1] += 1;
+  const Mids m0 = tri_mids(p0);
+  const float w1x = wx * 0.25f, w1y = wy * 0.25f, w1z = wz * 0.25f, q1 = q * 0.25f, thr1 = thr0 * 0.5f;
+#pragma unroll 1
+  for (int k1 = 0; k1 < 4; ++k1) {
+    const Tri p1 = tri_child(p0, m0, k1);
+    if (pan_node<GRAD>(third_sum(p1.x0, p1.x1, p1.x2), third_sum(p1.y0, p1.y1, p1.y2), third_sum(p1.z0, p1.z1, p1.z2),
+                       thr1, false, tx, ty, tz, w1x, w1y, w1z, q1, acc)) {
+      counts[0] += 1;
+      continue;
+    }
+    counts[1] += 1;
+    const Mids m1 = tri_mids(p1);
+    const float w2x = w1x * 0.25f, w2y = w1y * 0.25f, w2z = w1z * 0.25f, q2 = q1 * 0.25f, thr2 = thr1 * 0.5f;
+#pragma unroll 1
+    for (int k2 = 0; k2 < 4; ++k2) {
+      const Tri p2 = tri_child(p1, m1, k2);
+      if (pan_node<GRAD>(third_sum(p2.x0, p2.x1, p2.x2), third_sum(p2.y0, p2.y1, p2.y2),
+                         third_sum(p2.z0, p2.z1, p2.z2), thr2, false, tx, ty, tz, w2x, w2y, w2z, q2, acc)) {
+        counts[0] += 1;
+        continue;
+      }
+      counts[1] += 1;
+      const Mids m2 = tri_mids(p2);
+      const float w3x = w2x * 0.25f, w3y = w2y * 0.25f, w3z = w2z * 0.25f, q3 = q2 * 0.25f;
+#pragma unroll 1
+      for (int k3 = 0; k3 < 4; ++k3) {
+        const Tri p3 = tri_child(p2, m2, k3);
+        pan_node<GRAD>(third_sum(p3.x0, p3.x1, p3.x2), third_sum(p3.y0, p3.y1, p3.y2), third_sum(p3.z0, p3.z1, p3.z2),
+                       0.0f, true, tx, ty, tz, w3x, w3y, w3z, q3, acc);
+        counts[0] += 1;
+      }
+    }
+  }
+}
+
+// Fold a tile's FP32 partials into the FP64 sums (u v w | ux vx wx | uy vy wy | uz vz wz) and clear them.
+template <bool GRAD>
+__device__ __forceinline__ void pan_promote(float (&acc)[PanAcc<GRAD>::N], double (&sum)[GRAD ? 12 : 3]) {
+  sum[0] += (double)acc[0]; sum[1] += (double)acc[1]; sum[2] += (double)acc[2];
+  if constexpr (GRAD) {
+    const float ax = acc[12], ay = acc[13], az = acc[14], s = acc[15];
+    sum[3]  += (double)(acc[3] + s);
+    sum[4]  += (double)(acc[4] + az);
+    sum[5]  += (double)(acc[5] - ay);
+    sum[6]  += (double)(acc[6] - az);
+    sum[7]  += (double)(acc[7] + s);
+    sum[8]  += (double)(acc[8] + ax);
+    sum[9]  += (double)(acc[9] + ay);
+    sum[10] += (double)(acc[10] - ax);
+    sum[11] += (double)(acc[11] + s);
+  }
+#pragma unroll
+  for (int k = 0; k < PanAcc<GRAD>::N; ++k) acc[k] = 0.0f;
+}
+
+// ---- packed panel records ---------------------------------------------------------------------------
+//   r[0] = { x0 y0 z0 x1 }  r[1] = { y1 z1 x2 y2 }  r[2] = { z2 wx wy wz }  r[3] = { q cx cy cz }
+//   r[4] = { thr0 = 4 sqrt(area), area, 0, 0 }
+// Padding records (j >= np) sit far away with zero strength and thr0 = 0: always one zero-valued leaf.
+__global__ void pan_pack_kernel(int64_t np, int64_t np_pad, const float* nx, const float* ny, const float* nz,
+                                const uint32_t* idx, const float* tsx, const float* tsy, const float* tsz,
+                                const float* area, const float* sss, float4* out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= np_pad) return;
+  float4 r0 = make_float4(1e18f, 1e18f, 1e18f, 1e18f), r1 = r0, r2 = make_float4(1e18f, 0.f, 0.f, 0.f);
+  float4 r3 = make_float4(0.f, 1e18f, 1e18f, 1e18f), r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (j < np) {
+    const uint32_t a = idx[3 * j], b = idx[3 * j + 1], c = idx[3 * j + 2];
+    const float x0 = nx[a], y0 = ny[a], z0 = nz[a], x1 = nx[b], y1 = ny[b], z1 = nz[b], x2 = nx[c], y2 = ny[c], z2 = nz[c];
+    const float sa = area[j];
+    r0 = make_float4(x0, y0, z0, x1);
+    r1 = make_float4(y1, z1, x2, y2);
+    r2 = make_float4(z2, tsx ? tsx[j] : 0.f, tsy ? tsy[j] : 0.f, tsz ? tsz[j] : 0.f);
+    r3 = make_float4(sss ? __fmul_rn(sss[j], sa) : 0.f, third_sum(x0, x1, x2), third_sum(y0, y1, y2), third_sum(z0, z1, z2));
+    r4 = make_float4(__fmul_rn(__fsqrt_rn(sa), 4.0f), sa, 0.f, 0.f);
+  }
+  float4* o = out + (size_t)j * kPanRec;
+  o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4;
+}
+
+__host__ __device__ inline int64_t padded_panels(int64_t np) { return ((np + kPanTile - 1) / kPanTile) * kPanTile; }
+
+struct PanPtsArgs {
+  const float4* pan;     // packed panel records, padded to whole tiles
+  int ntiles;            // tiles in the stream
+  int nsplit;            // gridDim.y slices of the tile range
+  int64_t nt;
+  const float* tx; const float* ty; const float* tz;
+  float* tu; float* tv; float* tw;
+  float* tug; int64_t tug_stride;
+  double* partial;       // nsplit > 1: [nsplit][12|3][nt], one slab per panel-tile slice
+  unsigned long long* counts;  // [0] leaves, [1] splits (may be nullptr)
+};
+
+__device__ __forceinline__ void add_counts(unsigned long long* g, unsigned (&counts)[2]) {
+  if (!g) return;
+  const unsigned l = __reduce_add_sync(0xffffffffu, counts[0]);
+  const unsigned s = __reduce_add_sync(0xffffffffu, counts[1]);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(g, (unsigned long long)l);
+    atomicAdd(g + 1, (unsigned long long)s);
+  }
+}
+
+// panels -> points: one target point per thread, panel tiles through shared memory.
+template <bool GRAD, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pan_pts_kernel(const PanPtsArgs p) {
+  constexpr int NA = PanAcc<GRAD>::N;
+  constexpr int NS = GRAD ? 12 : 3;
+  __shared__ alignas(16) float4 tile[kPanTile * kPanRec];
+
+  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int k0 = blockIdx.y * per;
+  const int k1 = min(p.ntiles, k0 + per);
+
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  const int64_t ic = min(i, p.nt - 1);
+  const float tx = p.tx[ic], ty = p.ty[ic], tz = p.tz[ic];
+
+  float acc[NA];
+  double sum[NS];
+  unsigned counts[2] = {0u, 0u};
+#pragma unroll
+  for (int k = 0; k < NA; ++k) acc[k] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) sum[k] = 0.0;
+
+  for (int k = k0; k < k1; ++k) {
+    __syncthreads();
+    const float4* g = p.pan + (size_t)k * (kPanTile * kPanRec);
+    for (int e = threadIdx.x; e < kPanTile * kPanRec; e += BLOCK) tile[e] = g[e];
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < kPanTile; ++j) {
+      const float4 r0 = tile[j * kPanRec], r1 = tile[j * kPanRec + 1], r2 = tile[j * kPanRec + 2],
+                   r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
+      const Tri t{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+      pan_on_point<GRAD>(t, r3.y, r3.z, r3.w, r4.x, r2.y, r2.z, r2.w, r3.x, tx, ty, tz, acc, counts);
+    }
+    pan_promote<GRAD>(acc, sum);
+  }
+
+  // padding records and clamped duplicate threads are not part of the reference's count
+  if (i >= p.nt) counts[0] = counts[1] = 0u;
+  add_counts(p.counts, counts);
+  if (i >= p.nt) return;
+  if (p.nsplit > 1) {
+    double* slab = p.partial + (size_t)blockIdx.y * NS * p.nt;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) slab[(size_t)k * p.nt + i] = sum[k];
+  } else {
+    p.tu[i] = (float)((double)p.tu[i] + sum[0]);
+    p.tv[i] = (float)((double)p.tv[i] + sum[1]);
+    p.tw[i] = (float)((double)p.tw[i] + sum[2]);
+    if constexpr (GRAD) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        float* g = p.tug + (size_t)k * p.tug_stride + i;
+        *g = (float)((double)*g + sum[3 + k]);
+      }
+    }
+  }
+}
+
+// ---- particles -> panels (BEM right-hand side) ---------------------------------------------------------
+// One target PANEL per thread (its triangle stays in registers); the particles stream through shared
+// memory in the packed pair-interleaved layout of biot_pp.cuh (positions negated). The particle axis is
+// split over gridDim.y; per-slice FP64 slabs are summed in order by pp_finish_kernel, which applies the `-=`.
+struct PtsPanArgs {
+  const float4* src;     // packed particle stream (pp_pack2_kernel)
+  int64_t ns;            // real particle count (padding records are skipped)
+  int ntiles, nsplit;
+  int64_t np;            // target panels
+  const float4* pan;     // packed panel records (strength fields unused)
+  double* partial;       // [nsplit][3][np], one slab per particle slice
+  unsigned long long* counts;
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pts_pan_kernel(const PtsPanArgs p) {
+  __shared__ alignas(128) float4 tile[kTile * 2];
+  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int k0 = blockIdx.y * per;
+  const int k1 = min(p.ntiles, k0 + per);
+
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  const int64_t ic = min(i, p.np - 1);
+  const float4* r = p.pan + (size_t)ic * kPanRec;
+  const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4];
+  const Tri t{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+  const float cx = r3.y, cy = r3.z, cz = r3.w, thr0 = r4.x;
+
+  float acc[3] = {0.f, 0.f, 0.f};
+  double sum[3] = {0.0, 0.0, 0.0};
+  unsigned counts[2] = {0u, 0u};
+
+  for (int k = k0; k < k1; ++k) {
+    __syncthreads();
+    const float4* g = p.src + (size_t)k * (kTile * 2);
+    for (int e = threadIdx.x; e < kTile * 2; e += BLOCK) tile[e] = g[e];
+    __syncthreads();
+    const int cnt = (int)min((int64_t)kTile, p.ns - (int64_t)k * kTile);
+#pragma unroll 1
+    for (int j = 0; j < cnt; ++j) {
+      const int pr = j >> 1, h = j & 1;
+      const float4 q0 = tile[4 * pr], q1 = tile[4 * pr + 1], q2 = tile[4 * pr + 2], q3 = tile[4 * pr + 3];
+      const float px = -(h ? q0.y : q0.x), py = -(h ? q0.w : q0.z), pz = -(h ? q1.y : q1.x);
+      const float wx = h ? q2.y : q2.x, wy = h ? q2.w : q2.z, wz = h ? q3.y : q3.x;
+      pan_on_point<false>(t, cx, cy, cz, thr0, wx, wy, wz, 0.0f, px, py, pz, acc, counts);
+    }
+    sum[0] += (double)acc[0]; sum[1] += (double)acc[1]; sum[2] += (double)acc[2];
+    acc[0] = acc[1] = acc[2] = 0.f;
+  }
+  if (i >= p.np) counts[0] = counts[1] = 0u;
+  add_counts(p.counts, counts);
+  if (i >= p.np) return;
+  double* slab = p.partial + (size_t)blockIdx.y * 3 * p.np;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) slab[(size_t)k * p.np + i] = sum[k];
+}
+
+// ---- panel -> panel BEM coefficient block -------------------------------------------------------------
+// rkernel_2vs_2p (src/Kernels.h:1217-1315): both triangles subdivide, 16 children per level, the
+// strength falls by 1/16, size = sqrt(sa) + sqrt(ta). The reference runs it three times per pair with
+// unit sheet strength along the source's x1, x2 and a unit source sheet (src/Coefficients.h:356-405);
+// the traversal does not depend on the strength, so one traversal carries all three: per leaf
+//   R1 += s r3 (d x b1),  R2 += s r3 (d x b2),  R3 += s r3 d      (s = sa 16^-l, exact)
+// accumulated in FP32 in the reference's leaf order (it accumulates this block in S = float).
+struct PanCoefArgs {
+  const float4* spn;  // packed source panels
+  const float4* tpn;  // packed target panels
+  int64_t nsp, ntp;
+  int64_t j0, j1;     // source-panel (column) range of this launch
+  const float* sb1; const float* sb2;              // source bases, SoA x|y|z with stride nsp
+  const float* tb1; const float* tb2; const float* tnrm;  // target bases, stride ntp
+  int self;
+  float* coeffs;      // column-major (3 ntp) x (3 nsp); this launch writes columns 3 j0 .. 3 j1
+  int64_t col_offset; // column index of j0 inside `coeffs` (0 when the buffer holds only this range)
+  unsigned long long* counts;  // [0] leaves, [1] splits
+};
+
+struct Coef9 {
+  float v[9];
+};
+
+__device__ __forceinline__ void coef_leaf(float dx, float dy, float dz, float distsq, float s, const float (&b1)[3],
+                                          const float (&b2)[3], Coef9& R) {
+  const float rs = rsqrt_approx(distsq);
+  const float k = s * (rs * rs * rs);
+  R.v[0] = fmaf(k, fmaf(dz, b1[1], -(dy * b1[2])), R.v[0]);
+  R.v[1] = fmaf(k, fmaf(dx, b1[2], -(dz * b1[0])), R.v[1]);
+  R.v[2] = fmaf(k, fmaf(dy, b1[0], -(dx * b1[1])), R.v[2]);
+  R.v[3] = fmaf(k, fmaf(dz, b2[1], -(dy * b2[2])), R.v[3]);
+  R.v[4] = fmaf(k, fmaf(dx, b2[2], -(dz * b2[0])), R.v[4]);
+  R.v[5] = fmaf(k, fmaf(dy, b2[0], -(dx * b2[1])), R.v[5]);
+  R.v[6] = fmaf(k, dx, R.v[6]);
+  R.v[7] = fmaf(k, dy, R.v[7]);
+  R.v[8] = fmaf(k, dz, R.v[8]);
+}
+
+__device__ __forceinline__ bool coef_node(const Tri& s, const Tri& t, float thr, bool deepest, float str,
+                                          const float (&b1)[3], const float (&b2)[3], Coef9& R) {
+  const float sx = third_sum(s.x0, s.x1, s.x2), sy = third_sum(s.y0, s.y1, s.y2), sz = third_sum(s.z0, s.z1, s.z2);
+  const float tx = third_sum(t.x0, t.x1, t.x2), ty = third_sum(t.y0, t.y1, t.y2), tz = third_sum(t.z0, t.z1, t.z2);
+  const float dx = __fsub_rn(tx, sx), dy = __fsub_rn(ty, sy), dz = __fsub_rn(tz, sz);
+  const float distsq = sumsq_rn(dx, dy, dz);
+  if (__fsqrt_rn(distsq) > thr || deepest) {
+    coef_leaf(dx, dy, dz, distsq, str, b1, b2, R);
+    return true;
+  }
+  return false;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pan_coef_kernel(const PanCoefArgs p) {
+  const int64_t j = p.j0 + blockIdx.x;                              // source panel = column block
+  const int64_t i = (int64_t)blockIdx.y * BLOCK + threadIdx.x;      // target panel = row block
+  const int64_t ic = min(i, p.ntp - 1);
+  unsigned counts[2] = {0u, 0u};
+
+  const float4* sr = p.spn + (size_t)j * kPanRec;
+  const float4 a0 = sr[0], a1 = sr[1], a2 = sr[2], a4 = sr[4];
+  const Tri s0{a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
+  const float sa = a4.y;
+  const float4* tr = p.tpn + (size_t)ic * kPanRec;
+  const float4 c0 = tr[0], c1 = tr[1], c2 = tr[2], c4 = tr[4];
+  const Tri t0{c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x};
+  const float b1[3] = {p.sb1[j], p.sb1[p.nsp + j], p.sb1[2 * p.nsp + j]};
+  const float b2[3] = {p.sb2[j], p.sb2[p.nsp + j], p.sb2[2 * p.nsp + j]};
+  // trisize = sqrt(sa) + sqrt(ta); threshold 4 * trisize, halves exactly per level
+  const float thr0 = __fmul_rn(__fadd_rn(__fsqrt_rn(sa), __fsqrt_rn(c4.y)), 4.0f);
+
+  Coef9 R;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R.v[k] = 0.0f;
+
+  if (coef_node(s0, t0, thr0, false, sa, b1, b2, R)) {
+    counts[0] += 1;
+  } else {
+    counts[1] += 1;
+    const Mids sm0 = tri_mids(s0), tm0 = tri_mids(t0);
+    const float str1 = sa * 0.0625f, thr1 = thr0 * 0.5f;
+#pragma unroll 1
+    for (int e1 = 0; e1 < 16; ++e1) {
+      const Tri s1 = tri_child(s0, sm0, e1 >> 2), t1 = tri_child(t0, tm0, e1 & 3);
+      if (coef_node(s1, t1, thr1, false, str1, b1, b2, R)) { counts[0] += 1; continue; }
+      counts[1] += 1;
+      const Mids sm1 = tri_mids(s1), tm1 = tri_mids(t1);
+      const float str2 = str1 * 0.0625f, thr2 = thr1 * 0.5f;
+#pragma unroll 1
+      for (int e2 = 0; e2 < 16; ++e2) {
+        const Tri s2 = tri_child(s1, sm1, e2 >> 2), t2 = tri_child(t1, tm1, e2 & 3);
+        if (coef_node(s2, t2, thr2, false, str2, b1, b2, R)) { counts[0] += 1; continue; }
+        counts[1] += 1;
+        const Mids sm2 = tri_mids(s2), tm2 = tri_mids(t2);
+        const float str3 = str2 * 0.0625f;
+#pragma unroll 1
+        for (int e3 = 0; e3 < 16; ++e3) {
+          const Tri s3 = tri_child(s2, sm2, e3 >> 2), t3 = tri_child(t2, tm2, e3 & 3);
+          coef_node(s3, t3, 0.0f, true, str3, b1, b2, R);
+          counts[0] += 1;
+        }
+      }
+    }
+  }
+
+  if (i >= p.ntp) counts[0] = counts[1] = 0u;
+  add_counts(p.counts, counts);
+  if (i >= p.ntp) return;
+
+  const float t1x = p.tb1[i], t1y = p.tb1[p.ntp + i], t1z = p.tb1[2 * p.ntp + i];
+  const float t2x = p.tb2[i], t2y = p.tb2[p.ntp + i], t2z = p.tb2[2 * p.ntp + i];
+  const float tnx = p.tnrm[i], tny = p.tnrm[p.ntp + i], tnz = p.tnrm[2 * p.ntp + i];
+  const float fac = (float)(1.0 / (4.0 * 3.14159265358979323846));  // src/Coefficients.h:448
+  const float twopi = (float)(2.0 * 3.14159265358979323846);
+  const size_t nrows = (size_t)3 * p.ntp;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float ru = R.v[3 * k], rv = R.v[3 * k + 1], rw = R.v[3 * k + 2];
+    float m0 = __fadd_rn(__fadd_rn(__fmul_rn(ru, t1x), __fmul_rn(rv, t1y)), __fmul_rn(rw, t1z));
+    float m1 = __fadd_rn(__fadd_rn(__fmul_rn(ru, t2x), __fmul_rn(rv, t2y)), __fmul_rn(rw, t2z));
+    float m2 = __fadd_rn(__fadd_rn(__fmul_rn(ru, tnx), __fmul_rn(rv, tny)), __fmul_rn(rw, tnz));
+    if (p.self && i == j) {  // src/Coefficients.h:414-436
+      m0 = k == 1 ? -twopi : 0.0f;
+      m1 = k == 0 ? twopi : 0.0f;
+      m2 = k == 2 ? twopi : 0.0f;
+    }
+    float* col = p.coeffs + ((size_t)(p.col_offset + (j - p.j0)) * 3 + k) * nrows + (size_t)3 * i;
+    col[0] = m0 * fac; col[1] = m1 * fac; col[2] = m2 * fac;
+  }
+}
+
+}  // namespace o3d

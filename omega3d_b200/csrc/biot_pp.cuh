@@ -106,7 +106,7 @@ struct PPArgs {
   float* tu; float* tv; float* tw;   // velocity, read-modify-write
   float* tug;             // 9 rows of stride tug_stride, or nullptr
   int64_t tug_stride;
-  double* partial;        // nsplit > 1: [12 or 3][nt] FP64 workspace receiving atomic partial sums
+  double* partial;        // nsplit > 1: [nsplit][12 or 3][nt] FP64 workspace, one slab per source slice
   float sign;             // +1, or -1 for the points->panels convention
 };
 
@@ -183,8 +183,11 @@ __global__ void __launch_bounds__(BLOCK) pp_kernel(const PPArgs p) {
     const int64_t i = base + (int64_t)t * BLOCK;
     if (i >= p.nt) continue;
     if (p.nsplit > 1) {
+      // slice blockIdx.y owns its own [NS][nt] slab: plain stores, summed in slice order by
+      // pp_finish_kernel, so the result does not depend on CTA scheduling
+      double* slab = p.partial + (size_t)blockIdx.y * NS * p.nt;
 #pragma unroll
-      for (int k = 0; k < NS; ++k) atomicAdd(p.partial + (size_t)k * p.nt + i, sum[t][k]);
+      for (int k = 0; k < NS; ++k) slab[(size_t)k * p.nt + i] = sum[t][k];
     } else {
       const double sg = (double)p.sign;
       p.tu[i] = (float)((double)p.tu[i] + sg * sum[t][0]);
@@ -201,16 +204,16 @@ __global__ void __launch_bounds__(BLOCK) pp_kernel(const PPArgs p) {
   }
 }
 
-// nsplit > 1 epilogue: out[i] = float(double(out[i]) + sign * partial[i]), then clear the workspace.
-__global__ void pp_finish_kernel(int nrows, int64_t nt, double* partial, float* tu, float* tv, float* tw, float* tug,
-                                 int64_t tug_stride, float sign) {
+// nsplit > 1 epilogue: out[i] = float(double(out[i]) + sign * sum over slices (in slice order) of partial).
+__global__ void pp_finish_kernel(int nrows, int nsplit, int64_t nt, const double* partial, float* tu, float* tv, float* tw,
+                                 float* tug, int64_t tug_stride, float sign) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nt) return;
   for (int k = 0; k < nrows; ++k) {
-    double* w = partial + (size_t)k * nt + i;
+    double acc = 0.0;
+    for (int s = 0; s < nsplit; ++s) acc += partial[((size_t)s * nrows + k) * nt + i];
     float* o = k == 0 ? tu + i : k == 1 ? tv + i : k == 2 ? tw + i : tug + (size_t)(k - 3) * tug_stride + i;
-    *o = (float)((double)*o + (double)sign * *w);
-    *w = 0.0;
+    *o = (float)((double)*o + (double)sign * acc);
   }
 }
 
@@ -359,8 +362,11 @@ __global__ void __launch_bounds__(BLOCK) pp2_kernel(const PPArgs p) {
     const int64_t i = base + (int64_t)t * BLOCK;
     if (i >= p.nt) continue;
     if (p.nsplit > 1) {
+      // slice blockIdx.y owns its own [NS][nt] slab: plain stores, summed in slice order by
+      // pp_finish_kernel, so the result does not depend on CTA scheduling
+      double* slab = p.partial + (size_t)blockIdx.y * NS * p.nt;
 #pragma unroll
-      for (int k = 0; k < NS; ++k) atomicAdd(p.partial + (size_t)k * p.nt + i, sum[t][k]);
+      for (int k = 0; k < NS; ++k) slab[(size_t)k * p.nt + i] = sum[t][k];
     } else {
       const double sg = (double)p.sign;
       p.tu[i] = (float)((double)p.tu[i] + sg * sum[t][0]);

@@ -46,7 +46,7 @@ int main(int argc, char** argv) {
   pp_pack_kernel<<<(npad + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk);
   pp_pack2_kernel<<<(npad / 2 + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk2);
   float* out; CHECK(cudaMalloc(&out, (size_t)n * 12 * 4));
-  double* partial; CHECK(cudaMalloc(&partial, (size_t)n * 12 * 8)); CHECK(cudaMemset(partial, 0, (size_t)n * 12 * 8));
+  double* partial; CHECK(cudaMalloc(&partial, (size_t)n * 12 * 8 * 4));  // up to 4 source slices
   CHECK(cudaDeviceSynchronize());
 
   // host reference on 8 targets
@@ -73,7 +73,7 @@ int main(int argc, char** argv) {
       CHECK(cudaMemset(out, 0, (size_t)n * 12 * 4));
       cudaEventRecord(e0);
       kern<<<grid, BLOCK>>>(a);
-      if (nsplit > 1) pp_finish_kernel<<<(n + 255) / 256, 256>>>(grad ? 12 : 3, n, partial, a.tu, a.tv, a.tw, a.tug, n, 1.0f);
+      if (nsplit > 1) pp_finish_kernel<<<(n + 255) / 256, 256>>>(grad ? 12 : 3, nsplit, n, partial, a.tu, a.tv, a.tw, a.tug, n, 1.0f);
       cudaEventRecord(e1);
       CHECK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, e0, e1);
