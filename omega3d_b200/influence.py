@@ -227,8 +227,8 @@ class Surfaces:
         centroid + offset * normal (used by panels_affect_panels with offset 1e-4)."""
         self.vortex_sheet_to_panel_strength()
         p0, p1, p2 = (self.x[:, self.idx[:, k]] for k in range(3))
-        px = (f32(1.0 / 3.0) * (p0 + p1 + p2)).astype(f32)
-        px = (px + f32(offset) * self.nrm).astype(f32)
+        px = ((1.0 / 3.0) * ((p0 + p1).astype(f32) + p2).astype(f32).astype(np.float64)).astype(f32)  # (1./3.) is a double there
+        px = (px + (f32(offset) * self.nrm).astype(f32)).astype(f32)
         val = self.ts.copy()
         if self.E == reactive:
             val = (val + (self.bc[0] * self.b1 + self.bc[1] * self.b2) * self.area).astype(f32)
