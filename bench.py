@@ -294,7 +294,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1 << 20, help="particles (sources = targets)")
+    ap.add_argument("--particles", "--n", dest="n", type=int, default=1 << 20, help="particles (sources = targets)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")

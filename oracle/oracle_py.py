@@ -29,6 +29,8 @@ def build(want_ref: bool = True) -> None:
     subprocess.run(["make", "-s", "-C", HERE, "restate"], check=True)
     if want_ref and os.path.isdir(os.path.join(REFERENCE_ROOT, "src")):
         subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+        if os.path.exists(os.path.join(HERE, "..", "omega3d_b200", "lib", "libo3d_cuda.so")):
+            subprocess.run(["make", "-s", "-C", HERE, "dropin"], check=True)
 
 
 def _p(a):
@@ -107,8 +109,10 @@ class Reference:
 
     TARG_FIELD, TARG_TRACER, TARG_BLOB = 0, 1, 2
 
-    def __init__(self, fast: bool = False):
-        path = os.path.join(OUT, "libo3d_ref_fast.so" if fast else "libo3d_ref.so")
+    def __init__(self, fast: bool = False, dropin: bool = False):
+        """dropin=True: the patched, -DUSE_CUDA build of the same driver (oracle/_ref/libo3d_dropin.so); call
+        set_accel(4) on it to route the reference's own routines into the CUDA arm."""
+        path = os.path.join(OUT, "libo3d_dropin.so" if dropin else "libo3d_ref_fast.so" if fast else "libo3d_ref.so")
         if not os.path.exists(path):
             build(want_ref=True)
         if not os.path.exists(path):
@@ -131,6 +135,13 @@ class Reference:
 
     def max_threads(self):
         return int(self.lib.o3d_ref_max_threads())
+
+    def set_accel(self, accel: int):
+        """accel_t of the ExecEnv handed to the reference routines: 1 cpu_x86, 4 gpu_cuda."""
+        self.lib.o3d_ref_set_accel(int(accel))
+
+    def built_with_cuda(self) -> bool:
+        return bool(self.lib.o3d_ref_built_with_cuda())
 
     def pts_on_pts(self, sx, sr, ss, tx, tr, tu, tug, targ_kind=None):
         ns, nt = sx.shape[1], tx.shape[1]

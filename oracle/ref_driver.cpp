@@ -51,6 +51,7 @@ struct Mute {
 };
 
 bool g_mute = true;
+int g_accel = cpu_x86;  // accel_t handed to ExecEnv; gpu_cuda only means something in the -DUSE_CUDA (drop-in) build
 
 Points<float> make_points(int n, const float* x, const float* y, const float* z,
                           const float* str3 /*SoA 3 x n or NULL*/, const float* rad /*or NULL*/,
@@ -111,6 +112,16 @@ void store_results(Points<float>& t, int nt, float* tu, float* tug) {
 extern "C" {
 
 void o3d_ref_set_mute(int on) { g_mute = on != 0; }
+// 1 = cpu_x86 (the oracle), 4 = gpu_cuda (dispatches into integration/O3DCudaInfluence.h when built with
+// the patched headers and -DUSE_CUDA: oracle/_ref/libo3d_dropin.so)
+void o3d_ref_set_accel(int a) { g_accel = a; }
+int o3d_ref_built_with_cuda() {
+#ifdef USE_CUDA
+  return 1;
+#else
+  return 0;
+#endif
+}
 int o3d_ref_max_threads() { return omp_get_max_threads(); }
 void o3d_ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
@@ -125,7 +136,7 @@ int o3d_ref_pts_on_pts(int ns, const float* sx, const float* sy, const float* sz
   Points<float> src = make_points(ns, sx, sy, sz, ss3, sr, active, lagrangian);
   Points<float> targ = make_targets(targ_kind, nt, tx, ty, tz, tr);
   load_results(targ, nt, tu, tug);
-  ExecEnv env(true, true, direct, cpu_x86);
+  ExecEnv env(true, true, direct, (accel_t)g_accel);
   points_affect_points<float, double>(src, targ, ResultsType(want_grad ? velandgrad : velonly), env);
   store_results(targ, nt, tu, tug);
   return 0;
@@ -158,7 +169,7 @@ int o3d_ref_pan_on_pts(int nn, const float* nodes, int np, const uint32_t* idx, 
   Surfaces<float> src = make_surfaces(nn, nodes, np, idx, val, active);
   Points<float> targ = make_targets(targ_kind, nt, tx, ty, tz, tr);
   load_results(targ, nt, tu, tug);
-  ExecEnv env(true, true, direct, cpu_x86);
+  ExecEnv env(true, true, direct, (accel_t)g_accel);
   panels_affect_points<float, double>(src, targ, ResultsType(velonly), env);
   store_results(targ, nt, tu, tug);
   return 0;
@@ -174,7 +185,7 @@ int o3d_ref_pts_on_pan(int ns, const float* sx, const float* sy, const float* sz
   Surfaces<float> targ = make_surfaces(nn, nodes, np, idx, val, active);
   auto& u = targ.get_vel();
   for (int d = 0; d < 3; ++d) std::memcpy(u[d].data(), pu + (size_t)d*np, sizeof(float)*np);
-  ExecEnv env(true, true, direct, cpu_x86);
+  ExecEnv env(true, true, direct, (accel_t)g_accel);
   points_affect_panels<float, double>(src, targ, ResultsType(velonly), env);
   for (int d = 0; d < 3; ++d) std::memcpy(pu + (size_t)d*np, u[d].data(), sizeof(float)*np);
   return 0;
@@ -187,7 +198,7 @@ int o3d_ref_pan_on_pan(int nn, const float* nodes, int np, const uint32_t* idx, 
   Mute m(g_mute);
   Surfaces<float> src = make_surfaces(nn, nodes, np, idx, val, active);
   Surfaces<float> targ = make_surfaces(tnn, tnodes, tnp, tidx, tval, reactive);
-  ExecEnv env(true, true, direct, cpu_x86);
+  ExecEnv env(true, true, direct, (accel_t)g_accel);
   panels_affect_panels<float, double>(src, targ, ResultsType(velonly), env);
   auto& u = targ.get_vel();
   for (int d = 0; d < 3; ++d) std::memcpy(pu + (size_t)d*tnp, u[d].data(), sizeof(float)*tnp);

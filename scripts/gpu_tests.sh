@@ -6,4 +6,4 @@ mkdir -p $OUT
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -25 | tee $OUT/pytest_gpu.txt
 echo "== issue model"; timeout 120 omega3d_b200/csrc/microbench/issue_model 2>&1 | tee $OUT/issue_model.txt
 echo "== kbench"; timeout 300 omega3d_b200/csrc/microbench/kbench 262144 3 2>&1 | tee $OUT/kbench.txt
-echo "== bench 256K"; timeout 300 python bench.py --n 262144 --no-cpu 2>&1 | tail -1 | tee $OUT/bench_256k.json
+echo "== bench 256K"; timeout 300 python bench.py --particles 262144 --no-cpu 2>&1 | tail -1 | tee $OUT/bench_256k.json

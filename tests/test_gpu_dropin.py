@@ -1,0 +1,88 @@
+"""GPU (-m gpu): the drop-in itself. oracle/_ref/libo3d_dropin.so is the REFERENCE's own Influence.h /
+Coefficients.h / ExecEnv.h with integration/omega3d_use_cuda.patch applied, compiled with -DUSE_CUDA around the
+reference's real Points<float> / Surfaces<float> containers (built in the container that has /root/reference;
+the .so travels to the GPU box). Calling the reference's routines with ExecEnv(..., gpu_cuda) must give what the
+same routines give with ExecEnv(..., cpu_x86)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GRAD_TOL, VEL_TOL, golden, rel_err
+
+from omega3d_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+CPU_X86, GPU_CUDA = 1, 4
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    from oracle import oracle_py
+    if not os.path.exists(os.path.join(oracle_py.OUT, "libo3d_dropin.so")):
+        pytest.skip("oracle/_ref/libo3d_dropin.so not built (needs /root/reference at build time)")
+    lib = oracle_py.Reference(dropin=True)
+    assert lib.built_with_cuda()
+    return lib
+
+
+def both(lib, fn):
+    out = []
+    for accel in (CPU_X86, GPU_CUDA):
+        lib.set_accel(accel)
+        out.append(fn())
+    lib.set_accel(CPU_X86)
+    return out
+
+
+@pytest.mark.parametrize("kind,grad", [("blob", True), ("blob", False), ("field", True), ("tracer", False)])
+def test_points_affect_points_through_reference_dispatch(dropin, kind, grad):
+    n = 3000
+    x, s, r = W.random_cloud(n, seed=61)
+    tx, _, tr = W.random_cloud(1111, seed=62)
+    tk = {"blob": dropin.TARG_BLOB, "field": dropin.TARG_FIELD, "tracer": dropin.TARG_TRACER}[kind]
+
+    def run():
+        tu = np.full((3, 1111), 0.25, f32)            # non-zero start: the arm must accumulate
+        tug = np.full((9, 1111), -0.5, f32) if grad else None
+        dropin.pts_on_pts(x, r, s, tx, tr if kind == "blob" else None, tu, tug, targ_kind=tk)
+        return tu, tug
+    (cu, cg), (gu, gg) = both(dropin, run)
+    assert rel_err(gu - 0.25, cu - 0.25) <= VEL_TOL
+    if grad:
+        assert rel_err(gg + 0.5, cg + 0.5) <= GRAD_TOL
+
+
+def test_panel_routines_through_reference_dispatch(dropin):
+    g = golden("panels_80.npz")
+
+    def pan_pts():
+        tu, tug = g["u0"].copy(), g["g0"].copy()
+        dropin.pan_on_pts(g["nodes_i"], g["idx"], g["val"], g["tx"], None, tu, tug, targ_kind=dropin.TARG_FIELD)
+        return tu, tug
+    (cu, cg), (gu, gg) = both(dropin, pan_pts)
+    assert np.array_equal(cu, g["u_grad"])           # the CPU arm of the patched build is still the reference
+    assert rel_err(gu - g["u0"], cu - g["u0"]) <= VEL_TOL and rel_err(gg - g["g0"], cg - g["g0"]) <= GRAD_TOL
+
+    def pts_pan():
+        pu = g["pu0"].copy()
+        dropin.pts_on_pan(g["psx"], g["psr"], g["pss"], g["nodes_i"], g["idx"], g["val"], pu)
+        return pu
+    cpu, gpu = both(dropin, pts_pan)
+    assert np.array_equal(cpu, g["pu"]) and rel_err(gpu - g["pu0"], cpu - g["pu0"]) <= VEL_TOL
+
+    def pan_pan():
+        return dropin.pan_on_pan(g["nodes_i"], g["idx"], g["val"], g["nodes_i"], g["idx"], np.zeros_like(g["val"]))
+    cpu, gpu = both(dropin, pan_pan)
+    assert np.array_equal(cpu, g["pan_on_pan_pu"]) and rel_err(gpu, cpu) <= VEL_TOL
+
+
+def test_coefficients_through_reference_dispatch(dropin):
+    """-DUSE_CUDA makes the patched panels_on_panels_coeff build its block on the GPU; compare with the golden block."""
+    g = golden("coeff_20.npz")
+    bc = np.zeros((20, 3), f32)
+    a = dropin.pan_on_pan_coeff(g["n0"], g["i0"], bc)
+    assert rel_err(a, g["a_self"]) <= 2e-5
+    a = dropin.pan_on_pan_coeff(g["n0"], g["i0"], bc, target=(g["n1"], g["i1"], bc))
+    assert rel_err(a, g["a_cross"]) <= 2e-5

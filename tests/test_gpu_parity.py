@@ -252,3 +252,30 @@ def test_translation_invariance_and_self_term(cuda_ctx):
     assert np.all(u == 0)
     assert g[0, 0] == 0 and g[4, 0] == 0 and g[8, 0] == 0
     assert g[1, 0] == -g[3, 0] != 0 and g[2, 0] == -g[6, 0] != 0 and g[5, 0] == -g[7, 0] != 0
+
+
+def test_two_device_context_equals_one_device(cuda_ctx):
+    """In-process multi-GPU (one context driving 2 GPUs): targets are partitioned across the devices, sources
+    replicated; every target's sum is computed by exactly one device."""
+    if cuda_ctx.lib.o3d_cuda_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx2 = I.CudaContext((0, 1))
+    n = 60001
+    x, s, r = W.random_cloud(n, seed=77)
+    u1, g1 = np.zeros((3, n), f32), np.zeros((9, n), f32)
+    u2, g2 = np.zeros((3, n), f32), np.zeros((9, n), f32)
+    cuda_ctx.pts_on_pts(x, r, s, x, r, u1, g1)
+    ctx2.pts_on_pts(x, r, s, x, r, u2, g2)
+    assert rel_err(u2, u1) <= 2e-7 and rel_err(g2, g1) <= 2e-7
+    nodes, idx = W.icosphere(2, 0.5)
+    surf = I.Surfaces(soa(nodes), idx, W.panel_strengths(idx.shape[0], seed=5), I.active)
+    a, b = np.zeros((3, n), f32), np.zeros((3, n), f32)
+    cuda_ctx.pan_on_pts(surf.x, surf.idx, surf.ts, surf.area, surf.ps[2], x, a, None)
+    ctx2.pan_on_pts(surf.x, surf.idx, surf.ts, surf.area, surf.ps[2], x, b, None)
+    assert rel_err(b, a) <= 2e-7
+    pa, pb = np.zeros((3, surf.np_), f32), np.zeros((3, surf.np_), f32)
+    cuda_ctx.pts_on_pan(x, s, surf.x, surf.idx, surf.area, pa)
+    ctx2.pts_on_pan(x, s, surf.x, surf.idx, surf.area, pb)
+    assert rel_err(pb, pa) <= 2e-7
+    assert np.array_equal(I.panels_on_panels_coeff(surf, surf, cuda_ctx), I.panels_on_panels_coeff(surf, surf, ctx2))
+    ctx2.close()
