@@ -27,7 +27,23 @@
 #pragma once
 #include "o3d_common.cuh"
 
+#ifndef O3D_PP_TRACE
+#define O3D_PP_TRACE 1    // 1: recover the wz gradient slot from the trace-free identity instead of accumulating it
+#endif
+#ifndef O3D_PP_MINB
+#define O3D_PP_MINB 3     // __launch_bounds__ min CTAs per SM for pp2_kernel (caps registers at 168)
+#endif
+#ifndef O3D_PP_UNROLL_GRAD
+#define O3D_PP_UNROLL_GRAD 4   // source pairs per trip of the packed inner loop, velocity+gradient kernel
+#endif
+#ifndef O3D_PP_UNROLL_VEL
+#define O3D_PP_UNROLL_VEL 2    // ... velocity-only kernel
+#endif
+
 namespace o3d {
+
+constexpr int kPPUnrollGrad = O3D_PP_UNROLL_GRAD;
+constexpr int kPPUnrollVel = O3D_PP_UNROLL_VEL;
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float y;
@@ -108,6 +124,7 @@ struct PPArgs {
   int64_t tug_stride;
   double* partial;        // nsplit > 1: [nsplit][12 or 3][nt] FP64 workspace, one slab per source slice
   float sign;             // +1, or -1 for the points->panels convention
+  const uint32_t* radius_range;  // pp_scan_kernel output, or nullptr: no uniform-radius fast path
 };
 
 // Scalar-FFMA kernel: T register-blocked targets per thread.
@@ -243,14 +260,26 @@ __global__ void pp_pack_kernel(int64_t ns, int64_t ns_pad, const float* sx, cons
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
-template <bool GRAD>
+// Instruction ORDER matters here. A packed FP32 instruction holds the FMA pipe for 2 cycles and the register
+// file feeds two fresh 64-bit operands in that time; a third distinct operand costs a third cycle unless the
+// operand-reuse cache serves it, which happens when the PREVIOUS instruction used the same register in the same
+// operand slot (tools/sass_rf_model.py; measured in profiles/r01_issue_model_microbench.txt). ptxas largely
+// keeps the source order of independent instructions, so the sequence below is written as a chain in which
+// every instruction shares slot 0 or slot 1 with its predecessor (marked <). Measured gain over formula order:
+// 1.5-3 % (profiles/r01_variants_256k.txt).
+//
+// UNI: every source radius equals one value and every target radius equals one value (the usual case: particles
+// are created with one core size), so r2 = sr^2 + tr^2 is a kernel-wide constant and the per-pair FADD2 goes.
+// TRACE (O3D_PP_TRACE): the vortex-only gradient is trace free, d.(d x w) = 0, so the wz slot is recovered in
+// the epilogue as -(ux + vy) instead of being accumulated: one FFMA2 less per interaction.
+template <bool GRAD, bool UNI>
 __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
                                              const float2 tx, const float2 ty, const float2 tz, const float2 tr2,
                                              float2 (&acc)[PPAcc<GRAD>::N]) {
   const float2 dx = __fadd2_rn(tx, f2(q0.x, q0.y));
   const float2 dy = __fadd2_rn(ty, f2(q0.z, q0.w));
   const float2 dz = __fadd2_rn(tz, f2(q1.x, q1.y));
-  const float2 r2 = __fadd2_rn(tr2, f2(q1.z, q1.w));
+  const float2 r2 = UNI ? tr2 : __fadd2_rn(tr2, f2(q1.z, q1.w));   // UNI: tr2 already holds sr^2 + tr^2
   const float2 wx = f2(q2.x, q2.y), wy = f2(q2.z, q2.w), wz = f2(q3.x, q3.y);
   const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, r2)));
   const float2 top = __ffma2_rn(f2(1.5f, 1.5f), r2, d2);
@@ -259,36 +288,85 @@ __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, c
   const float2 rs4 = __fmul2_rn(rs2, rs2);
   const float2 dn5 = __fmul2_rn(rs4, rs);
   const float2 r3 = __fmul2_rn(top, dn5);
-  // negated cross product n = -(c): n_x = dy wz - dz wy ... using only multiplies and FMAs with a
-  // negated first product folded into the sign of the accumulation (u -= r3 n  <=>  u += (-r3) n)
-  const float2 ndx = neg2(dx), ndy = neg2(dy), ndz = neg2(dz);
-  float2 cx = __ffma2_rn(dz, wy, __fmul2_rn(ndy, wz));
-  float2 cy = __ffma2_rn(dx, wz, __fmul2_rn(ndz, wx));
-  float2 cz = __ffma2_rn(dy, wx, __fmul2_rn(ndx, wy));
-  acc[0] = __ffma2_rn(r3, cx, acc[0]);
-  acc[1] = __ffma2_rn(r3, cy, acc[1]);
-  acc[2] = __ffma2_rn(r3, cz, acc[2]);
+  // c = (dz wy - dy wz, dx wz - dz wx, dy wx - dx wy)
+  const float2 t1 = __fmul2_rn(dy, wz);
+  const float2 t2 = __fmul2_rn(dx, wz);                       // < wz
+  const float2 t3 = __fmul2_rn(dx, wy);                       // < dx
+  float2 cx = __ffma2_rn(dz, wy, neg2(t1));                   // < wy
+  float2 cy = __ffma2_rn(neg2(dz), wx, t2);                   // < dz
+  float2 cz = __ffma2_rn(dy, wx, neg2(t3));                   // < wx
+  if constexpr (GRAD) {
+    acc[12] = __ffma2_rn(r3, wx, acc[12]);                    // < wx
+    acc[13] = __ffma2_rn(r3, wy, acc[13]);                    // < r3
+    acc[14] = __ffma2_rn(r3, wz, acc[14]);                    // < r3
+  }
+  acc[0] = __ffma2_rn(r3, cx, acc[0]);                        // < r3
+  acc[1] = __ffma2_rn(r3, cy, acc[1]);                        // < r3
+  acc[2] = __ffma2_rn(r3, cz, acc[2]);                        // < r3
   if constexpr (GRAD) {
     const float2 bbb = __fmul2_rn(dn5, __ffma2_rn(f2(-5.0f, -5.0f), __fmul2_rn(top, rs2), f2(2.0f, 2.0f)));
-    cx = __fmul2_rn(cx, bbb); cy = __fmul2_rn(cy, bbb); cz = __fmul2_rn(cz, bbb);
+    cz = __fmul2_rn(bbb, cz);                                 // < cz
+    cy = __fmul2_rn(bbb, cy);                                 // < bbb
+    cx = __fmul2_rn(bbb, cx);                                 // < bbb
     acc[3]  = __ffma2_rn(dx, cx, acc[3]);
-    acc[4]  = __ffma2_rn(dx, cy, acc[4]);
-    acc[5]  = __ffma2_rn(dx, cz, acc[5]);
-    acc[6]  = __ffma2_rn(dy, cx, acc[6]);
-    acc[7]  = __ffma2_rn(dy, cy, acc[7]);
-    acc[8]  = __ffma2_rn(dy, cz, acc[8]);
-    acc[9]  = __ffma2_rn(dz, cx, acc[9]);
-    acc[10] = __ffma2_rn(dz, cy, acc[10]);
-    acc[11] = __ffma2_rn(dz, cz, acc[11]);
-    acc[12] = __ffma2_rn(wx, r3, acc[12]);
-    acc[13] = __ffma2_rn(wy, r3, acc[13]);
-    acc[14] = __ffma2_rn(wz, r3, acc[14]);
+    acc[4]  = __ffma2_rn(dx, cy, acc[4]);                     // < dx
+    acc[5]  = __ffma2_rn(dx, cz, acc[5]);                     // < dx
+    acc[8]  = __ffma2_rn(dy, cz, acc[8]);                     // < cz   (snake through the 3x3 outer product)
+    acc[7]  = __ffma2_rn(dy, cy, acc[7]);                     // < dy
+    acc[6]  = __ffma2_rn(dy, cx, acc[6]);                     // < dy
+    acc[9]  = __ffma2_rn(dz, cx, acc[9]);                     // < cx
+    acc[10] = __ffma2_rn(dz, cy, acc[10]);                    // < dz
+#if !O3D_PP_TRACE
+    acc[11] = __ffma2_rn(dz, cz, acc[11]);                    // < dz
+#endif
+  }
+}
+
+// One CTA's pass over its source tiles; the UNI flag is warp-uniform, so the two instantiations are two
+// straight-line copies of the loop selected once per kernel.
+template <int T, bool GRAD, bool UNI, int BLOCK>
+__device__ __forceinline__ void pp2_tiles(const PPArgs& p, const int k0, const int nk, float4 (&tile)[2][kTile * 2],
+                                          uint64_t (&full)[2], const float2 (&tx)[T], const float2 (&ty)[T],
+                                          const float2 (&tz)[T], const float2 (&tr2)[T],
+                                          double (&sum)[T][GRAD ? 12 : 3]) {
+  constexpr int NA = PPAcc<GRAD>::N;
+  constexpr int U = GRAD ? kPPUnrollGrad : kPPUnrollVel;
+  float2 acc[T][NA];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[t][k] = f2(0.f, 0.f);
+  }
+  for (int k = 0; k < nk; ++k) {
+    const int buf = k & 1;
+    mbar_wait(&full[buf], (k >> 1) & 1);
+    const float4* __restrict__ s = tile[buf];
+#pragma unroll(U)
+    for (int j = 0; j < kTile / 2; ++j) {
+      const float4 q0 = s[4 * j], q1 = s[4 * j + 1], q2 = s[4 * j + 2], q3 = s[4 * j + 3];
+#pragma unroll
+      for (int t = 0; t < T; ++t) pp_interact2<GRAD, UNI>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tr2[t], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      float h[NA];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) { h[q] = acc[t][q].x + acc[t][q].y; acc[t][q] = f2(0.f, 0.f); }
+#if O3D_PP_TRACE
+      if constexpr (GRAD) h[11] = -(h[3] + h[7]);
+#endif
+      pp_promote<GRAD>(h, sum[t]);
+    }
+    __syncthreads();  // every warp is done with tile[buf]; safe to refill
+    if (threadIdx.x == 0 && k + 2 < nk) {
+      mbar_expect_tx(&full[buf], kTileBytes);
+      bulk_g2s(tile[buf], p.src + (size_t)(k0 + k + 2) * (kTile * 2), kTileBytes, &full[buf]);
+    }
   }
 }
 
 template <int T, bool GRAD, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) pp2_kernel(const PPArgs p) {
-  constexpr int NA = PPAcc<GRAD>::N;
+__global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) pp2_kernel(const PPArgs p) {
   constexpr int NS = GRAD ? 12 : 3;
   __shared__ alignas(128) float4 tile[2][kTile * 2];
   __shared__ alignas(8) uint64_t full[2];
@@ -313,6 +391,17 @@ __global__ void __launch_bounds__(BLOCK) pp2_kernel(const PPArgs p) {
       }
   }
 
+  // radius scan (pp_scan_kernel): [0] min, [1] max of sr^2 bit patterns over sources that carry strength,
+  // [2] min, [3] max of tr bit patterns. Uniform <=> both ranges collapse and the constant r2 is positive.
+  bool uni = false;
+  float r2u = 0.0f;
+  if (p.radius_range) {
+    const uint32_t s0 = p.radius_range[0], s1 = p.radius_range[1], t0 = p.radius_range[2], t1 = p.radius_range[3];
+    const float tr = p.tr ? __uint_as_float(t0) : 0.0f;
+    r2u = __fadd_rn(__uint_as_float(s0), __fmul_rn(tr, tr));   // sr*sr + tr*tr, the reference's r2 (src/CoreFunc.h:267)
+    uni = s0 == s1 && (!p.tr || t0 == t1) && r2u > 0.0f && s0 != 0xffffffffu;
+  }
+
   float2 tx[T], ty[T], tz[T], tr2[T];
   const int64_t base = (int64_t)blockIdx.x * (BLOCK * T) + threadIdx.x;
 #pragma unroll
@@ -320,42 +409,18 @@ __global__ void __launch_bounds__(BLOCK) pp2_kernel(const PPArgs p) {
     const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
     tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
     const float r = p.tr ? p.tr[i] : 0.0f;
-    tr2[t] = f2(r * r, r * r);
+    tr2[t] = uni ? f2(r2u, r2u) : f2(r * r, r * r);
   }
 
-  float2 acc[T][NA];
   double sum[T][NS];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
 #pragma unroll
-    for (int k = 0; k < NA; ++k) acc[t][k] = f2(0.f, 0.f);
-#pragma unroll
     for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
   }
 
-  for (int k = 0; k < nk; ++k) {
-    const int buf = k & 1;
-    mbar_wait(&full[buf], (k >> 1) & 1);
-    const float4* __restrict__ s = tile[buf];
-#pragma unroll 2
-    for (int j = 0; j < kTile / 2; ++j) {
-      const float4 q0 = s[4 * j], q1 = s[4 * j + 1], q2 = s[4 * j + 2], q3 = s[4 * j + 3];
-#pragma unroll
-      for (int t = 0; t < T; ++t) pp_interact2<GRAD>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tr2[t], acc[t]);
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      float h[NA];
-#pragma unroll
-      for (int q = 0; q < NA; ++q) { h[q] = acc[t][q].x + acc[t][q].y; acc[t][q] = f2(0.f, 0.f); }
-      pp_promote<GRAD>(h, sum[t]);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && k + 2 < nk) {
-      mbar_expect_tx(&full[buf], kTileBytes);
-      bulk_g2s(tile[buf], p.src + (size_t)(k0 + k + 2) * (kTile * 2), kTileBytes, &full[buf]);
-    }
-  }
+  if (uni) pp2_tiles<T, GRAD, true, BLOCK>(p, k0, nk, tile, full, tx, ty, tz, tr2, sum);
+  else     pp2_tiles<T, GRAD, false, BLOCK>(p, k0, nk, tile, full, tx, ty, tz, tr2, sum);
 
 #pragma unroll
   for (int t = 0; t < T; ++t) {
@@ -380,6 +445,31 @@ __global__ void __launch_bounds__(BLOCK) pp2_kernel(const PPArgs p) {
         }
       }
     }
+  }
+}
+
+// Radius ranges for the uniform-radius fast path of pp2_kernel. range[0..1]: min/max of the sr^2 bit patterns
+// (non-negative floats order like unsigned integers) over records that carry strength - zero-strength records,
+// padding included, contribute exactly 0 whatever their radius; range[2..3]: min/max of the tr bit patterns.
+// Initialise range to {0xffffffff, 0, 0xffffffff, 0}.
+__global__ void pp_scan_kernel(int64_t nrec, const float4* packed, int64_t nt, const float* tr, uint32_t* range) {
+  uint32_t smin = 0xffffffffu, smax = 0u, tmin = 0xffffffffu, tmax = 0u;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t pr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pr < nrec / 2; pr += stride) {
+    const float4 q1 = packed[4 * pr + 1], q2 = packed[4 * pr + 2], q3 = packed[4 * pr + 3];
+    if (q2.x != 0.f || q2.z != 0.f || q3.x != 0.f) { const uint32_t b = __float_as_uint(q1.z); smin = min(smin, b); smax = max(smax, b); }
+    if (q2.y != 0.f || q2.w != 0.f || q3.y != 0.f) { const uint32_t b = __float_as_uint(q1.w); smin = min(smin, b); smax = max(smax, b); }
+  }
+  if (tr)
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nt; i += stride) {
+      const uint32_t b = __float_as_uint(tr[i]);
+      tmin = min(tmin, b); tmax = max(tmax, b);
+    }
+  smin = __reduce_min_sync(0xffffffffu, smin); smax = __reduce_max_sync(0xffffffffu, smax);
+  tmin = __reduce_min_sync(0xffffffffu, tmin); tmax = __reduce_max_sync(0xffffffffu, tmax);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(range + 0, smin); atomicMax(range + 1, smax);
+    atomicMin(range + 2, tmin); atomicMax(range + 3, tmax);
   }
 }
 

@@ -76,7 +76,7 @@ struct Device {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // h2d start, compute start, compute end, d2h end
   cudaEvent_t evk[2] = {nullptr, nullptr};                   // around the dominant kernel of a *_dev call
   bool profile = false;
-  DevBuf src, packed, targ, out, work, geom, panels, tpanels, cnt;
+  DevBuf src, packed, targ, out, work, geom, panels, tpanels, cnt, rng;
   unsigned long long counts[2] = {0, 0};  // leaves, splits of the last panel call on this device
   // result of the last call on this device
   float kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
@@ -225,6 +225,14 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
     }
     a.partial = workspace;
   }
+  // radius ranges for the uniform-radius fast path (one pass over the records' r^2 lane and the target radii)
+  static const uint32_t kRangeInit[4] = {0xffffffffu, 0u, 0xffffffffu, 0u};
+  O3D_TRY(d, d.rng.ensure(sizeof kRangeInit));
+  O3D_TRY(d, cudaMemcpyAsync(d.rng.p, kRangeInit, sizeof kRangeInit, cudaMemcpyHostToDevice, st));
+  pp_scan_kernel<<<d.sm_count * 4, 256, 0, st>>>(nrec, packed, nt, tr, d.rng.as<uint32_t>());
+  O3D_TRY(d, cudaGetLastError());
+  d.launches += 1;
+  a.radius_range = d.rng.as<uint32_t>();
   if (d.profile) O3D_TRY(d, cudaEventRecord(d.evk[0], st));
   if (grad)
     pp2_kernel<kPPTgrad, true, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a);
@@ -331,7 +339,7 @@ void o3d_cuda_destroy(o3d_ctx* c) {
   if (!c) return;
   for (Device& d : c->dev) {
     cudaSetDevice(d.id);
-    for (DevBuf* b : {&d.src, &d.packed, &d.targ, &d.out, &d.work, &d.geom, &d.panels, &d.tpanels, &d.cnt}) b->release();
+    for (DevBuf* b : {&d.src, &d.packed, &d.targ, &d.out, &d.work, &d.geom, &d.panels, &d.tpanels, &d.cnt, &d.rng}) b->release();
     for (cudaEvent_t e : d.ev)
       if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : d.evk)

@@ -47,6 +47,10 @@ int main(int argc, char** argv) {
   pp_pack2_kernel<<<(npad / 2 + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk2);
   float* out; CHECK(cudaMalloc(&out, (size_t)n * 12 * 4));
   double* partial; CHECK(cudaMalloc(&partial, (size_t)n * 12 * 8 * 4));  // up to 4 source slices
+  uint32_t* range; CHECK(cudaMalloc(&range, 16));
+  { const uint32_t init[4] = {0xffffffffu, 0u, 0xffffffffu, 0u}; CHECK(cudaMemcpy(range, init, 16, cudaMemcpyHostToDevice)); }
+  pp_scan_kernel<<<prop.multiProcessorCount * 4, 256>>>(npad, pk2, n, d[3], range);
+  const bool no_uniform = getenv("KBENCH_NO_UNIFORM") != nullptr;   // force the general-radius path
   CHECK(cudaDeviceSynchronize());
 
   // host reference on 8 targets
@@ -67,6 +71,7 @@ int main(int argc, char** argv) {
     a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
     a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = out + 3 * (size_t)n; a.tug_stride = n;
     a.partial = partial; a.sign = 1.0f;
+    a.radius_range = (src == pk2 && !no_uniform) ? range : nullptr;
     dim3 grid((n + BLOCK * T - 1) / (BLOCK * T), nsplit);
     float best = 1e30f;
     for (int r = 0; r < reps + 1; ++r) {
