@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define O3D_CUDA_ABI_VERSION 1
+#define O3D_CUDA_ABI_VERSION 2
 
 enum {
   O3D_OK = 0,
@@ -127,6 +127,63 @@ int o3d_cuda_pack_sources_dev(o3d_ctx* ctx, void* stream, int64_t ns, const floa
 int o3d_cuda_pts_on_pts_dev(o3d_ctx* ctx, void* stream, int64_t nrec, const void* packed, int64_t nt,
                             const float* tx, const float* ty, const float* tz, const float* tr, float* tu,
                             float* tv, float* tw, float* tug, int64_t tug_stride);
+
+
+/* ---- convection on the device: the O(N) steps around the influence sums --- */
+
+/* One Runge-Kutta stage as the reference's Points::move sees it: velocity u[3] and, optionally, the 9 x ug_stride
+ * velocity-gradient block of a Points object evaluated at that stage (device pointers). */
+typedef struct {
+  const float* u[3];
+  const float* ug;      /* NULL: this stage carries no gradients => no stretching (src/Points.h:296,366,453) */
+  int64_t ug_stride;
+} o3d_stage;
+
+/* finalize_vels on device arrays: u = fs + u/(4 pi) in double, grads *= float(1/(4 pi))
+ * (src/ElementBase.h:187-192, src/Points.h:265-277). ug may be NULL. */
+int o3d_cuda_pts_finalize_dev(o3d_ctx* ctx, void* stream, int64_t n, float* u, float* v, float* w, float* ug,
+                              int64_t ug_stride, const double* fs);
+/* Points::move with `order` = 1, 2 or 3 stages (src/ElementBase.h:253-336 advection, src/Points.h:288-520
+ * stretching and elongation), rounding as the reference's scalar build does. State is read from xin/sin/ein and
+ * written to xout/sout/eout (may alias; arrays of 3 device pointers; sin/sout NULL: inert points; ein/eout NULL:
+ * elongation not tracked). order 1: position moves with stages[0].u, strengths stretch with stages[0].ug (the
+ * caller passes the object's OWN gradients there, as src/Points.h:296-332 uses them). order >= 2 also stores the
+ * combined velocity in uout (3 pointers), as the reference does into this->u. wt: `order` stage weights. */
+int o3d_cuda_pts_move_dev(o3d_ctx* ctx, void* stream, int64_t n, int order, double dt, const double* wt,
+                          const o3d_stage* stages, const float* const* xin, const float* const* sin,
+                          const float* ein, float* const* xout, float* const* sout, float* eout, float* const* uout);
+
+/* A vortex-particle collection resident in HBM (the reference's Points<S>, active + lagrangian: position,
+ * strength, radius, elongation, velocity, velocity gradient). With a multi-device context the particles are
+ * block-partitioned over the devices in whole 512-particle tiles; each device evaluates and moves its own block
+ * and the packed source records are exchanged device-to-device (NVLink peer copies) once per evaluation. */
+typedef struct o3d_particles o3d_particles;
+int o3d_cuda_particles_create(o3d_ctx* ctx, o3d_particles** out);
+void o3d_cuda_particles_destroy(o3d_ctx* ctx, o3d_particles* p);
+int64_t o3d_cuda_particles_count(const o3d_particles* p);
+/* host -> device. elong == NULL: 1 everywhere (a fresh collection, src/Points.h:120-127). */
+int o3d_cuda_particles_upload(o3d_ctx* ctx, o3d_particles* p, int64_t n, const float* x, const float* y,
+                              const float* z, const float* sx, const float* sy, const float* sz, const float* r,
+                              const float* elong);
+/* device -> host; any pointer may be NULL (skipped). ug: 9 host arrays or NULL. */
+int o3d_cuda_particles_download(o3d_ctx* ctx, o3d_particles* p, float* x, float* y, float* z, float* sx, float* sy,
+                                float* sz, float* r, float* elong, float* u, float* v, float* w, float* const* ug);
+/* Convection::find_vels(fs, vort, {}, vort) for this collection (src/Convection.h:130-184): zero_vels,
+ * particles -> themselves (velocity [+ gradient]), finalize_vels(fs). */
+int o3d_cuda_particles_find_vels(o3d_ctx* ctx, o3d_particles* p, const double* fs, int want_grad, double* flops_out);
+/* `nsteps` calls of Convection::advect(time, dt, fs, ...) for a particle-only system (no boundaries, no field
+ * points): order 1 = advect_1st (src/Convection.h:232-262), 2 = advect_2nd_ralston (:349-425), 3 = advect_3rd
+ * (:431-556). Nothing leaves the device between steps; steps of unchanged size replay one captured CUDA graph.
+ * Afterwards velocity holds what the reference leaves in it (order 1: u at the start of the last step; order >= 2:
+ * the last combined stage velocity) and the gradient the first-stage gradient of the last step. */
+int o3d_cuda_particles_advect(o3d_ctx* ctx, o3d_particles* p, int order, double time, double dt, const double* fs,
+                              int nsteps, double* flops_out);
+/* CUDA-graph replay of repeated steps is on by default; off = launch every kernel individually (same results,
+ * bit for bit - tests compare the two). o3d_cuda_particles_graph_active: 1 if the collection holds a captured step. */
+int o3d_cuda_set_graphs(o3d_ctx* ctx, int on);
+int o3d_cuda_particles_graph_active(const o3d_particles* p);
+/* sqrt(max |s|^2) (ElementBase::get_max_str, src/ElementBase.h:339-351) and max elongation (src/Points.h:523-532). */
+int o3d_cuda_particles_stats(o3d_ctx* ctx, o3d_particles* p, float* max_str, float* max_elong);
 
 
 /* ---- measurement helpers ----------------------------------------------------------------------------- */

@@ -34,6 +34,18 @@ SYMBOLS = {
     "o3d_cuda_packed_records": (c_int64, [c_int64]),
     "o3d_cuda_pack_sources_dev": (c_int, [c_void_p, c_void_p, c_int64] + [_P] * 7 + [c_int64, _P]),
     "o3d_cuda_pts_on_pts_dev": (c_int, [c_void_p, c_void_p, c_int64, _P, c_int64] + [_P] * 4 + [_P] * 3 + [_P, c_int64]),
+    "o3d_cuda_pts_finalize_dev": (c_int, [c_void_p, c_void_p, c_int64, _P, _P, _P, _P, c_int64, POINTER(c_double)]),
+    "o3d_cuda_pts_move_dev": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_double, POINTER(c_double), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "o3d_cuda_particles_create": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "o3d_cuda_particles_destroy": (None, [c_void_p, c_void_p]),
+    "o3d_cuda_particles_count": (c_int64, [c_void_p]),
+    "o3d_cuda_particles_upload": (c_int, [c_void_p, c_void_p, c_int64] + [_P] * 8),
+    "o3d_cuda_particles_download": (c_int, [c_void_p, c_void_p] + [_P] * 12),
+    "o3d_cuda_particles_find_vels": (c_int, [c_void_p, c_void_p, POINTER(c_double), c_int, POINTER(c_double)]),
+    "o3d_cuda_particles_advect": (c_int, [c_void_p, c_void_p, c_int, c_double, c_double, POINTER(c_double), c_int, POINTER(c_double)]),
+    "o3d_cuda_particles_stats": (c_int, [c_void_p, c_void_p, POINTER(ctypes.c_float), POINTER(ctypes.c_float)]),
+    "o3d_cuda_set_graphs": (c_int, [c_void_p, c_int]),
+    "o3d_cuda_particles_graph_active": (c_int, [c_void_p]),
     "o3d_cuda_set_profiling": (c_int, [c_void_p, c_int]),
     "o3d_cuda_dev_kernel_ms": (c_int, [c_void_p, POINTER(c_double)]),
     "o3d_cuda_probe_fp32_peak": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),

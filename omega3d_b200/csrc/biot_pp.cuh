@@ -391,12 +391,12 @@ __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) pp2_kernel(const PPArgs p)
       }
   }
 
-  // radius scan (pp_scan_kernel): [0] min, [1] max of sr^2 bit patterns over sources that carry strength,
-  // [2] min, [3] max of tr bit patterns. Uniform <=> both ranges collapse and the constant r2 is positive.
+  // radius scan (pp_scan_kernel): [0] ~min, [1] max of sr^2 bit patterns over sources that carry strength,
+  // [2] ~min, [3] max of tr bit patterns. Uniform <=> both ranges collapse and the constant r2 is positive.
   bool uni = false;
   float r2u = 0.0f;
   if (p.radius_range) {
-    const uint32_t s0 = p.radius_range[0], s1 = p.radius_range[1], t0 = p.radius_range[2], t1 = p.radius_range[3];
+    const uint32_t s0 = ~p.radius_range[0], s1 = p.radius_range[1], t0 = ~p.radius_range[2], t1 = p.radius_range[3];
     const float tr = p.tr ? __uint_as_float(t0) : 0.0f;
     r2u = __fadd_rn(__uint_as_float(s0), __fmul_rn(tr, tr));   // sr*sr + tr*tr, the reference's r2 (src/CoreFunc.h:267)
     uni = s0 == s1 && (!p.tr || t0 == t1) && r2u > 0.0f && s0 != 0xffffffffu;
@@ -451,7 +451,8 @@ __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) pp2_kernel(const PPArgs p)
 // Radius ranges for the uniform-radius fast path of pp2_kernel. range[0..1]: min/max of the sr^2 bit patterns
 // (non-negative floats order like unsigned integers) over records that carry strength - zero-strength records,
 // padding included, contribute exactly 0 whatever their radius; range[2..3]: min/max of the tr bit patterns.
-// Initialise range to {0xffffffff, 0, 0xffffffff, 0}.
+// The minima are kept COMPLEMENTED (range[0] = max of ~bits) so that the whole block starts as zeros: one
+// cudaMemsetAsync, which - unlike a copy from pageable host memory - can be captured into a CUDA graph.
 __global__ void pp_scan_kernel(int64_t nrec, const float4* packed, int64_t nt, const float* tr, uint32_t* range) {
   uint32_t smin = 0xffffffffu, smax = 0u, tmin = 0xffffffffu, tmax = 0u;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -468,8 +469,8 @@ __global__ void pp_scan_kernel(int64_t nrec, const float4* packed, int64_t nt, c
   smin = __reduce_min_sync(0xffffffffu, smin); smax = __reduce_max_sync(0xffffffffu, smax);
   tmin = __reduce_min_sync(0xffffffffu, tmin); tmax = __reduce_max_sync(0xffffffffu, tmax);
   if ((threadIdx.x & 31) == 0) {
-    atomicMin(range + 0, smin); atomicMax(range + 1, smax);
-    atomicMin(range + 2, tmin); atomicMax(range + 3, tmax);
+    atomicMax(range + 0, ~smin); atomicMax(range + 1, smax);
+    atomicMax(range + 2, ~tmin); atomicMax(range + 3, tmax);
   }
 }
 

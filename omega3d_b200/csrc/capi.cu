@@ -15,6 +15,7 @@
 #include "../../include/o3d_cuda.h"
 #include "biot_panel.cuh"
 #include "biot_pp.cuh"
+#include "convect.cuh"
 
 using namespace o3d;
 
@@ -92,6 +93,7 @@ struct o3d_ctx {
   std::string err;
   double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
   int launches = 0;
+  bool use_graphs = true;   // o3d_cuda_set_graphs
 };
 
 namespace {
@@ -226,9 +228,8 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
     a.partial = workspace;
   }
   // radius ranges for the uniform-radius fast path (one pass over the records' r^2 lane and the target radii)
-  static const uint32_t kRangeInit[4] = {0xffffffffu, 0u, 0xffffffffu, 0u};
-  O3D_TRY(d, d.rng.ensure(sizeof kRangeInit));
-  O3D_TRY(d, cudaMemcpyAsync(d.rng.p, kRangeInit, sizeof kRangeInit, cudaMemcpyHostToDevice, st));
+  O3D_TRY(d, d.rng.ensure(4 * sizeof(uint32_t)));
+  O3D_TRY(d, cudaMemsetAsync(d.rng.p, 0, 4 * sizeof(uint32_t), st));
   pp_scan_kernel<<<d.sm_count * 4, 256, 0, st>>>(nrec, packed, nt, tr, d.rng.as<uint32_t>());
   O3D_TRY(d, cudaGetLastError());
   d.launches += 1;
@@ -284,6 +285,279 @@ bool run_fma_probe(Device& d, double* tflops, double* ms_out) {
   *tflops = flops / (best * 1e-3) * 1e-12;
   *ms_out = best;
   return true;
+}
+
+// ---- device-resident particle collections (include/o3d_cuda.h: o3d_particles) ------------------------
+// Row layout of one per-device state block (rows of `cap` floats; only this device's slice is stored):
+enum { kRowX = 0, kRowS = 3, kRowR = 6, kRowE = 7, kRowU = 8, kRowG = 11, kRowsMain = 20 };
+// an interim Runge-Kutta copy keeps position, strength, velocity, gradient: x 0-2, s 3-5, u 6-8, ug 9-17
+enum { kIntX = 0, kIntS = 3, kIntU = 6, kIntG = 9, kRowsInterim = 18 };
+
+struct PartDev {
+  DevBuf main, interim[2], packed, stats;
+  cudaEvent_t packed_ready = nullptr;   // this device's slice of the packed stream is written
+  cudaEvent_t pulled = nullptr;         // this device has copied every peer's slice
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaGraphExec_t graph = nullptr;      // one captured advect step (single-device contexts)
+  int64_t graph_n = -1;
+  int graph_order = 0;
+  double graph_dt = 0, graph_fs[3] = {0, 0, 0};
+  bool graph_failed = false;
+  int launches_per_step = 0;
+  int64_t t0 = 0, n = 0, cap = 0;       // slice [t0, t0 + n) of the collection, row stride
+};
+
+}  // namespace
+
+struct o3d_particles {
+  int64_t n = 0;
+  int64_t per = 0;          // particles per device, a whole number of tiles
+  int64_t nrec = 0;         // packed records in the whole stream = ndev slices of `per`, the last one padded
+  std::vector<PartDev> dev;
+  bool peers_enabled = false;
+};
+
+namespace {
+
+float* prow(DevBuf& b, int64_t cap, int row) { return b.as<float>() + (size_t)row * cap; }
+
+bool part_layout(o3d_ctx* c, o3d_particles* p, int64_t n) {
+  const int nd = (int)c->dev.size();
+  p->n = n;
+  p->per = padded_sources((n + nd - 1) / nd);   // tile-aligned blocks: the packed stream is the same for any device count
+  p->nrec = 0;
+  for (int k = 0; k < nd; ++k) {
+    PartDev& q = p->dev[k];
+    q.t0 = std::min(n, p->per * k);
+    q.n = std::min(n, p->per * (k + 1)) - q.t0;
+    if (q.n > 0) p->nrec = q.t0 + padded_sources(q.n);
+  }
+  for (int k = 0; k < nd; ++k) {
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    O3D_TRY(d, cudaSetDevice(d.id));
+    const int64_t cap = std::max<int64_t>(q.n, 1);
+    if (cap > q.cap || cap * 2 < q.cap) q.cap = (cap + cap / 8 + 63) & ~int64_t(63);   // head-room for growth, 256-byte rows
+    O3D_TRY(d, q.main.ensure((size_t)kRowsMain * q.cap * 4));
+    O3D_TRY(d, q.packed.ensure((size_t)std::max<int64_t>(p->nrec, kTile) * 32));
+    O3D_TRY(d, q.stats.ensure(2 * sizeof(uint32_t)));
+    if (!q.packed_ready) {
+      O3D_TRY(d, cudaEventCreateWithFlags(&q.packed_ready, cudaEventDisableTiming));
+      O3D_TRY(d, cudaEventCreateWithFlags(&q.pulled, cudaEventDisableTiming));
+      O3D_TRY(d, cudaEventCreate(&q.ev[0]));
+      O3D_TRY(d, cudaEventCreate(&q.ev[1]));
+    }
+  }
+  if (nd > 1 && !p->peers_enabled) {
+    for (int k = 0; k < nd; ++k) {
+      cudaSetDevice(c->dev[k].id);
+      for (int j = 0; j < nd; ++j)
+        if (j != k) {
+          int can = 0;
+          cudaDeviceCanAccessPeer(&can, c->dev[k].id, c->dev[j].id);
+          if (can && cudaDeviceEnablePeerAccess(c->dev[j].id, 0) != cudaSuccess) cudaGetLastError();  // already enabled is fine
+        }
+    }
+    p->peers_enabled = true;
+  }
+  return true;
+}
+
+// A view of one Points-like state on one device: where its x, s, r, u, ug rows live.
+struct PartView {
+  float* x[3]; float* s[3]; float* r; float* u[3]; float* ug; int64_t stride;
+};
+PartView view_main(PartDev& q) {
+  PartView v;
+  for (int d = 0; d < 3; ++d) v.x[d] = prow(q.main, q.cap, kRowX + d), v.s[d] = prow(q.main, q.cap, kRowS + d), v.u[d] = prow(q.main, q.cap, kRowU + d);
+  v.r = prow(q.main, q.cap, kRowR);
+  v.ug = prow(q.main, q.cap, kRowG);
+  v.stride = q.cap;
+  return v;
+}
+PartView view_interim(PartDev& q, int which) {
+  PartView v;
+  DevBuf& b = q.interim[which];
+  for (int d = 0; d < 3; ++d) v.x[d] = prow(b, q.cap, kIntX + d), v.s[d] = prow(b, q.cap, kIntS + d), v.u[d] = prow(b, q.cap, kIntU + d);
+  v.r = prow(q.main, q.cap, kRowR);   // radii never change inside a convection step
+  v.ug = prow(b, q.cap, kIntG);
+  v.stride = q.cap;
+  return v;
+}
+
+// Convection::find_vels for one state, on every device of the context (src/Convection.h:130-184 with no boundaries):
+// zero_vels; pack own slice; exchange packed slices; particles -> own targets; finalize_vels(fs).
+// `sel`: 0 = main state, 1/2 = interim copy 0/1. Everything is enqueued on the per-device streams; no host sync.
+bool part_find_vels(o3d_ctx* c, o3d_particles* p, int sel, const double* fs, bool grad, bool in_capture) {
+  const int nd = (int)c->dev.size();
+  // 1. each device: (wait until every peer has finished reading its previous packed slice) zero, pack own slice
+  for (int k = 0; k < nd; ++k) {
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    if (q.n == 0) continue;
+    O3D_TRY(d, cudaSetDevice(d.id));
+    cudaStream_t st = d.stream;
+    if (nd > 1)
+      for (int j = 0; j < nd; ++j)
+        if (j != k && p->dev[j].n > 0) O3D_TRY(d, cudaStreamWaitEvent(st, p->dev[j].pulled, 0));
+    PartView v = sel == 0 ? view_main(q) : view_interim(q, sel - 1);
+    const unsigned gb = (unsigned)((q.n + 255) / 256);
+    pts_fill_kernel<<<gb, 256, 0, st>>>(q.n, 3, v.u[0], v.stride, 0.0f);
+    if (grad) pts_fill_kernel<<<gb, 256, 0, st>>>(q.n, 9, v.ug, v.stride, 0.0f);
+    O3D_TRY(d, cudaGetLastError());
+    d.launches += grad ? 2 : 1;
+    float4* slice = q.packed.as<float4>() + (size_t)q.t0 * 2;
+    if (!launch_pack(d, st, q.n, v.x[0], v.x[1], v.x[2], v.r, v.s[0], v.s[1], v.s[2], slice, padded_sources(q.n))) return false;
+    if (nd > 1) O3D_TRY(d, cudaEventRecord(q.packed_ready, st));
+  }
+  // 2. each device pulls every peer's slice of the packed stream (NVLink peer copy), then evaluates its targets
+  for (int k = 0; k < nd; ++k) {
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    if (q.n == 0) continue;
+    O3D_TRY(d, cudaSetDevice(d.id));
+    cudaStream_t st = d.stream;
+    if (nd > 1) {
+      for (int j = 0; j < nd; ++j) {
+        PartDev& o = p->dev[j];
+        if (j == k || o.n == 0) continue;
+        O3D_TRY(d, cudaStreamWaitEvent(st, o.packed_ready, 0));
+        const size_t off = (size_t)o.t0 * 32, bytes = (size_t)padded_sources(o.n) * 32;
+        O3D_TRY(d, cudaMemcpyPeerAsync((char*)q.packed.p + off, d.id, (const char*)o.packed.p + off, c->dev[j].id, bytes, st));
+      }
+      O3D_TRY(d, cudaEventRecord(q.pulled, st));
+    }
+    PartView v = sel == 0 ? view_main(q) : view_interim(q, sel - 1);
+    if (d.profile && !in_capture) O3D_TRY(d, cudaEventRecord(q.ev[0], st));
+    if (!launch_pp(d, st, p->nrec, q.packed.as<float4>(), q.n, v.x[0], v.x[1], v.x[2], v.r, v.u[0], v.u[1], v.u[2],
+                   grad ? v.ug : nullptr, v.stride, nullptr))
+      return false;
+    pts_finalize_kernel<<<(unsigned)((q.n + 255) / 256), 256, 0, st>>>(q.n, v.u[0], v.u[1], v.u[2], grad ? v.ug : nullptr, v.stride,
+                                                                      fs[0], fs[1], fs[2]);
+    O3D_TRY(d, cudaGetLastError());
+    d.launches += 1;
+  }
+  return true;
+}
+
+bool launch_move(Device& d, cudaStream_t st, const MoveArgs& a, int order) {
+  if (a.n == 0) return true;
+  const unsigned gb = (unsigned)((a.n + 255) / 256);
+  if (order == 1) pts_move_kernel<1><<<gb, 256, 0, st>>>(a);
+  else if (order == 2) pts_move_kernel<2><<<gb, 256, 0, st>>>(a);
+  else pts_move_kernel<3><<<gb, 256, 0, st>>>(a);
+  O3D_TRY(d, cudaGetLastError());
+  d.launches += 1;
+  return true;
+}
+
+StageRef stage_of(const PartView& v) {
+  StageRef s;
+  for (int d = 0; d < 3; ++d) s.u[d] = v.u[d];
+  s.ug = v.ug;
+  s.ug_stride = v.stride;
+  return s;
+}
+
+// `dst` <- Euler move of `src` over dt with velocity `vel`'s u and gradient `own`'s ug (src/Points.h:288-351: the
+// one-stage move stretches with the moving object's OWN gradient). Elongation is only tracked on the main state.
+MoveArgs euler_args(const PartDev& q, const PartView& src, const PartView& dst, const PartView& vel, const PartView& own, double dt) {
+  MoveArgs a{};
+  a.n = q.n;
+  a.dt = dt;
+  a.wt[0] = 1.0;
+  a.st[0] = stage_of(vel);
+  a.st[0].ug = own.ug;
+  for (int d = 0; d < 3; ++d) {
+    a.xin[d] = src.x[d]; a.sin[d] = src.s[d];
+    a.xout[d] = dst.x[d]; a.sout[d] = dst.s[d];
+    a.uout[d] = nullptr;
+  }
+  a.ein = nullptr; a.eout = nullptr;
+  return a;
+}
+
+// One Convection::advect call (src/Convection.h:208-228) for a particle-only system, enqueued on every device.
+bool part_advect_once(o3d_ctx* c, o3d_particles* p, int order, double dt, const double* fs, bool in_capture) {
+  const int nd = (int)c->dev.size();
+  auto each = [&](auto&& f) {
+    for (int k = 0; k < nd; ++k) {
+      Device& d = c->dev[k];
+      PartDev& q = p->dev[k];
+      if (q.n == 0) continue;
+      if (cudaSetDevice(d.id) != cudaSuccess) return false;
+      if (!f(d, q)) return false;
+    }
+    return true;
+  };
+  // find_derivs at the current state (no BEM to solve)
+  if (!part_find_vels(c, p, 0, fs, true, in_capture)) return false;
+  if (order == 1) {
+    // advect_1st :247-250 - elem.move(time, dt, 1.0, elem)
+    return each([&](Device& d, PartDev& q) {
+      PartView m = view_main(q);
+      MoveArgs a = euler_args(q, m, m, m, m, dt);
+      a.ein = a.eout = prow(q.main, q.cap, kRowE);
+      return launch_move(d, d.stream, a, 1);
+    });
+  }
+  if (order == 2) {
+    // advect_2nd_ralston :366-405 - interim = copy moved by 2/3 dt; derivatives there; combine 1/4, 3/4
+    const double twothirds = 2.0 / 3.0;
+    if (!each([&](Device& d, PartDev& q) {
+          PartView m = view_main(q), i1 = view_interim(q, 0);
+          return launch_move(d, d.stream, euler_args(q, m, i1, m, m, twothirds * dt), 1);
+        }))
+      return false;
+    if (!part_find_vels(c, p, 1, fs, true, in_capture)) return false;
+    return each([&](Device& d, PartDev& q) {
+      PartView m = view_main(q), i1 = view_interim(q, 0);
+      MoveArgs a{};
+      a.n = q.n; a.dt = dt; a.wt[0] = 0.25; a.wt[1] = 0.75;
+      a.st[0] = stage_of(m); a.st[1] = stage_of(i1);
+      for (int k = 0; k < 3; ++k) { a.xin[k] = a.xout[k] = m.x[k]; a.sin[k] = a.sout[k] = m.s[k]; a.uout[k] = m.u[k]; }
+      a.ein = a.eout = prow(q.main, q.cap, kRowE);
+      return launch_move(d, d.stream, a, 2);
+    });
+  }
+  // advect_3rd :446-532 - vort1 = copy moved 1/2 dt with its own derivatives; vort2 = copy of the ORIGINAL moved
+  // 3/4 dt with vort1's velocity (and, being a one-stage move, its own = the original's gradient); combine 2/9, 3/9, 4/9
+  if (!each([&](Device& d, PartDev& q) {
+        PartView m = view_main(q), i1 = view_interim(q, 0);
+        return launch_move(d, d.stream, euler_args(q, m, i1, m, m, 0.5 * dt), 1);
+      }))
+    return false;
+  if (!part_find_vels(c, p, 1, fs, true, in_capture)) return false;
+  if (!each([&](Device& d, PartDev& q) {
+        PartView m = view_main(q), i1 = view_interim(q, 0), i2 = view_interim(q, 1);
+        return launch_move(d, d.stream, euler_args(q, m, i2, i1, m, 0.75 * dt), 1);
+      }))
+    return false;
+  if (!part_find_vels(c, p, 2, fs, true, in_capture)) return false;
+  return each([&](Device& d, PartDev& q) {
+    PartView m = view_main(q), i1 = view_interim(q, 0), i2 = view_interim(q, 1);
+    MoveArgs a{};
+    a.n = q.n; a.dt = dt; a.wt[0] = 2.0 / 9.0; a.wt[1] = 3.0 / 9.0; a.wt[2] = 4.0 / 9.0;
+    a.st[0] = stage_of(m); a.st[1] = stage_of(i1); a.st[2] = stage_of(i2);
+    for (int k = 0; k < 3; ++k) { a.xin[k] = a.xout[k] = m.x[k]; a.sin[k] = a.sout[k] = m.s[k]; a.uout[k] = m.u[k]; }
+    a.ein = a.eout = prow(q.main, q.cap, kRowE);
+    return launch_move(d, d.stream, a, 3);
+  });
+}
+
+bool part_sync_all(o3d_ctx* c, o3d_particles* p) {
+  for (size_t k = 0; k < c->dev.size(); ++k) {
+    Device& d = c->dev[k];
+    O3D_TRY(d, cudaSetDevice(d.id));
+    O3D_TRY(d, cudaStreamSynchronize(d.stream));
+  }
+  return true;
+}
+
+void part_release_graph(PartDev& q) {
+  if (q.graph) cudaGraphExecDestroy(q.graph);
+  q.graph = nullptr;
+  q.graph_n = -1;
 }
 
 bool check_counts(o3d_ctx* c, int64_t a, int64_t b) {
@@ -750,6 +1024,274 @@ int o3d_cuda_pts_on_pts_dev(o3d_ctx* c, void* stream, int64_t nrec, const void* 
   return collect(c);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Convection on the device
+int o3d_cuda_pts_finalize_dev(o3d_ctx* c, void* stream, int64_t n, float* u, float* v, float* w, float* ug,
+                              int64_t ug_stride, const double* fs) {
+  if (!c || n < 0 || n >= (int64_t(1) << 31)) return fail(c, O3D_ERR_INVALID, "pts_finalize_dev: bad context or count");
+  if (n == 0) return O3D_OK;
+  if (!u || !v || !w || !fs || (ug && ug_stride < n)) return fail(c, O3D_ERR_INVALID, "pts_finalize_dev: NULL array");
+  Device& d = c->dev[0];
+  d.launches = 0;
+  pts_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, u, v, w, ug, ug_stride, fs[0], fs[1], fs[2]);
+  d.status = cudaGetLastError();
+  d.where = "pts_finalize_kernel";
+  d.launches = 1;
+  return collect(c);
+}
+
+int o3d_cuda_pts_move_dev(o3d_ctx* c, void* stream, int64_t n, int order, double dt, const double* wt,
+                          const o3d_stage* stages, const float* const* xin, const float* const* sin, const float* ein,
+                          float* const* xout, float* const* sout, float* eout, float* const* uout) {
+  if (!c || n < 0 || n >= (int64_t(1) << 31) || order < 1 || order > 3)
+    return fail(c, O3D_ERR_INVALID, "pts_move_dev: bad context, count or order");
+  if (n == 0) return O3D_OK;
+  if (!wt || !stages || !xin || !xout || (order > 1 && !uout) || ((sin == nullptr) != (sout == nullptr)) ||
+      ((ein == nullptr) != (eout == nullptr)))
+    return fail(c, O3D_ERR_INVALID, "pts_move_dev: NULL argument");
+  MoveArgs a{};
+  a.n = n;
+  a.dt = dt;
+  for (int k = 0; k < order; ++k) {
+    a.wt[k] = wt[k];
+    for (int d = 0; d < 3; ++d) {
+      if (!stages[k].u[d]) return fail(c, O3D_ERR_INVALID, "pts_move_dev: NULL stage velocity");
+      a.st[k].u[d] = stages[k].u[d];
+    }
+    if (stages[k].ug && stages[k].ug_stride < n) return fail(c, O3D_ERR_INVALID, "pts_move_dev: gradient stride < n");
+    a.st[k].ug = stages[k].ug;
+    a.st[k].ug_stride = stages[k].ug_stride;
+  }
+  for (int d = 0; d < 3; ++d) {
+    if (!xin[d] || !xout[d] || (sin && (!sin[d] || !sout[d])) || (order > 1 && !uout[d]))
+      return fail(c, O3D_ERR_INVALID, "pts_move_dev: NULL state array");
+    a.xin[d] = xin[d]; a.xout[d] = xout[d];
+    a.sin[d] = sin ? sin[d] : nullptr; a.sout[d] = sout ? sout[d] : nullptr;
+    a.uout[d] = order > 1 ? uout[d] : nullptr;
+  }
+  a.ein = ein; a.eout = eout;
+  Device& d = c->dev[0];
+  d.launches = 0;
+  launch_move(d, (cudaStream_t)stream, a, order);
+  return collect(c);
+}
+
+int o3d_cuda_particles_create(o3d_ctx* c, o3d_particles** out) {
+  if (!c || !out) return O3D_ERR_INVALID;
+  o3d_particles* p = new o3d_particles();
+  p->dev.resize(c->dev.size());
+  *out = p;
+  return O3D_OK;
+}
+
+void o3d_cuda_particles_destroy(o3d_ctx* c, o3d_particles* p) {
+  if (!p) return;
+  for (size_t k = 0; k < p->dev.size(); ++k) {
+    if (c && k < c->dev.size()) cudaSetDevice(c->dev[k].id);
+    PartDev& q = p->dev[k];
+    part_release_graph(q);
+    for (DevBuf* b : {&q.main, &q.interim[0], &q.interim[1], &q.packed, &q.stats}) b->release();
+    for (cudaEvent_t e : {q.packed_ready, q.pulled, q.ev[0], q.ev[1]})
+      if (e) cudaEventDestroy(e);
+  }
+  delete p;
+}
+
+int64_t o3d_cuda_particles_count(const o3d_particles* p) { return p ? p->n : 0; }
+
+int o3d_cuda_particles_upload(o3d_ctx* c, o3d_particles* p, int64_t n, const float* x, const float* y, const float* z,
+                              const float* sx, const float* sy, const float* sz, const float* r, const float* elong) {
+  if (!c || !p || n < 0 || n >= (int64_t(1) << 31) || p->dev.size() != c->dev.size())
+    return fail(c, O3D_ERR_INVALID, "particles_upload: bad context, collection or count");
+  if (n > 0 && (!x || !y || !z || !sx || !sy || !sz || !r)) return fail(c, O3D_ERR_INVALID, "particles_upload: NULL array");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  if (!part_layout(c, p, n)) return collect(c);
+  const float* rows[8] = {x, y, z, sx, sy, sz, r, elong};
+  for (size_t k = 0; k < c->dev.size(); ++k) {
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    if (q.n == 0) continue;
+    auto go = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      for (int a = 0; a < 8; ++a) {
+        float* dst = prow(q.main, q.cap, a);
+        if (rows[a]) O3D_TRY(d, cudaMemcpyAsync(dst, rows[a] + q.t0, (size_t)q.n * 4, cudaMemcpyHostToDevice, d.stream));
+      }
+      if (!elong) {   // a fresh collection: elong = 1 (src/Points.h:120-127)
+        pts_fill_kernel<<<(unsigned)((q.n + 255) / 256), 256, 0, d.stream>>>(q.n, 1, prow(q.main, q.cap, kRowE), q.cap, 1.0f);
+        O3D_TRY(d, cudaGetLastError());
+        d.launches += 1;
+      }
+      pts_fill_kernel<<<(unsigned)((q.n + 255) / 256), 256, 0, d.stream>>>(q.n, 12, prow(q.main, q.cap, kRowU), q.cap, 0.0f);
+      O3D_TRY(d, cudaGetLastError());
+      d.launches += 1;
+      O3D_TRY(d, cudaStreamSynchronize(d.stream));
+      return true;
+    };
+    if (!go()) break;
+  }
+  return collect(c);
+}
+
+int o3d_cuda_particles_download(o3d_ctx* c, o3d_particles* p, float* x, float* y, float* z, float* sx, float* sy, float* sz,
+                                float* r, float* elong, float* u, float* v, float* w, float* const* ug) {
+  if (!c || !p || p->dev.size() != c->dev.size()) return fail(c, O3D_ERR_INVALID, "particles_download: bad context or collection");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  float* rows[20] = {x, y, z, sx, sy, sz, r, elong, u, v, w};
+  for (int a = 0; a < 9; ++a) rows[11 + a] = ug ? ug[a] : nullptr;
+  for (size_t k = 0; k < c->dev.size(); ++k) {
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    if (q.n == 0) continue;
+    auto go = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      for (int a = 0; a < 20; ++a)
+        if (rows[a]) O3D_TRY(d, cudaMemcpyAsync(rows[a] + q.t0, prow(q.main, q.cap, a), (size_t)q.n * 4, cudaMemcpyDeviceToHost, d.stream));
+      O3D_TRY(d, cudaStreamSynchronize(d.stream));
+      return true;
+    };
+    if (!go()) break;
+  }
+  return collect(c);
+}
+
+int o3d_cuda_particles_find_vels(o3d_ctx* c, o3d_particles* p, const double* fs, int want_grad, double* flops_out) {
+  if (!c || !p || !fs || p->dev.size() != c->dev.size()) return fail(c, O3D_ERR_INVALID, "particles_find_vels: bad argument");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  const double n = (double)p->n;
+  if (flops_out) *flops_out = want_grad ? n * (12.0 + 70.0 * n) : n * (3.0 + 33.0 * n);   // src/Influence.h:475,534
+  if (p->n == 0) return collect(c);
+  if (part_find_vels(c, p, 0, fs, want_grad != 0, false)) part_sync_all(c, p);
+  return collect(c);
+}
+
+int o3d_cuda_particles_advect(o3d_ctx* c, o3d_particles* p, int order, double time, double dt, const double* fs, int nsteps,
+                              double* flops_out) {
+  (void)time;   // no time-dependent boundary motion in a particle-only system
+  if (!c || !p || !fs || order < 1 || order > 3 || nsteps < 0 || p->dev.size() != c->dev.size())
+    return fail(c, O3D_ERR_INVALID, "particles_advect: bad argument");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  const double n = (double)p->n;
+  if (flops_out) *flops_out = (double)nsteps * order * n * (12.0 + 70.0 * n);
+  if (p->n == 0 || nsteps == 0) return collect(c);
+  const int nd = (int)c->dev.size();
+  auto run = [&]() {
+    for (int k = 0; k < nd; ++k) {
+      Device& d = c->dev[k];
+      PartDev& q = p->dev[k];
+      O3D_TRY(d, cudaSetDevice(d.id));
+      for (int i = 0; i + 1 < order; ++i) O3D_TRY(d, q.interim[i].ensure((size_t)kRowsInterim * q.cap * 4));
+      O3D_TRY(d, cudaEventRecord(q.ev[0], d.stream));
+    }
+    int done = 0;
+    // Single-device contexts replay one captured CUDA graph per step (the step is ~20 small launches around
+    // 1-3 big ones: launch-bound for small collections). The first step always runs eagerly so that every
+    // grow-only buffer has its final size before capture.
+    Device& d0 = c->dev[0];
+    PartDev& q0 = p->dev[0];
+    const bool same = c->use_graphs && q0.graph && q0.graph_n == p->n && q0.graph_order == order && q0.graph_dt == dt &&
+                      q0.graph_fs[0] == fs[0] && q0.graph_fs[1] == fs[1] && q0.graph_fs[2] == fs[2];
+    if (!same) part_release_graph(q0);
+    int per_step = 0;
+    if (!same) {
+      const int before = d0.launches;
+      if (!part_advect_once(c, p, order, dt, fs, false)) return false;
+      per_step = d0.launches - before;
+      done = 1;
+    }
+    if (nd == 1 && c->use_graphs && done < nsteps && !q0.graph_failed) {
+      if (!q0.graph) {
+        const bool prof = d0.profile;
+        d0.profile = false;
+        cudaGraph_t g = nullptr;
+        const int before = d0.launches;
+        bool ok = cudaStreamBeginCapture(d0.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+          const bool enq = part_advect_once(c, p, order, dt, fs, true);
+          ok = cudaStreamEndCapture(d0.stream, &g) == cudaSuccess && enq && g;
+        }
+        per_step = d0.launches - before;
+        d0.launches = before;
+        if (ok) ok = cudaGraphInstantiate(&q0.graph, g, 0) == cudaSuccess;
+        if (g) cudaGraphDestroy(g);
+        d0.profile = prof;
+        if (!ok) {   // still the GPU path: just launch-by-launch
+          cudaGetLastError();
+          d0.status = cudaSuccess;
+          q0.graph = nullptr;
+          q0.graph_failed = true;
+        } else {
+          q0.graph_n = p->n; q0.graph_order = order; q0.graph_dt = dt;
+          for (int a = 0; a < 3; ++a) q0.graph_fs[a] = fs[a];
+          q0.launches_per_step = per_step;
+        }
+      }
+      if (q0.graph) {
+        for (; done < nsteps; ++done) {
+          O3D_TRY(d0, cudaGraphLaunch(q0.graph, d0.stream));
+          d0.launches += q0.launches_per_step;
+        }
+      }
+    }
+    for (; done < nsteps; ++done)
+      if (!part_advect_once(c, p, order, dt, fs, false)) return false;
+    for (int k = 0; k < nd; ++k) {
+      Device& d = c->dev[k];
+      PartDev& q = p->dev[k];
+      O3D_TRY(d, cudaSetDevice(d.id));
+      O3D_TRY(d, cudaEventRecord(q.ev[1], d.stream));
+    }
+    if (!part_sync_all(c, p)) return false;
+    for (int k = 0; k < nd; ++k) {
+      Device& d = c->dev[k];
+      O3D_TRY(d, cudaEventElapsedTime(&d.kernel_ms, p->dev[k].ev[0], p->dev[k].ev[1]));
+    }
+    return true;
+  };
+  run();
+  return collect(c);
+}
+
+int o3d_cuda_particles_stats(o3d_ctx* c, o3d_particles* p, float* max_str, float* max_elong) {
+  if (!c || !p || p->dev.size() != c->dev.size()) return fail(c, O3D_ERR_INVALID, "particles_stats: bad argument");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  float ms = 0.0f, me = 0.0f;
+  for (size_t k = 0; k < c->dev.size(); ++k) {
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    if (q.n == 0) continue;
+    uint32_t h[2] = {0, 0};
+    auto go = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      O3D_TRY(d, cudaMemsetAsync(q.stats.p, 0, 2 * sizeof(uint32_t), d.stream));
+      pts_stats_kernel<<<d.sm_count * 2, 256, 0, d.stream>>>(q.n, prow(q.main, q.cap, kRowS), prow(q.main, q.cap, kRowS + 1),
+                                                             prow(q.main, q.cap, kRowS + 2), prow(q.main, q.cap, kRowE), q.stats.as<uint32_t>());
+      O3D_TRY(d, cudaGetLastError());
+      d.launches += 1;
+      O3D_TRY(d, cudaMemcpyAsync(h, q.stats.p, sizeof h, cudaMemcpyDeviceToHost, d.stream));
+      O3D_TRY(d, cudaStreamSynchronize(d.stream));
+      return true;
+    };
+    if (!go()) break;
+    float a, b;
+    std::memcpy(&a, &h[0], 4);
+    std::memcpy(&b, &h[1], 4);
+    ms = std::max(ms, a);
+    me = std::max(me, b);
+  }
+  if (max_str) *max_str = std::sqrt(ms);   // ElementBase::get_max_str returns sqrt of the largest |s|^2
+  if (max_elong) *max_elong = me;
+  return collect(c);
+}
+
+int o3d_cuda_set_graphs(o3d_ctx* c, int on) {
+  if (!c) return O3D_ERR_INVALID;
+  c->use_graphs = on != 0;
+  return O3D_OK;
+}
+
+int o3d_cuda_particles_graph_active(const o3d_particles* p) { return p && !p->dev.empty() && p->dev[0].graph != nullptr; }
 
 int o3d_cuda_set_profiling(o3d_ctx* c, int on) {
   if (!c) return O3D_ERR_INVALID;

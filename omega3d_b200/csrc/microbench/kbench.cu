@@ -48,7 +48,7 @@ int main(int argc, char** argv) {
   float* out; CHECK(cudaMalloc(&out, (size_t)n * 12 * 4));
   double* partial; CHECK(cudaMalloc(&partial, (size_t)n * 12 * 8 * 4));  // up to 4 source slices
   uint32_t* range; CHECK(cudaMalloc(&range, 16));
-  { const uint32_t init[4] = {0xffffffffu, 0u, 0xffffffffu, 0u}; CHECK(cudaMemcpy(range, init, 16, cudaMemcpyHostToDevice)); }
+  CHECK(cudaMemset(range, 0, 16));
   pp_scan_kernel<<<prop.multiProcessorCount * 4, 256>>>(npad, pk2, n, d[3], range);
   const bool no_uniform = getenv("KBENCH_NO_UNIFORM") != nullptr;   // force the general-radius path
   CHECK(cudaDeviceSynchronize());

@@ -136,8 +136,10 @@ class Points:
             self.r = np.ascontiguousarray(np.broadcast_to(np.asarray(r, f32), (self.n,)), dtype=f32).copy()
         self.u = np.zeros((3, self.n), f32)
         self.ug = None if (self.E == inert and self.M == lagrangian) else np.zeros((9, self.n), f32)
+        self.elong = None if self.E == inert else np.ones(self.n, f32)   # src/Points.h:105-109
 
     def get_n(self): return self.n
+    def get_elong(self): return self.elong
     def is_inert(self): return self.E == inert
     def get_pos(self): return self.x
     def get_str(self): return self.s

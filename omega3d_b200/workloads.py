@@ -49,6 +49,101 @@ def vortex_rings(n: int, seed: int = 7, separation: float = 0.25, major: float =
     return np.ascontiguousarray(x), np.ascontiguousarray(s), r
 
 
+# ---- the example cases' initial conditions (3Dexamples/*.json), restated from src/FlowFeature.cpp and src/Simulation.cpp ----
+def sim_scales(re: float, dt: float, overlap_ratio: float = 1.5, core_size_ratio: float = 8.0 ** 0.5):
+    """Simulation::get_hnu / get_ips / get_vdelta (src/Simulation.cpp:57-58,77-79): nominal particle spacing and core radius."""
+    f = np.float32
+    hnu = f(np.sqrt(f(f(dt) / f(re))))
+    ips = f(f(core_size_ratio) * hnu)
+    vdelta = f(f(overlap_ratio) * ips)
+    return float(ips), float(vdelta)
+
+
+def _onb(normal):
+    """normalizeVec + branchlessONB (src/MathHelper.h:186-192,220-230), float32 as the reference."""
+    f = np.float32
+    n = np.asarray(normal, f)
+    n = (n * f(1.0 / np.sqrt(np.float64(f(f(n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]))))).astype(f)
+    sign = f(np.copysign(1.0, n[2]))
+    a = f(-1.0 / np.float64(sign + n[2]))
+    b = f(f(n[0] * n[1]) * a)
+    b1 = np.array([f(1.0 + np.float64(f(f(sign * n[0]) * n[0]) * a)), f(sign * b), f(-sign * n[0])], f)
+    b2 = np.array([b, f(sign + f(f(n[1] * n[1]) * a)), f(-n[1])], f)
+    return n, b1, b2
+
+
+def singular_ring(center=(0.0, 0.0, 0.0), normal=(1.0, 0.0, 0.0), majrad=0.5, circ=1.0, ips=0.015):
+    """SingularRing::init_elements (src/FlowFeature.cpp:789-832): one row of particles on a circle, strength along
+    the tangent. Returns x, s (3,n) float32 (agrees with the reference's generator to float rounding; the fixtures
+    in tests/golden/convection.npz hold the reference's own output)."""
+    f = np.float32
+    ndiam = int(1 + (2.0 * np.pi * f(majrad)) / f(ips))
+    this_ips = f((2.0 * np.pi * f(majrad)) / f(ndiam))
+    _, b1, b2 = _onb(normal)
+    theta = (2.0 * np.pi * np.arange(ndiam, dtype=f).astype(np.float64) / float(ndiam)).astype(f)
+    ct, st = np.cos(theta).astype(f), np.sin(theta).astype(f)
+    c = np.asarray(center, f)
+    x = np.stack([c[d] + f(majrad) * (b1[d] * ct + b2[d] * st) for d in range(3)]).astype(f)
+    s = np.stack([f(this_ips * f(circ)) * (b2[d] * ct - b1[d] * st) for d in range(3)]).astype(f)
+    return np.ascontiguousarray(x), np.ascontiguousarray(s)
+
+
+def thick_ring(center=(0.0, 0.0, 0.0), normal=(1.0, 0.0, 0.0), majrad=0.5, minrad=0.05, circ=1.0, ips=0.015):
+    """ThickRing::init_elements (src/FlowFeature.cpp:941-1019): a disk of concentric particle layers swept around the ring."""
+    f = np.float32
+    nlayers = int(1 + f(minrad) / f(ips))
+    dx, dy, dl = [0.0], [0.0], [1.0]
+    for l in range(1, nlayers):
+        rad = f(l) * f(ips)
+        nl = int(1 + (2.0 * np.pi * rad) / f(ips))
+        phi = (2.0 * np.pi * np.arange(nl, dtype=f).astype(np.float64) / float(nl)).astype(f)
+        dx += list(rad * np.cos(phi).astype(f)); dy += list(rad * np.sin(phi).astype(f))
+        dl += list((f(majrad) + rad * np.cos(phi).astype(f)) / f(majrad))
+    dx, dy, dl = np.asarray(dx, f), np.asarray(dy, f), np.asarray(dl, f)
+    ndisk = dx.size
+    ndiam = int(1 + (2.0 * np.pi * f(majrad)) / f(ips))
+    this_ips = f((2.0 * np.pi * f(majrad)) / f(ndiam))
+    nrm, b1, b2 = _onb(normal)
+    theta = (2.0 * np.pi * np.arange(ndiam, dtype=f).astype(np.float64) / float(ndiam)).astype(f)
+    ct, st = np.cos(theta).astype(f)[:, None], np.sin(theta).astype(f)[:, None]
+    c = np.asarray(center, f)
+    x = np.stack([(c[d] + (f(majrad) + dx[None, :]) * (b1[d] * ct + b2[d] * st) + dy[None, :] * nrm[d]).reshape(-1) for d in range(3)]).astype(f)
+    sscale = (dl * this_ips * f(circ) / f(ndisk)).astype(f)[None, :]
+    s = np.stack([(sscale * (b2[d] * ct - b1[d] * st)).reshape(-1) for d in range(3)]).astype(f)
+    return np.ascontiguousarray(x), np.ascontiguousarray(s)
+
+
+EXAMPLES = {
+    # 3Dexamples/single_vortex_ring_nv.json (BASELINE configs[0])
+    "single_vortex_ring_nv": dict(re=71.11111450195313, dt=0.0020000000949949026, fs=(0.0, 0.0, 0.0), rings=[
+        dict(center=(0.0, 0.0, 0.0), normal=(0.8999999761581421, 0.05000000074505806, 0.10000000149011612), majrad=0.5, circ=1.0)]),
+    # 3Dexamples/leapfrog_vortex_rings_nv.json (BASELINE configs[1] before growing the particle count)
+    "leapfrog_vortex_rings_nv": dict(re=40.000003814697266, dt=0.0020000000949949026, fs=(0.0, 0.0, 0.0), rings=[
+        dict(center=(0.0, 0.0, 0.0), normal=(0.8999999761581421, 0.05000000074505806, 0.10000000149011612), majrad=0.5, circ=1.0),
+        dict(center=(-0.18000000715255737, -0.009999999776482582, -0.019999999552965164),
+             normal=(0.8999999761581421, 0.05000000074505806, 0.10000000149011612), majrad=0.5, circ=1.0)]),
+}
+
+
+def example_case(name: str, minrad: float | None = None, ips: float | None = None):
+    """Initial particles of an example input file as Simulation::add_elements builds them (src/Simulation.cpp:1009):
+    every flow structure's particles appended to one collection, radius = vdelta. `minrad` swaps the singular rings
+    for thick ones and `ips` overrides the spacing - the way the BASELINE configs grow the particle count.
+    Returns x, s (3,n), r (n,), dt, fs."""
+    case = EXAMPLES[name]
+    ips0, vdelta = sim_scales(case["re"], case["dt"])
+    if ips is not None:
+        vdelta = float(np.float32(1.5) * np.float32(ips))
+    else:
+        ips = ips0
+    xs, ss = [], []
+    for ring in case["rings"]:
+        x, s = (singular_ring(ips=ips, **ring) if minrad is None else thick_ring(ips=ips, minrad=minrad, **ring))
+        xs.append(x); ss.append(s)
+    x, s = np.concatenate(xs, axis=1), np.concatenate(ss, axis=1)
+    return np.ascontiguousarray(x), np.ascontiguousarray(s), np.full(x.shape[1], vdelta, np.float32), case["dt"], case["fs"]
+
+
 def icosphere(levels: int, radius: float = 0.5, center=(0.0, 0.0, 0.0)):
     """Triangulated sphere by midpoint refinement of an icosahedron (20 * 4^levels panels), outward
     normals. Returns nodes (nn,3) float32 interleaved and idx (np,3) uint32 - the ElementPacket layout

@@ -336,3 +336,135 @@ void o3d_oracle_pan_on_pan_coeff(int64_t nsp, const float* snx, const float* sny
 
 void o3d_oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 int o3d_oracle_max_threads(void) { return omp_get_max_threads(); }
+
+/* =====================================================================================================
+ * Convection: the O(N) steps around the influence sums. Every expression keeps the reference's operand
+ * types (S = float; dt, weights, fs = double) and its operation order; -ffp-contract=off keeps them unfused.
+ * ===================================================================================================== */
+#include <stdlib.h>
+#include <string.h>
+
+/* src/ElementBase.h:187-192 (u = fs + u * factor, factor a double) and src/Points.h:269-276 (grads * S factor) */
+void o3d_oracle_finalize_vels(int64_t n, float* u, float* ug, const double* fs) {
+  const double factor = 0.25 / M_PI;
+  for (int d = 0; d < 3; ++d)
+    for (int64_t i = 0; i < n; ++i) u[d * n + i] = (float)(fs[d] + u[d * n + i] * factor);
+  if (ug) {
+    const float ff = (float)(0.25 / M_PI);
+    for (int64_t k = 0; k < 9 * n; ++k) ug[k] = ug[k] * ff;
+  }
+}
+
+/* w . grad u, src/Points.h:316-318 */
+static inline void stretch_term(const float* ug, int64_t n, int64_t i, const float s[3], float wdu[3]) {
+  for (int k = 0; k < 3; ++k) wdu[k] = s[0] * ug[k * n + i] + s[1] * ug[(3 + k) * n + i] + s[2] * ug[(6 + k) * n + i];
+}
+
+/* Points::move with 1, 2 or 3 stages: src/ElementBase.h:253-336 (advection), src/Points.h:288-520 (stretch).
+ * u[k] is 3 x n, ug[k] 9 x n or NULL. order 1 stretches with ug[0] = the moving object's own gradient.
+ * uout (3 x n, may be NULL or alias u[0]) receives the combined velocity for order >= 2. elong may be NULL. */
+void o3d_oracle_move(int order, int64_t n, double dt, const double* wt, const float* const* u, const float* const* ug,
+                     float* x, float* s, float* elong, float* uout) {
+  const float dtf = (float)dt;
+  int have = s != NULL;
+  for (int k = 0; k < order; ++k) have = have && ug[k] != NULL;
+  for (int64_t i = 0; i < n; ++i) {
+    float un[3];
+    if (order == 1) {
+      for (int d = 0; d < 3; ++d) x[d * n + i] = (float)(x[d * n + i] + dtf * wt[0] * u[0][d * n + i]);   /* :264 */
+    } else {
+      for (int d = 0; d < 3; ++d) {
+        double c = wt[0] * u[0][d * n + i] + wt[1] * u[1][d * n + i];                                     /* :287 */
+        if (order == 3) c = c + wt[2] * u[2][d * n + i];                                                  /* :319 */
+        un[d] = (float)c;
+      }
+      for (int d = 0; d < 3; ++d) {
+        x[d * n + i] = x[d * n + i] + dtf * un[d];                                                        /* :294,326 */
+        if (uout) uout[d * n + i] = un[d];
+      }
+    }
+    if (!have) continue;
+    const float ts[3] = {s[i], s[n + i], s[2 * n + i]};
+    float wdu[3];
+    stretch_term(ug[0], n, i, ts, wdu);
+    if (order >= 2) {
+      float w2[3], w3[3] = {0, 0, 0};
+      stretch_term(ug[1], n, i, ts, w2);
+      if (order == 3) stretch_term(ug[2], n, i, ts, w3);
+      for (int k = 0; k < 3; ++k) {
+        double c = wt[0] * wdu[k] + wt[1] * w2[k];                                                        /* src/Points.h:399-402 */
+        if (order == 3) c = c + wt[2] * w3[k];                                                            /* :498-501 */
+        wdu[k] = (float)c;
+      }
+    }
+    const float circ = ts[0] * ts[0] + ts[1] * ts[1] + ts[2] * ts[2];
+    if (elong && circ > 0.0f) {
+      const float sd = ts[0] * wdu[0] + ts[1] * wdu[1] + ts[2] * wdu[2];
+      float ef;
+      if (order == 1) ef = (float)(dtf * wt[0] * sd / circ);                                              /* :321 */
+      else ef = dtf * sd / circ;                                                                          /* :407,505 */
+      elong[i] = (float)(elong[i] * (1.0 + ef));                                                          /* :322 */
+    }
+    for (int d = 0; d < 3; ++d) {
+      if (order == 1) s[d * n + i] = (float)(ts[d] + dt * wt[0] * wdu[d]);                                /* :330-332 */
+      else s[d * n + i] = (float)(ts[d] + dt * wdu[d]);                                                   /* :414-416 */
+    }
+  }
+}
+
+/* Convection::find_vels for a lone vortex-particle collection, src/Convection.h:130-184 */
+static void find_vels_one(int64_t n, const float* x, const float* s, const float* r, float* u, float* ug, const double* fs) {
+  memset(u, 0, sizeof(float) * 3 * n);
+  memset(ug, 0, sizeof(float) * 9 * n);
+  o3d_oracle_pts_on_pts(n, x, x + n, x + 2 * n, r, s, s + n, s + 2 * n, n, x, x + n, x + 2 * n, r, u, ug);
+  o3d_oracle_finalize_vels(n, u, ug, fs);
+}
+
+/* nsteps x Convection::advect: order 1 src/Convection.h:232-262, 2 (Ralston) :349-425, 3 :431-556; no boundaries,
+ * no field points. x, s 3 x n; r, elong n; u 3 x n and ug 9 x n hold what the collection holds afterwards. */
+void o3d_oracle_advect(int order, int nsteps, double dt, const double* fs, int64_t n, float* x, float* s, const float* r,
+                       float* elong, float* u, float* ug) {
+  float* x1 = malloc(sizeof(float) * 3 * n), *s1 = malloc(sizeof(float) * 3 * n);
+  float* u1 = malloc(sizeof(float) * 3 * n), *g1 = malloc(sizeof(float) * 9 * n);
+  float* x2 = malloc(sizeof(float) * 3 * n), *s2 = malloc(sizeof(float) * 3 * n);
+  float* u2 = malloc(sizeof(float) * 3 * n), *g2 = malloc(sizeof(float) * 9 * n);
+  const double one = 1.0;
+  for (int step = 0; step < nsteps; ++step) {
+    find_vels_one(n, x, s, r, u, ug, fs);
+    if (order == 1) {
+      const float* uu[1] = {u}; const float* gg[1] = {ug};
+      o3d_oracle_move(1, n, dt, &one, uu, gg, x, s, elong, NULL);
+    } else if (order == 2) {
+      memcpy(x1, x, sizeof(float) * 3 * n); memcpy(s1, s, sizeof(float) * 3 * n);
+      const float* uu[2] = {u, u1}; const float* gg[2] = {ug, g1};
+      o3d_oracle_move(1, n, (2.0 / 3.0) * dt, &one, uu, gg, x1, s1, NULL, NULL);   /* interim copy's elongation is discarded */
+      find_vels_one(n, x1, s1, r, u1, g1, fs);
+      const double wt[2] = {0.25, 0.75};
+      o3d_oracle_move(2, n, dt, wt, uu, gg, x, s, elong, u);
+    } else {
+      memcpy(x1, x, sizeof(float) * 3 * n); memcpy(s1, s, sizeof(float) * 3 * n);
+      const float* uu[3] = {u, u1, u2}; const float* gg[3] = {ug, g1, g2};
+      o3d_oracle_move(1, n, 0.5 * dt, &one, uu, gg, x1, s1, NULL, NULL);
+      find_vels_one(n, x1, s1, r, u1, g1, fs);
+      memcpy(x2, x, sizeof(float) * 3 * n); memcpy(s2, s, sizeof(float) * 3 * n);
+      const float* u_1[1] = {u1}; const float* g_0[1] = {ug};   /* vort2.move(.., vort1): vort1's velocity, its OWN (= the original's) gradient */
+      o3d_oracle_move(1, n, 0.75 * dt, &one, u_1, g_0, x2, s2, NULL, NULL);
+      find_vels_one(n, x2, s2, r, u2, g2, fs);
+      const double wt[3] = {2.0 / 9.0, 3.0 / 9.0, 4.0 / 9.0};
+      o3d_oracle_move(3, n, dt, wt, uu, gg, x, s, elong, u);
+    }
+  }
+  free(x1); free(s1); free(u1); free(g1); free(x2); free(s2); free(u2); free(g2);
+}
+
+/* ElementBase::get_max_str (src/ElementBase.h:339-351) and Points::get_max_elong (src/Points.h:523-532) */
+void o3d_oracle_stats(int64_t n, const float* s, const float* elong, float* max_str, float* max_elong) {
+  float ms = 0.0f, me = 0.0f;
+  for (int64_t i = 0; i < n; ++i) {
+    const float t = s[i] * s[i] + s[n + i] * s[n + i] + s[2 * n + i] * s[2 * n + i];
+    if (t > ms) ms = t;
+    if (elong[i] > me) me = elong[i];
+  }
+  *max_str = sqrtf(ms);
+  *max_elong = me;
+}

@@ -57,6 +57,17 @@ void o3d_oracle_pan_on_pan_coeff(int64_t nsp, const float* snx, const float* sny
                                  const uint32_t* tidx, const float* tb1, const float* tb2, const float* tnrm,
                                  const float* tarea, int self, float* coeffs);
 
+/* ---- convection: finalize_vels, Points::move, Convection::advect for a lone particle collection ---- */
+/* src/ElementBase.h:187-192, src/Points.h:265-277. u 3 x n, ug 9 x n or NULL. */
+void o3d_oracle_finalize_vels(int64_t n, float* u, float* ug, const double* fs);
+/* Points::move, 1-3 stages (src/ElementBase.h:253-336, src/Points.h:288-520). u[k] 3 x n, ug[k] 9 x n or NULL. */
+void o3d_oracle_move(int order, int64_t n, double dt, const double* wt, const float* const* u, const float* const* ug,
+                     float* x, float* s, float* elong, float* uout);
+/* nsteps x Convection::advect (src/Convection.h:232-262, :349-425, :431-556) with no boundaries / field points. */
+void o3d_oracle_advect(int order, int nsteps, double dt, const double* fs, int64_t n, float* x, float* s, const float* r,
+                       float* elong, float* u, float* ug);
+void o3d_oracle_stats(int64_t n, const float* s, const float* elong, float* max_str, float* max_elong);
+
 void o3d_oracle_set_threads(int n);
 int o3d_oracle_max_threads(void);
 

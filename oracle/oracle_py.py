@@ -15,7 +15,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_float, c_int, c_int64, c_long, c_void_p
+from ctypes import c_double, c_float, c_int, c_int64, c_long, c_void_p
 
 import numpy as np
 
@@ -58,9 +58,39 @@ class Restatement:
         L.o3d_oracle_rkernel_2vs_0p.argtypes = [c_void_p] * 3 + [c_float, c_void_p]
         L.o3d_oracle_rkernel_2vs_0pg.argtypes = [c_void_p] * 3 + [c_float, c_void_p]
         L.o3d_oracle_set_threads.argtypes = [c_int]
+        L.o3d_oracle_finalize_vels.argtypes = [c_int64, c_void_p, c_void_p, c_void_p]
+        L.o3d_oracle_move.argtypes = [c_int, c_int64, c_double, c_void_p, c_void_p, c_void_p] + [c_void_p] * 4
+        L.o3d_oracle_advect.argtypes = [c_int, c_int, c_double, c_void_p, c_int64] + [c_void_p] * 6
+        L.o3d_oracle_stats.argtypes = [c_int64] + [c_void_p] * 4
 
     def set_threads(self, n):
         self.lib.o3d_oracle_set_threads(int(n))
+
+    # ---- convection (all arrays float32, rows contiguous: x, s, u (3,n); ug (9,n); r, elong (n,)) ----
+    def finalize_vels(self, u, ug, fs):
+        fs = np.asarray(fs, np.float64)
+        self.lib.o3d_oracle_finalize_vels(u.shape[1], _p(u), _p(ug), _p(fs))
+
+    def move(self, order, dt, wt, us, ugs, x, s, elong, uout=None):
+        """Points::move with `order` stages; us/ugs: lists of (3,n) / (9,n)|None arrays; x, s, elong updated in place."""
+        n = x.shape[1]
+        wt = np.asarray(wt, np.float64)
+        pu = (c_void_p * 3)(*[u.ctypes.data if u is not None else None for u in (list(us) + [None] * 3)[:3]])
+        pg = (c_void_p * 3)(*[g.ctypes.data if g is not None else None for g in (list(ugs) + [None] * 3)[:3]])
+        self.lib.o3d_oracle_move(order, n, float(dt), _p(wt), pu, pg, _p(x), _p(s), _p(elong), _p(uout))
+
+    def advect(self, order, nsteps, dt, fs, x, s, r, elong):
+        """nsteps x Convection::advect on one particle collection; returns (u, ug) as left in the collection."""
+        n = x.shape[1]
+        fs = np.asarray(fs, np.float64)
+        u, ug = np.zeros((3, n), np.float32), np.zeros((9, n), np.float32)
+        self.lib.o3d_oracle_advect(order, nsteps, float(dt), _p(fs), n, _p(x), _p(s), _p(r), _p(elong), _p(u), _p(ug))
+        return u, ug
+
+    def stats(self, s, elong):
+        a, b = c_float(), c_float()
+        self.lib.o3d_oracle_stats(s.shape[1], _p(s), _p(elong), ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
 
     def max_threads(self):
         return int(self.lib.o3d_oracle_max_threads())
@@ -129,9 +159,64 @@ class Reference:
         L.o3d_ref_pan_on_pan_coeff.restype = c_long
         L.o3d_ref_rkernel_2vs_0p.argtypes = [c_void_p] * 3 + [c_float, c_void_p]
         L.o3d_ref_rkernel_2vs_0pg.argtypes = [c_void_p] * 3 + [c_float, c_void_p]
+        if hasattr(L, "o3d_ref_advect"):
+            L.o3d_ref_finalize_vels.argtypes = [c_int, c_void_p, c_void_p, c_void_p]
+            L.o3d_ref_move.argtypes = [c_int, c_int, c_double, c_void_p] + [c_void_p] * 10
+            L.o3d_ref_advect.argtypes = [c_int, c_int, c_double, c_void_p, c_int] + [c_void_p] * 6
+            L.o3d_ref_stats.argtypes = [c_int] + [c_void_p] * 4
+        if hasattr(L, "o3d_ref_has_features") and L.o3d_ref_has_features():
+            L.o3d_ref_singular_ring.argtypes = [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_long]
+            L.o3d_ref_singular_ring.restype = c_long
+            L.o3d_ref_thick_ring.argtypes = [c_void_p, c_void_p, c_float, c_float, c_float, c_float, c_void_p, c_void_p, c_long]
+            L.o3d_ref_thick_ring.restype = c_long
 
     def set_threads(self, n):
         self.lib.o3d_ref_set_threads(int(n))
+
+    # ---- convection through the reference's own Points<float> methods ----
+    def finalize_vels(self, u, ug, fs):
+        fs = np.asarray(fs, np.float64)
+        self.lib.o3d_ref_finalize_vels(u.shape[1], _p(u), _p(ug), _p(fs))
+
+    def move(self, order, dt, wt, us, ugs, x, s, elong, uout=None):
+        n = x.shape[1]
+        wt = np.asarray(wt, np.float64)
+        us = (list(us) + [None] * 3)[:3]
+        ugs = (list(ugs) + [None] * 3)[:3]
+        self.lib.o3d_ref_move(order, n, float(dt), _p(wt), _p(us[0]), _p(ugs[0]), _p(us[1]), _p(ugs[1]), _p(us[2]), _p(ugs[2]),
+                              _p(x), _p(s), _p(elong), _p(uout))
+
+    def advect(self, order, nsteps, dt, fs, x, s, r, elong):
+        n = x.shape[1]
+        fs = np.asarray(fs, np.float64)
+        u, ug = np.zeros((3, n), np.float32), np.zeros((9, n), np.float32)
+        self.lib.o3d_ref_advect(order, nsteps, float(dt), _p(fs), n, _p(x), _p(s), _p(r), _p(elong), _p(u), _p(ug))
+        return u, ug
+
+    def stats(self, s, elong):
+        a, b = c_float(), c_float()
+        self.lib.o3d_ref_stats(s.shape[1], _p(s), _p(elong), ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    # ---- initial conditions from the reference's feature generators (src/FlowFeature.cpp) ----
+    def has_features(self) -> bool:
+        return hasattr(self.lib, "o3d_ref_has_features") and bool(self.lib.o3d_ref_has_features())
+
+    def singular_ring(self, center, normal, majrad, circ, ips):
+        """SingularRing::init_elements(ips) -> x, s (3,n)"""
+        c, nn = _f32(center), _f32(normal)
+        n = self.lib.o3d_ref_singular_ring(_p(c), _p(nn), majrad, circ, ips, None, None, 0)
+        x, s = np.zeros((3, n), np.float32), np.zeros((3, n), np.float32)
+        self.lib.o3d_ref_singular_ring(_p(c), _p(nn), majrad, circ, ips, _p(x), _p(s), n)
+        return x, s
+
+    def thick_ring(self, center, normal, majrad, minrad, circ, ips):
+        """ThickRing::init_elements(ips) -> x, s (3,n)"""
+        c, nn = _f32(center), _f32(normal)
+        n = self.lib.o3d_ref_thick_ring(_p(c), _p(nn), majrad, minrad, circ, ips, None, None, 0)
+        x, s = np.zeros((3, n), np.float32), np.zeros((3, n), np.float32)
+        self.lib.o3d_ref_thick_ring(_p(c), _p(nn), majrad, minrad, circ, ips, _p(x), _p(s), n)
+        return x, s
 
     def max_threads(self):
         return int(self.lib.o3d_ref_max_threads())

@@ -26,8 +26,15 @@
 #include <unistd.h>
 #include <fcntl.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
+
+// Body.cpp needs the real Eigen and is not built. ElementBase::move references these two members for
+// body-bound collections; the oracle never attaches a Body (always nullptr), so they are link-time stand-ins
+// that abort if anything ever reaches them.
+void Body::transform(const double) { std::abort(); }
+Trans Body::get_transform_mat() { std::abort(); }
 
 namespace {
 
@@ -245,3 +252,169 @@ int o3d_ref_rkernel_2vs_0pg(const float* tri9, const float* str4, const float* t
 }
 
 }  // extern "C"
+
+// ---- convection: the reference's own Points<float>::zero_vels / finalize_vels / move (src/Points.h:252-520,
+// src/ElementBase.h:170-336) driven in the order Convection<S,A,I>::advect_* drives them for a system with no
+// boundaries and no field points (src/Convection.h:130-184 find_vels, :232-262 advect_1st, :349-425
+// advect_2nd_ralston, :431-556 advect_3rd). Convection.h itself cannot be compiled here (it includes BEM.h, which
+// needs the real Eigen), so only that call ORDER is restated below; every arithmetic step is the reference's.
+namespace {
+
+void load_state(Points<float>& p, int n, const float* x, const float* s, const float* elong) {
+  auto& px = p.get_pos();
+  for (int d = 0; d < 3; ++d) std::memcpy(px[d].data(), x + (size_t)d*n, sizeof(float)*n);
+  if (s) { auto& ps = p.get_str(); for (int d = 0; d < 3; ++d) std::memcpy(ps[d].data(), s + (size_t)d*n, sizeof(float)*n); }
+  if (elong) std::memcpy(p.get_elong().data(), elong, sizeof(float)*n);
+}
+void store_state(Points<float>& p, int n, float* x, float* s, float* elong) {
+  auto& px = p.get_pos();
+  for (int d = 0; d < 3; ++d) std::memcpy(x + (size_t)d*n, px[d].data(), sizeof(float)*n);
+  if (s) { auto& ps = p.get_str(); for (int d = 0; d < 3; ++d) std::memcpy(s + (size_t)d*n, ps[d].data(), sizeof(float)*n); }
+  if (elong) std::memcpy(elong, p.get_elong().data(), sizeof(float)*n);
+}
+
+// Convection::find_vels(_fs, _vort, _bdry = {}, _targets = _vort) for one collection
+void find_vels_one(Points<float>& p, const std::array<double,3>& fs, const ExecEnv& env) {
+  p.zero_vels();
+  points_affect_points<float, double>(p, p, ResultsType(velandgrad), env);
+  p.finalize_vels(fs);
+}
+
+void advect_once(Points<float>& vort, int order, double time, double dt, const std::array<double,3>& fs, const ExecEnv& env) {
+  find_vels_one(vort, fs, env);
+  if (order == 1) {
+    vort.move(time, dt, 1.0, vort);
+  } else if (order == 2) {
+    const double twothirds = 2.0/3.0;
+    Points<float> interim = vort;
+    interim.move(time, twothirds*dt, 1.0, interim);
+    find_vels_one(interim, fs, env);
+    vort.move(time, dt, 0.25, vort, 0.75, interim);
+  } else {
+    Points<float> v1 = vort;
+    v1.move(time, 0.5*dt, 1.0, v1);
+    find_vels_one(v1, fs, env);
+    Points<float> v2 = vort;
+    v2.move(time, 0.75*dt, 1.0, v1);
+    find_vels_one(v2, fs, env);
+    vort.move(time, dt, 2.0/9.0, vort, 3.0/9.0, v1, 4.0/9.0, v2);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+// Points::finalize_vels on flat arrays: u (3 x n), ug (9 x n or NULL)
+void o3d_ref_finalize_vels(int n, float* u, float* ug, const double* fs) {
+  Mute m(g_mute);
+  std::vector<float> zx(n, 0.0f), zs(3*(size_t)n, 0.0f);
+  Points<float> p = make_points(n, zx.data(), zx.data(), zx.data(), zs.data(), nullptr, active, lagrangian);
+  load_results(p, n, u, ug);
+  if (!ug) p.get_velgrad().reset();
+  p.finalize_vels({fs[0], fs[1], fs[2]});
+  store_results(p, n, u, ug);
+}
+
+// Points::move with `order` stages. State x, s (3 x n), elong (n) in/out. stage k: uk (3 x n), ugk (9 x n or NULL).
+// For order 1 the reference stretches with the moving object's OWN gradient: pass it as ug0 (u0 is the velocity of
+// the object handed to move(), which may be another collection - advect_3rd does exactly that).
+// uout (3 x n, may be NULL): this->u after the call (order >= 2 overwrites it with the combined velocity).
+void o3d_ref_move(int order, int n, double dt, const double* wt, const float* u0, const float* ug0, const float* u1,
+                  const float* ug1, const float* u2, const float* ug2, float* x, float* s, float* elong, float* uout) {
+  Mute m(g_mute);
+  std::vector<float> zx(n, 0.0f), zs(3*(size_t)n, 0.0f);
+  Points<float> self = make_points(n, zx.data(), zx.data(), zx.data(), zs.data(), nullptr, active, lagrangian);
+  load_state(self, n, x, s, elong);
+  auto stage = [&](const float* u, const float* ug) {
+    Points<float> p = make_points(n, zx.data(), zx.data(), zx.data(), zs.data(), nullptr, active, lagrangian);
+    load_results(p, n, u, ug);
+    if (!ug) p.get_velgrad().reset();
+    return p;
+  };
+  if (order == 1) {
+    Points<float> a = stage(u0, nullptr);
+    if (ug0) load_results(self, n, u0, ug0); else self.get_velgrad().reset();
+    self.move(0.0, dt, wt[0], a);
+  } else if (order == 2) {
+    load_results(self, n, u0, ug0);           // _u1 is *this in the reference's calls; keep that aliasing
+    if (!ug0) self.get_velgrad().reset();
+    Points<float> b = stage(u1, ug1);
+    self.move(0.0, dt, wt[0], self, wt[1], b);
+  } else {
+    load_results(self, n, u0, ug0);
+    if (!ug0) self.get_velgrad().reset();
+    Points<float> b = stage(u1, ug1), c = stage(u2, ug2);
+    self.move(0.0, dt, wt[0], self, wt[1], b, wt[2], c);
+  }
+  store_state(self, n, x, s, elong);
+  if (uout) { auto& u = self.get_vel(); for (int d = 0; d < 3; ++d) std::memcpy(uout + (size_t)d*n, u[d].data(), sizeof(float)*n); }
+}
+
+// nsteps x Convection::advect(order) on one vortex-particle collection. x, s (3 x n), r, elong (n) in/out;
+// u (3 x n), ug (9 x n) out = what the collection holds afterwards. With the drop-in build and accel 4 the
+// influence sums run through the CUDA arm of the patched points_affect_points.
+void o3d_ref_advect(int order, int nsteps, double dt, const double* fs, int n, float* x, float* s, const float* r,
+                    float* elong, float* u, float* ug) {
+  Mute m(g_mute);
+  Points<float> vort = make_points(n, x, x + n, x + 2*(size_t)n, s, r, active, lagrangian);
+  load_state(vort, n, x, s, elong);
+  ExecEnv env(true, true, direct, (accel_t)g_accel);
+  const std::array<double,3> f = {fs[0], fs[1], fs[2]};
+  double time = 0.0;
+  for (int k = 0; k < nsteps; ++k) { advect_once(vort, order, time, dt, f, env); time += dt; }
+  store_state(vort, n, x, s, elong);
+  store_results(vort, n, u, ug);
+}
+
+// ElementBase::get_max_str and Points::get_max_elong
+void o3d_ref_stats(int n, const float* s, const float* elong, float* max_str, float* max_elong) {
+  Mute m(g_mute);
+  std::vector<float> zx(n, 0.0f);
+  Points<float> p = make_points(n, zx.data(), zx.data(), zx.data(), s, nullptr, active, lagrangian);
+  std::memcpy(p.get_elong().data(), elong, sizeof(float)*n);
+  *max_str = p.get_max_str();
+  *max_elong = p.get_max_elong();
+}
+
+}  // extern "C"
+
+// ---- initial conditions of the example cases, from the reference's own feature generators ------------
+// (src/FlowFeature.cpp, compiled where it lies; its three GUI draw-geometry helpers live in GeomHelper.cpp, which
+// needs igl/Eigen, so they are link-time stand-ins below - init_elements never calls them).
+#ifdef O3D_REF_WITH_FEATURES
+#include "FlowFeature.h"
+#include "GeomHelper.h"
+ElementPacket<float> generate_ovoid(const float, const float, const float, const float) { return ElementPacket<float>(); }
+ElementPacket<float> generate_cuboid(const float, const float, const float, const float) { return ElementPacket<float>(); }
+ElementPacket<float> generate_torus(const float, const float, const float) { return ElementPacket<float>(); }
+
+namespace {
+long emit_packet(const ElementPacket<float>& pk, float* x, float* s, long cap) {
+  const long n = (long)pk.nelem;
+  if (!x || !s || cap < n) return n;
+  for (long i = 0; i < n; ++i)
+    for (int d = 0; d < 3; ++d) { x[(size_t)d*n + i] = pk.x[3*i + d]; s[(size_t)d*n + i] = pk.val[3*i + d]; }
+  return n;
+}
+}  // namespace
+
+extern "C" {
+int o3d_ref_has_features() { return 1; }
+// SingularRing::init_elements(ips) (src/FlowFeature.cpp:789-832) -> SoA x, s (3 x n). Returns n; call with
+// x == NULL to size the arrays.
+long o3d_ref_singular_ring(const float* c3, const float* n3, float majrad, float circ, float ips, float* x, float* s, long cap) {
+  Mute m(g_mute);
+  SingularRing r(c3[0], c3[1], c3[2], n3[0], n3[1], n3[2], majrad, circ);
+  return emit_packet(r.init_elements(ips), x, s, cap);
+}
+// ThickRing::init_elements(ips) (src/FlowFeature.cpp:941-1019)
+long o3d_ref_thick_ring(const float* c3, const float* n3, float majrad, float minrad, float circ, float ips, float* x, float* s, long cap) {
+  Mute m(g_mute);
+  ThickRing r(c3[0], c3[1], c3[2], n3[0], n3[1], n3[2], majrad, minrad, circ);
+  return emit_packet(r.init_elements(ips), x, s, cap);
+}
+}  // extern "C"
+#else
+extern "C" int o3d_ref_has_features() { return 0; }
+#endif

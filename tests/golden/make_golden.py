@@ -25,9 +25,72 @@ def cloud(n, seed, rlo, rhi):
     return x, s, W.varied_radii(n, seed + 1, rlo, rhi)
 
 
+def convection(ref):
+    """tests/golden/convection.npz: the reference's own Points::finalize_vels / move and the Convection::advect
+    sequence (oracle/ref_driver.cpp: o3d_ref_finalize_vels, o3d_ref_move, o3d_ref_advect), plus the initial
+    conditions of the two particle-only example inputs from the reference's SingularRing::init_elements."""
+    rng = np.random.Generator(np.random.MT19937(4711))
+    g = {}
+    # --- finalize_vels and the three move() overloads on random stage data ---
+    n = 257
+    x = (rng.random((3, n), dtype=f32) - f32(0.5)).astype(f32)
+    s = ((rng.random((3, n), dtype=f32) - f32(0.5)) * f32(0.01)).astype(f32)
+    s[:, 5] = 0.0   # a zero-strength particle: the elongation update is skipped (circmagsqrd == 0)
+    elong = (f32(1.0) + rng.random(n, dtype=f32) * f32(0.2)).astype(f32)
+    us = [(rng.random((3, n), dtype=f32) - f32(0.5)).astype(f32) for _ in range(3)]
+    gs = [((rng.random((9, n), dtype=f32) - f32(0.5)) * f32(4.0)).astype(f32) for _ in range(3)]
+    g.update(mv_x=x, mv_s=s, mv_elong=elong, mv_dt=np.float64(0.0125), mv_fs=np.array([0.3, -0.1, 0.05]))
+    for k in range(3):
+        g[f"mv_u{k}"], g[f"mv_g{k}"] = us[k], gs[k]
+    fu, fg = us[0].copy(), gs[0].copy()
+    ref.finalize_vels(fu, fg, g["mv_fs"])
+    g["fin_u"], g["fin_g"] = fu, fg
+    for order, wt in ((1, [0.75]), (2, [0.25, 0.75]), (3, [2.0 / 9.0, 3.0 / 9.0, 4.0 / 9.0])):
+        a, b, c = x.copy(), s.copy(), elong.copy()
+        uo = np.zeros((3, n), f32)
+        ref.move(order, float(g["mv_dt"]), wt, us[:order], gs[:order], a, b, c, uo)
+        g[f"mv{order}_wt"] = np.array(wt)
+        g[f"mv{order}_x"], g[f"mv{order}_s"], g[f"mv{order}_elong"], g[f"mv{order}_u"] = a, b, c, uo
+    # no gradients on one stage: advection only, strengths and elongation untouched
+    a, b, c = x.copy(), s.copy(), elong.copy()
+    ref.move(2, float(g["mv_dt"]), [0.5, 0.5], us[:2], [gs[0], None], a, b, c, None)
+    g["mv2ng_x"], g["mv2ng_s"], g["mv2ng_elong"] = a, b, c
+    # --- Convection::advect, all three orders, random cloud with a freestream ---
+    n = 400
+    cx, cs, cr = W.random_cloud(n, seed=777, radius=0.08)
+    cs = (cs * f32(40.0)).astype(f32)
+    g.update(adv_x=cx, adv_s=cs, adv_r=cr, adv_dt=np.float64(0.05), adv_fs=np.array([0.1, 0.0, 0.2]), adv_steps=np.int64(2))
+    for order in (1, 2, 3):
+        a, b, e = cx.copy(), cs.copy(), np.ones(n, f32)
+        u, ug = ref.advect(order, 2, 0.05, g["adv_fs"], a, b, cr, e)
+        g[f"adv{order}_x"], g[f"adv{order}_s"], g[f"adv{order}_elong"], g[f"adv{order}_u"], g[f"adv{order}_ug"] = a, b, e, u, ug
+    g["adv_stats"] = np.array(ref.stats(b, e), f32)
+    # --- the particle-only example inputs: initial conditions from the reference's generator, then 5 RK2 steps ---
+    for name in ("single_vortex_ring_nv", "leapfrog_vortex_rings_nv"):
+        case = W.EXAMPLES[name]
+        ips, vdelta = W.sim_scales(case["re"], case["dt"])
+        parts = [ref.singular_ring(r["center"], r["normal"], r["majrad"], r["circ"], ips) for r in case["rings"]]
+        x0 = np.ascontiguousarray(np.concatenate([p[0] for p in parts], axis=1))
+        s0 = np.ascontiguousarray(np.concatenate([p[1] for p in parts], axis=1))
+        r0 = np.full(x0.shape[1], vdelta, f32)
+        a, b, e = x0.copy(), s0.copy(), np.ones(x0.shape[1], f32)
+        u, ug = ref.advect(2, 5, case["dt"], case["fs"], a, b, r0, e)
+        g.update({f"{name}_x0": x0, f"{name}_s0": s0, f"{name}_r0": r0, f"{name}_x": a, f"{name}_s": b, f"{name}_elong": e,
+                  f"{name}_u": u, f"{name}_ug": ug, f"{name}_steps": np.int64(5)})
+    # a thick ring (the geometry the BASELINE configs grow to 1M-4M particles), initial condition only
+    tx, ts = ref.thick_ring((0.1, 0.0, 0.0), (0.9, 0.05, 0.1), 0.5, 0.07, 1.0, 0.03)
+    g["thick_x0"], g["thick_s0"] = tx, ts
+    np.savez_compressed(os.path.join(OUT, "convection.npz"), **g)
+
+
 def main():
     oracle_py.build(want_ref=True)
     ref = oracle_py.Reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "convection":
+        convection(ref)
+        print("convection.npz", os.path.getsize(os.path.join(OUT, "convection.npz")))
+        return
+    convection(ref)
     rng = np.random.Generator(np.random.MT19937(99))
 
     # ---- single-interaction known answers (src/Kernels.h) ----

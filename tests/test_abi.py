@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/o3d_cuda.h but not exported"
     # and the binding table covers exactly the header
     assert sorted(_lib.SYMBOLS) == names
-    assert _lib.load().o3d_cuda_abi_version() == 1
+    assert _lib.load().o3d_cuda_abi_version() == 2
 
 
 def test_library_targets_sm100a_with_bulk_copy_and_packed_fma():

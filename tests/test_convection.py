@@ -1,0 +1,87 @@
+"""CPU: the convection restatement (oracle/biot_oracle.c: finalize_vels, Points::move, Convection::advect) against the
+golden vectors minted from the reference's own Points<float> methods and the reference's feature generators
+(tests/golden/make_golden.py convection), bit for bit; the synthetic ring generators against the reference's."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+from omega3d_b200 import workloads as W
+
+f32 = np.float32
+STATE = ("x", "s", "elong")
+
+
+def test_finalize_vels_bit_identical(restate):
+    g = golden("convection.npz")
+    u, ug = g["mv_u0"].copy(), g["mv_g0"].copy()
+    restate.finalize_vels(u, ug, g["mv_fs"])
+    assert np.array_equal(u, g["fin_u"]) and np.array_equal(ug, g["fin_g"])
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_move_bit_identical(restate, order):
+    g = golden("convection.npz")
+    x, s, e = g["mv_x"].copy(), g["mv_s"].copy(), g["mv_elong"].copy()
+    uo = np.zeros_like(x)
+    restate.move(order, float(g["mv_dt"]), g[f"mv{order}_wt"], [g[f"mv_u{k}"] for k in range(order)],
+                 [g[f"mv_g{k}"] for k in range(order)], x, s, e, uo)
+    assert np.array_equal(x, g[f"mv{order}_x"]) and np.array_equal(s, g[f"mv{order}_s"]) and np.array_equal(e, g[f"mv{order}_elong"])
+    if order > 1:
+        assert np.array_equal(uo, g[f"mv{order}_u"])
+    assert e[5] == g["mv_elong"][5]   # the zero-strength particle keeps its elongation (src/Points.h:320)
+
+
+def test_move_without_gradients_only_advects(restate):
+    g = golden("convection.npz")
+    x, s, e = g["mv_x"].copy(), g["mv_s"].copy(), g["mv_elong"].copy()
+    restate.move(2, float(g["mv_dt"]), [0.5, 0.5], [g["mv_u0"], g["mv_u1"]], [g["mv_g0"], None], x, s, e, np.zeros_like(x))
+    assert np.array_equal(x, g["mv2ng_x"]) and np.array_equal(s, g["mv_s"]) and np.array_equal(e, g["mv_elong"])
+    assert np.array_equal(g["mv2ng_s"], g["mv_s"]) and np.array_equal(g["mv2ng_elong"], g["mv_elong"])
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_advect_bit_identical(restate, order):
+    g = golden("convection.npz")
+    x, s, e = g["adv_x"].copy(), g["adv_s"].copy(), np.ones(g["adv_x"].shape[1], f32)
+    u, ug = restate.advect(order, int(g["adv_steps"]), float(g["adv_dt"]), g["adv_fs"], x, s, g["adv_r"], e)
+    for name, mine in (("x", x), ("s", s), ("elong", e), ("u", u), ("ug", ug)):
+        assert np.array_equal(mine, g[f"adv{order}_{name}"]), name
+    if order == 3:
+        assert np.allclose(restate.stats(s, e), g["adv_stats"], rtol=0, atol=0)
+    # the step did something: particles moved, strengths stretched, elongation left 1
+    assert np.max(np.abs(x - g["adv_x"])) > 1e-3 and np.max(np.abs(s - g["adv_s"])) > 0 and np.max(np.abs(e - 1)) > 1e-4
+
+
+@pytest.mark.parametrize("name,n", [("single_vortex_ring_nv", 210), ("leapfrog_vortex_rings_nv", 316)])
+def test_example_cases_bit_identical(restate, name, n):
+    """BASELINE configs[0] and the shipped size of configs[1]: the reference's initial particles, five of the
+    reference's RK2 steps (src/Convection.h:349-425 with the input file's dt)."""
+    g = golden("convection.npz")
+    assert g[f"{name}_x0"].shape == (3, n)
+    x, s, e = g[f"{name}_x0"].copy(), g[f"{name}_s0"].copy(), np.ones(n, f32)
+    case = W.EXAMPLES[name]
+    u, ug = restate.advect(2, int(g[f"{name}_steps"]), case["dt"], case["fs"], x, s, g[f"{name}_r0"], e)
+    for key, mine in (("x", x), ("s", s), ("elong", e), ("u", u), ("ug", ug)):
+        assert np.array_equal(mine, g[f"{name}_{key}"]), key
+
+
+def test_ring_generators_match_reference():
+    g = golden("convection.npz")
+    for name in ("single_vortex_ring_nv", "leapfrog_vortex_rings_nv"):
+        x, s, r, dt, fs = W.example_case(name)
+        assert x.shape == g[f"{name}_x0"].shape
+        assert np.max(np.abs(x - g[f"{name}_x0"])) < 2e-7 and np.max(np.abs(s - g[f"{name}_s0"])) < 1e-8
+        assert np.array_equal(r, g[f"{name}_r0"])
+    # the survey's recorded first particle of the single ring
+    np.testing.assert_allclose(g["single_vortex_ring_nv_x0"][:, 0], [0.05650058, -0.02463886, -0.4961861], atol=1e-7)
+    x, s = W.thick_ring((0.1, 0.0, 0.0), (0.9, 0.05, 0.1), 0.5, 0.07, 1.0, 0.03)
+    assert x.shape == g["thick_x0"].shape
+    assert np.max(np.abs(x - g["thick_x0"])) < 3e-7 and np.max(np.abs(s - g["thick_s0"])) < 1e-8
+
+
+def test_reference_reproduces_convection_golden(reference_lib):
+    g = golden("convection.npz")
+    x, s, e = g["adv_x"].copy(), g["adv_s"].copy(), np.ones(g["adv_x"].shape[1], f32)
+    u, ug = reference_lib.advect(2, int(g["adv_steps"]), float(g["adv_dt"]), g["adv_fs"], x, s, g["adv_r"], e)
+    assert np.array_equal(x, g["adv2_x"]) and np.array_equal(ug, g["adv2_ug"])

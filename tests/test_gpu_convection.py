@@ -1,0 +1,247 @@
+"""GPU (-m gpu): convection on the device (omega3d_b200/csrc/convect.cuh + the resident-particle entry points of
+include/o3d_cuda.h) against the golden vectors minted from the reference's own Points<float>::move /
+finalize_vels / the Convection::advect sequence, and against the oracle restatement.
+
+The O(N) kernels are integer-like in spirit: given the same velocities they must return the same BITS as the
+reference's scalar build. A whole step inherits the influence kernel's floating-point tolerance (velocity 1e-5,
+gradient 1e-4, BASELINE.json); positions move by dt*u, so they agree far more tightly - the bounds are stated below.
+"""
+import numpy as np
+import pytest
+
+from conftest import GRAD_TOL, VEL_TOL, golden, rel_err
+
+from omega3d_b200 import convection as C
+from omega3d_b200 import influence as I
+from omega3d_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+X_TOL = 1e-6      # max |x - x_ref| / max |x_ref| after a few steps (dt * velocity error, far below VEL_TOL)
+S_TOL = 2e-5      # strengths integrate dt * (w . grad u): gradient tolerance times dt*|grad u| headroom
+E_TOL = 1e-5      # elongation
+
+
+@pytest.fixture(scope="module")
+def engine():
+    import torch
+    from omega3d_b200.device import DeviceBiotSavart
+    assert torch.cuda.is_available()
+    return DeviceBiotSavart(0)
+
+
+def dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a).copy()).cuda()
+
+
+# ---- the O(N) kernels through the *_dev entry points: bit for bit ------------------------------------------
+def test_finalize_dev_bit_exact(engine):
+    g = golden("convection.npz")
+    u, ug = dev(g["mv_u0"]), dev(g["mv_g0"])
+    engine.finalize(u, ug, g["mv_fs"])
+    assert np.array_equal(u.cpu().numpy(), g["fin_u"]) and np.array_equal(ug.cpu().numpy(), g["fin_g"])
+    u2 = dev(g["mv_u0"])
+    engine.finalize(u2, None, g["mv_fs"])
+    assert np.array_equal(u2.cpu().numpy(), g["fin_u"])
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_move_dev_bit_exact(engine, order):
+    g = golden("convection.npz")
+    x, s, e = dev(g["mv_x"]), dev(g["mv_s"]), dev(g["mv_elong"])
+    us = [dev(g[f"mv_u{k}"]) for k in range(order)]
+    gs = [dev(g[f"mv_g{k}"]) for k in range(order)]
+    uo = dev(np.zeros_like(g["mv_x"]))
+    engine.move(order, float(g["mv_dt"]), g[f"mv{order}_wt"], us, gs, x, s, e, x, s, e, uo)
+    assert np.array_equal(x.cpu().numpy(), g[f"mv{order}_x"])
+    assert np.array_equal(s.cpu().numpy(), g[f"mv{order}_s"])
+    assert np.array_equal(e.cpu().numpy(), g[f"mv{order}_elong"])
+    if order > 1:
+        assert np.array_equal(uo.cpu().numpy(), g[f"mv{order}_u"])
+
+
+def test_move_dev_out_of_place_and_no_gradients(engine):
+    g = golden("convection.npz")
+    x, s, e = dev(g["mv_x"]), dev(g["mv_s"]), dev(g["mv_elong"])
+    xo, so, eo = dev(np.zeros_like(g["mv_x"])), dev(np.zeros_like(g["mv_s"])), dev(np.zeros_like(g["mv_elong"]))
+    uo = dev(np.zeros_like(g["mv_x"]))
+    engine.move(2, float(g["mv_dt"]), [0.5, 0.5], [dev(g["mv_u0"]), dev(g["mv_u1"])], [dev(g["mv_g0"]), None], x, s, e, xo, so, eo, uo)
+    assert np.array_equal(xo.cpu().numpy(), g["mv2ng_x"])
+    assert np.array_equal(so.cpu().numpy(), g["mv_s"]) and np.array_equal(eo.cpu().numpy(), g["mv_elong"])
+    assert np.array_equal(x.cpu().numpy(), g["mv_x"])   # inputs untouched
+
+
+def test_move_dev_rejects_bad_arguments(engine):
+    g = golden("convection.npz")
+    x = dev(g["mv_x"])
+    with pytest.raises(I.O3DError):
+        engine.move(0, 0.1, [1.0], [x], [None], x, x, None, x, x, None)
+
+
+# ---- whole steps on resident particles ---------------------------------------------------------------------
+def check_state(out, g, prefix):
+    assert rel_err(out["x"], g[prefix + "_x"]) <= X_TOL
+    assert rel_err(out["s"], g[prefix + "_s"]) <= S_TOL
+    assert rel_err(out["elong"], g[prefix + "_elong"]) <= E_TOL
+    assert rel_err(out["u"], g[prefix + "_u"]) <= VEL_TOL
+    assert rel_err(out["ug"], g[prefix + "_ug"]) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_resident_advect_golden(cuda_ctx, order):
+    g = golden("convection.npz")
+    p = C.DeviceParticles(cuda_ctx).upload(g["adv_x"], g["adv_s"], g["adv_r"])
+    fl = p.advect(order, 0.0, float(g["adv_dt"]), g["adv_fs"], int(g["adv_steps"]))
+    n = g["adv_x"].shape[1]
+    assert fl == int(g["adv_steps"]) * order * n * (12 + 70 * n)
+    out = p.download()
+    check_state(out, g, f"adv{order}")
+    assert np.array_equal(out["r"], g["adv_r"])
+    if order == 3:
+        ms, me = p.stats()
+        np.testing.assert_allclose([ms, me], g["adv_stats"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["single_vortex_ring_nv", "leapfrog_vortex_rings_nv"])
+def test_example_cases_reproduce_reference_fields(cuda_ctx, name):
+    """BASELINE configs[0] and the shipped configs[1]: the input file's particles (reference generator output from the
+    fixture), dt and freestream; five RK2 steps on the device vs five of the reference's."""
+    g = golden("convection.npz")
+    case = W.EXAMPLES[name]
+    p = C.DeviceParticles(cuda_ctx).upload(g[f"{name}_x0"], g[f"{name}_s0"], g[f"{name}_r0"])
+    p.advect(2, 0.0, case["dt"], case["fs"], int(g[f"{name}_steps"]))
+    check_state(p.download(), g, name)
+
+
+def test_graph_replay_equals_eager_bit_for_bit(cuda_ctx):
+    g = golden("convection.npz")
+    lib = cuda_ctx.lib
+    outs = []
+    for graphs in (1, 0):
+        cuda_ctx.check(lib.o3d_cuda_set_graphs(cuda_ctx.h, graphs))
+        p = C.DeviceParticles(cuda_ctx).upload(g["adv_x"], g["adv_s"], g["adv_r"])
+        p.advect(2, 0.0, 0.05, g["adv_fs"], 4)
+        assert p.graph_active() == bool(graphs)
+        p.advect(2, 0.2, 0.05, g["adv_fs"], 2)     # a second call of the same shape reuses the captured step
+        outs.append(p.download())
+        p.close()
+    cuda_ctx.check(lib.o3d_cuda_set_graphs(cuda_ctx.h, 1))
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_resident_find_vels_equals_host_entry_point(cuda_ctx):
+    """The resident path and the drop-in host-pointer path run the same kernels on the same packed records."""
+    x, s, r = W.random_cloud(3000, seed=5)
+    fs = (0.25, 0.0, -0.5)
+    p = C.DeviceParticles(cuda_ctx).upload(x, s, r)
+    p.find_vels(fs)
+    out = p.download(("u", "ug"))
+    q = I.Points(x, s, r, I.active, I.lagrangian)
+    q.zero_vels()
+    I.points_affect_points(q, q, I.ResultsType(I.velandgrad), I.ExecEnv(), cuda_ctx)
+    q.finalize_vels(fs)
+    assert np.array_equal(out["u"], q.u) and np.array_equal(out["ug"], q.ug)
+    # velocity only leaves the gradient block alone
+    p.find_vels(fs, I.velonly)
+    assert np.array_equal(p.download(("u",))["u"], q.u)
+
+
+def test_convection_mirror_of_reference_interface(cuda_ctx, restate):
+    x, s, r = W.random_cloud(500, seed=8, radius=0.1)
+    s = (s * f32(50.0)).astype(f32)
+    pts = I.Points(x, s, r, I.active, I.lagrangian)
+    conv = C.Convection(order=2, ctx=cuda_ctx)
+    conv.advect(0.0, 0.02, (0.0, 0.1, 0.0), 0.05, [pts], [], [])
+    rx, rs, re = x.copy(), s.copy(), np.ones(500, f32)
+    ru, rg = restate.advect(2, 1, 0.02, (0.0, 0.1, 0.0), rx, rs, r, re)
+    assert rel_err(pts.x, rx) <= X_TOL and rel_err(pts.s, rs) <= S_TOL and rel_err(pts.elong, re) <= E_TOL
+    assert rel_err(pts.u, ru) <= VEL_TOL and rel_err(pts.ug, rg) <= GRAD_TOL
+    with pytest.raises(I.O3DError):   # boundaries bring the BEM solve: not this path
+        conv.advect(0.0, 0.02, (0, 0, 0), 0.05, [pts], [object()], [])
+    with pytest.raises(I.O3DError):
+        C.Convection(env=I.ExecEnv(acceltype=I.accel_t.cpu_x86), ctx=cuda_ctx).advect(0.0, 0.02, (0, 0, 0), 0.05, [pts])
+
+
+def test_edge_cases(cuda_ctx):
+    p = C.DeviceParticles(cuda_ctx)
+    z3 = np.zeros((3, 0), f32)
+    p.upload(z3, z3, np.zeros(0, f32))
+    assert p.n == 0 and p.advect(2, 0.0, 0.1, (0, 0, 0), 3) == 0.0
+    # a single particle: it induces no velocity on itself, so it only rides the freestream
+    p.upload(np.array([[0.1], [0.2], [0.3]], f32), np.array([[1.0], [0.0], [0.0]], f32), np.array([0.1], f32))
+    p.advect(2, 0.0, 0.5, (1.0, 2.0, 3.0), 2)
+    out = p.download()
+    np.testing.assert_allclose(out["x"][:, 0], [1.1, 2.2, 3.3], rtol=1e-6)
+    assert np.array_equal(out["s"][:, 0], [1.0, 0.0, 0.0]) and out["elong"][0] == 1.0
+    # re-upload with a different size reuses the collection (particle counts change every step in the reference)
+    x, s, r = W.random_cloud(1234, seed=3)
+    p.upload(x, s, r)
+    assert p.n == 1234
+    p.advect(1, 0.0, 0.01, (0, 0, 0), 1)
+    assert np.isfinite(p.download(("x",))["x"]).all()
+
+
+# ---- composition: resident step == the same step assembled from the *_dev blocks (the one-process-per-GPU path) ---
+@pytest.mark.parametrize("order,n", [(2, 20000), (3, 5000)])
+def test_resident_step_equals_dev_block_composition(cuda_ctx, engine, order, n):
+    from omega3d_b200.device import ShardedConvection
+    x, s, r = W.random_cloud(n, seed=21)
+    s = (s * f32(30.0)).astype(f32)
+    fs = (0.05, 0.0, 0.0)
+    p = C.DeviceParticles(cuda_ctx).upload(x, s, r)
+    p.advect(order, 0.0, 0.01, fs, 2)
+    a = p.download()
+    sc = ShardedConvection(n, 0, 1, engine, order=order)
+    import torch
+    xs, ss, rs, es = dev(x), dev(s), dev(r), torch.ones(n, device="cuda")
+    u, ug = torch.zeros((3, n), device="cuda"), torch.zeros((9, n), device="cuda")
+    for _ in range(2):
+        sc.advect(0.01, fs, xs, ss, rs, es, u, ug)
+    torch.cuda.synchronize()
+    for key, t in (("x", xs), ("s", ss), ("elong", es), ("u", u), ("ug", ug)):
+        assert np.array_equal(a[key], t.cpu().numpy()), key
+
+
+def test_euler_step_at_256k_against_oracle_sample(cuda_ctx, restate):
+    """Full-size check through a size-independent route: after one Euler step of a 262144-particle cloud, a strided
+    sample of particles must sit where the oracle's velocity (all sources, sampled targets) puts them."""
+    n = 262144
+    x, s, r = W.random_cloud(n)
+    dt = 0.05
+    p = C.DeviceParticles(cuda_ctx).upload(x, s, r)
+    p.advect(1, 0.0, dt, (0.0, 0.0, 0.0), 1)
+    out = p.download()
+    idx = W.strided_subset(n, 96)
+    tx = np.ascontiguousarray(x[:, idx]); tr = np.ascontiguousarray(r[idx])
+    ru, rg = np.zeros((3, idx.size), f32), np.zeros((9, idx.size), f32)
+    restate.pts_on_pts(x, r, s, tx, tr, ru, rg)
+    restate.finalize_vels(ru, rg, (0.0, 0.0, 0.0))
+    assert rel_err(out["u"][:, idx], ru) <= VEL_TOL and rel_err(out["ug"][:, idx], rg) <= GRAD_TOL
+    rx, rs, re = tx.copy(), np.ascontiguousarray(s[:, idx]), np.ones(idx.size, f32)
+    restate.move(1, dt, [1.0], [ru], [rg], rx, rs, re)
+    assert rel_err(out["x"][:, idx], rx) <= X_TOL and rel_err(out["s"][:, idx], rs) <= S_TOL
+    # everything not sampled at least obeys the step's invariants: finite, and displaced by exactly dt*u (bit for bit,
+    # from the downloaded velocity - the move kernel is deterministic arithmetic)
+    moved = (x.astype(np.float64) + (np.float64(f32(dt)) * 1.0) * out["u"].astype(np.float64)).astype(f32)
+    assert np.array_equal(moved, out["x"])
+
+
+def test_two_device_resident_equals_one_device(cuda_ctx):
+    lib = cuda_ctx.lib
+    if lib.o3d_cuda_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    ctx2 = I.CudaContext((0, 1))
+    x, s, r = W.random_cloud(40000, seed=77)
+    s = (s * f32(30.0)).astype(f32)
+    a = C.DeviceParticles(cuda_ctx).upload(x, s, r)
+    b = C.DeviceParticles(ctx2).upload(x, s, r)
+    for order in (2, 3):
+        a.advect(order, 0.0, 0.01, (0.1, 0.0, 0.0), 2)
+        b.advect(order, 0.0, 0.01, (0.1, 0.0, 0.0), 2)
+        oa, ob = a.download(), b.download()
+        for k in oa:
+            assert np.array_equal(oa[k], ob[k]), (order, k)   # tile-aligned blocks: the same packed stream on any device count
+    ctx2.close()
