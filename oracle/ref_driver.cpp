@@ -21,6 +21,9 @@
 #include "Collection.h"  // must precede Influence.h (ElementBase.h -> GlComputeState.h -> Collection.h cycle)
 #include "Influence.h"
 #include "Coefficients.h"
+#ifdef USE_CUDA
+#include "O3DCudaConvection.h"   // what the patched Convection.h includes (integration/omega3d_use_cuda.patch)
+#endif
 
 #include <omp.h>
 #include <unistd.h>
@@ -58,6 +61,7 @@ struct Mute {
 };
 
 bool g_mute = true;
+int g_device_convect = 1;  // drop-in build only: route whole convection steps to the device arm
 int g_accel = cpu_x86;  // accel_t handed to ExecEnv; gpu_cuda only means something in the -DUSE_CUDA (drop-in) build
 
 Points<float> make_points(int n, const float* x, const float* y, const float* z,
@@ -122,6 +126,7 @@ void o3d_ref_set_mute(int on) { g_mute = on != 0; }
 // 1 = cpu_x86 (the oracle), 4 = gpu_cuda (dispatches into integration/O3DCudaInfluence.h when built with
 // the patched headers and -DUSE_CUDA: oracle/_ref/libo3d_dropin.so)
 void o3d_ref_set_accel(int a) { g_accel = a; }
+void o3d_ref_set_device_convect(int on) { g_device_convect = on; }
 int o3d_ref_built_with_cuda() {
 #ifdef USE_CUDA
   return 1;
@@ -281,6 +286,16 @@ void find_vels_one(Points<float>& p, const std::array<double,3>& fs, const ExecE
 }
 
 void advect_once(Points<float>& vort, int order, double time, double dt, const std::array<double,3>& fs, const ExecEnv& env) {
+#ifdef USE_CUDA
+  // the arm integration/omega3d_use_cuda.patch adds to Convection::advect (src/Convection.h:218): one particle
+  // collection and nothing else -> the whole step on the device. g_device_convect = 0 keeps the reference's host
+  // sequencing below with only the influence sums on the GPU (the Influence.h arms), for comparison.
+  if (g_device_convect && env.is_internal() && env.get_instrs() == gpu_cuda &&
+      vort.get_elemt() == active && vort.get_movet() == lagrangian) {
+    (void) o3d::cuda_advect_particles(vort, order, time, dt, fs);
+    return;
+  }
+#endif
   find_vels_one(vort, fs, env);
   if (order == 1) {
     vort.move(time, dt, 1.0, vort);

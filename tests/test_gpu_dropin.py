@@ -86,3 +86,31 @@ def test_coefficients_through_reference_dispatch(dropin):
     assert rel_err(a, g["a_self"]) <= 2e-5
     a = dropin.pan_on_pan_coeff(g["n0"], g["i0"], bc, target=(g["n1"], g["i1"], bc))
     assert rel_err(a, g["a_cross"]) <= 2e-5
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_convection_through_reference_points(dropin, order):
+    """The reference's real Points<float> advanced three ways: (a) its own CPU code, (b) its own host Runge-Kutta
+    sequencing with only the influence sums on the GPU (the Influence.h arm), (c) the whole step on the device
+    (the Convection.h arm, integration/O3DCudaConvection.h). (b) and (c) must agree bit for bit - the same kernels see
+    the same inputs and the device's O(N) kernels round as the reference's do - and both must match (a) within tolerance."""
+    g = golden("convection.npz")
+    n = g["adv_x"].shape[1]
+
+    def run():
+        x, s, e = g["adv_x"].copy(), g["adv_s"].copy(), np.ones(n, f32)
+        u, ug = dropin.advect(order, 2, float(g["adv_dt"]), g["adv_fs"], x, s, g["adv_r"], e)
+        return x, s, e, u, ug
+    dropin.lib.o3d_ref_set_device_convect(0)
+    cpu, gpu_sums = both(dropin, run)
+    dropin.lib.o3d_ref_set_device_convect(1)
+    dropin.set_accel(GPU_CUDA)
+    gpu_step = run()
+    dropin.set_accel(CPU_X86)
+    for a, b in zip(cpu, [g[f"adv{order}_{k}"] for k in ("x", "s", "elong", "u", "ug")]):
+        assert np.array_equal(a, b)                  # the CPU arm of the patched build is still the reference
+    for a, b, name in zip(gpu_sums, gpu_step, ("x", "s", "elong", "u", "ug")):
+        assert np.array_equal(a, b), name
+    tol = {"x": 1e-6, "s": 2e-5, "elong": 1e-5, "u": VEL_TOL, "ug": GRAD_TOL}
+    for a, b, name in zip(gpu_step, cpu, ("x", "s", "elong", "u", "ug")):
+        assert rel_err(a, b) <= tol[name], name
