@@ -82,6 +82,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples), "reasons": [n for b, n in self.BITS.items() if self.reasons & b]}
 
 
+def dram_traffic(n, nloc):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one pp2_kernel launch, from the committed ncu --set full
+    captures (profiles/pp2_dram_traffic.json, keyed by particle count; single-GPU launches only)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "pp2_dram_traffic.json")) as f:
+            t = json.load(f)
+        return t.get(str(n)) if n == nloc else None
+    except (OSError, ValueError):
+        return None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -236,7 +247,8 @@ def run_ours(args, rank, world, local_rank):
     keep = [pinned(a) for a in (x_h, s_h, r_h, x_h[:, lo:hi], r_h[lo:hi], np.zeros((3, nloc), np.float32), np.zeros((9, nloc), np.float32))]
     hx, hs, hr, htx, htr, hu, hg = [k[1] for k in keep]
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    eng.ctx.pts_on_pts(hx, hr, hs, htx, htr, hu, hg)     # warm-up (allocations)
+    if not args.e2e_no_warmup:                           # (the 16M sweep point skips it: one call there is ~40 s)
+        eng.ctx.pts_on_pts(hx, hr, hs, htx, htr, hu, hg)     # warm-up (allocations)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -268,7 +280,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "256 MiB buffer written between timed iterations (L2 flush)"},
         "tflops_at_70": value * FLOPS_PER_INTERACTION * 1e-12,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s", "frac": achieved / peak_nominal,
-                     "traffic": None,
+                     "traffic": dram_traffic(n, nloc),
                      "peak_source": f"{props['sm_count']} SMs x 128 FP32 lanes x 2 x {f_max / 1e6:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                     "MEASURED_PEAKS.json carries no FP32 figure - the path is FP32-pipe bound (arithmetic intensity ~1e6 flop/B), "
                                     "not HBM or tensor bound",
@@ -297,6 +309,7 @@ def main():
     ap.add_argument("--particles", "--n", dest="n", type=int, default=1 << 20, help="particles (sources = targets)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="size of the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-no-warmup", action="store_true", help="time the first end-to-end call too (very large N)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

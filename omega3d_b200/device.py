@@ -109,9 +109,14 @@ class DeviceBiotSavart:
         return tf.value, ms.value
 
 
+TILE = 512  # particles per shared-memory tile of the influence kernel (csrc/o3d_common.cuh: kTile)
+
+
 def shard_bounds(n: int, world: int, rank: int):
-    """Contiguous block partition, the same rule as the C ABI's in-process partition (capi.cu: partition)."""
-    per = (n + world - 1) // world
+    """Contiguous block partition in whole 512-particle tiles - the rule of the C ABI's resident collections
+    (capi.cu: part_layout). Tile-aligned blocks make the all-gathered record stream identical to the single-GPU
+    stream (padding only at the very end), so a sharded evaluation returns the same bits for any number of ranks."""
+    per = -(-(-(-n // world)) // TILE) * TILE
     return min(n, per * rank), min(n, per * (rank + 1))
 
 
@@ -125,10 +130,10 @@ class ShardedBiotSavart:
     def __init__(self, n_total: int, rank: int, world: int, engine: DeviceBiotSavart | None):
         self.n, self.rank, self.world, self.engine = n_total, rank, world, engine
         self.lo, self.hi = shard_bounds(n_total, world, rank)
-        per = (n_total + world - 1) // world
+        per = shard_bounds(n_total, world, 0)[1] if world > 1 else n_total
         # every rank contributes the same number of records so one all_gather_into_tensor suffices;
         # short ranks pad with zero-strength records (exactly zero contribution)
-        self.rec_per_rank = int(_lib.load().o3d_cuda_packed_records(per))
+        self.rec_per_rank = int(_lib.load().o3d_cuda_packed_records(max(per, 1)))
         self.local_packed = None
         self.gathered = None
 

@@ -109,12 +109,13 @@ def test_shard_bounds_cover_every_target_once():
         spans = [shard_bounds(n, w, k) for k in range(w)]
         assert spans[0][0] == 0 and spans[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
-        assert max(hi - lo for lo, hi in spans) <= (n + w - 1) // w
+        assert max(hi - lo for lo, hi in spans) <= -(-(-(-n // w)) // 512) * 512   # whole tiles: at most 511 more than n/w
+        assert all(lo % 512 == 0 or lo == n for lo, _ in spans)
 
 
 @pytest.mark.timeout(300)
 def test_two_ranks_gloo_equal_single_rank(tmp_path):
-    n, world = 1500, 2   # 750 per rank -> 1024 records per rank, 274 of them padding
+    n, world = 1500, 2   # tile-aligned blocks: rank 0 owns [0,1024), rank 1 [1024,1500) + 548 padding records
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -123,7 +124,7 @@ def test_two_ranks_gloo_equal_single_rank(tmp_path):
     assert [int(p["nrec"]) for p in parts] == [1024, 1024]
     u = np.concatenate([p["u"] for p in parts], axis=1)
     ug = np.concatenate([p["ug"] for p in parts], axis=1)
-    assert int(parts[0]["lo"]) == 0 and int(parts[0]["hi"]) == int(parts[1]["lo"]) == 750 and int(parts[1]["hi"]) == n
+    assert int(parts[0]["lo"]) == 0 and int(parts[0]["hi"]) == int(parts[1]["lo"]) == 1024 and int(parts[1]["hi"]) == n
 
     from oracle import oracle_py
     x, s, r = W.random_cloud(n, seed=4242)
