@@ -186,6 +186,21 @@ int o3d_cuda_particles_graph_active(const o3d_particles* p);
 int o3d_cuda_particles_stats(o3d_ctx* ctx, o3d_particles* p, float* max_str, float* max_elong);
 
 
+/* ---- matrix-free BEM operator ----------------------------------------------------------- */
+/* y = A x where A is exactly the (3 ntp) x (3 nsp) block o3d_cuda_pan_on_pan_coeff builds (same arguments), applied
+ * without being stored: what the GMRES of BEM<S,I>::solve needs from A (src/BEM.h:182-202, `A * x`), for panel counts
+ * whose dense matrix no longer fits (the reference caps them for that reason, src/Simulation.cpp:675). create uploads
+ * and packs the geometry once; apply takes host vectors x (3 nsp) and y (3 ntp, overwritten). With a multi-device
+ * context the rows (target panels) are partitioned over the devices. */
+typedef struct o3d_bem_op o3d_bem_op;
+int o3d_cuda_bem_op_create(o3d_ctx* ctx, int64_t snn, const float* snx, const float* sny, const float* snz, int64_t nsp,
+                           const uint32_t* sidx, const float* sb1, const float* sb2, const float* sarea, int64_t tnn,
+                           const float* tnx, const float* tny, const float* tnz, int64_t ntp, const uint32_t* tidx,
+                           const float* tb1, const float* tb2, const float* tnrm, const float* tarea, int self,
+                           o3d_bem_op** out);
+int o3d_cuda_bem_op_apply(o3d_ctx* ctx, o3d_bem_op* op, const float* x, float* y, double* flops_out);
+void o3d_cuda_bem_op_destroy(o3d_ctx* ctx, o3d_bem_op* op);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* When on, o3d_cuda_pts_on_pts_dev brackets its dominant kernel with CUDA events on the launching stream;
  * o3d_cuda_dev_kernel_ms waits for the last such launch and returns its device time in milliseconds. */

@@ -44,6 +44,10 @@ SYMBOLS = {
     "o3d_cuda_particles_find_vels": (c_int, [c_void_p, c_void_p, POINTER(c_double), c_int, POINTER(c_double)]),
     "o3d_cuda_particles_advect": (c_int, [c_void_p, c_void_p, c_int, c_double, c_double, POINTER(c_double), c_int, POINTER(c_double)]),
     "o3d_cuda_particles_stats": (c_int, [c_void_p, c_void_p, POINTER(ctypes.c_float), POINTER(ctypes.c_float)]),
+    "o3d_cuda_bem_op_create": (c_int, [c_void_p, c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P,
+                                       c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, POINTER(c_void_p)]),
+    "o3d_cuda_bem_op_apply": (c_int, [c_void_p, c_void_p, _P, _P, POINTER(c_double)]),
+    "o3d_cuda_bem_op_destroy": (None, [c_void_p, c_void_p]),
     "o3d_cuda_set_graphs": (c_int, [c_void_p, c_int]),
     "o3d_cuda_particles_graph_active": (c_int, [c_void_p]),
     "o3d_cuda_set_profiling": (c_int, [c_void_p, c_int]),

@@ -410,18 +410,16 @@ __device__ __forceinline__ bool coef_node(const Tri& s, const Tri& t, float thr,
   return false;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) pan_coef_kernel(const PanCoefArgs p) {
-  const int64_t j = p.j0 + blockIdx.x;                              // source panel = column block
-  const int64_t i = (int64_t)blockIdx.y * BLOCK + threadIdx.x;      // target panel = row block
-  const int64_t ic = min(i, p.ntp - 1);
-  unsigned counts[2] = {0u, 0u};
-
+// The 3 x 3 influence block of source panel j on target panel i: rows = target (t1, t2, n) components, columns = the
+// three unknowns of the source panel (vortex x1, vortex x2, source), already scaled by 1/4pi, with the self-block
+// override applied. m[k][r] = A[3i + r, 3j + k]. One traversal carries all three unit strengths.
+__device__ __forceinline__ void coef_block(const PanCoefArgs& p, const int64_t i, const int64_t j, unsigned (&counts)[2],
+                                           float (&m)[3][3]) {
   const float4* sr = p.spn + (size_t)j * kPanRec;
   const float4 a0 = sr[0], a1 = sr[1], a2 = sr[2], a4 = sr[4];
   const Tri s0{a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x};
   const float sa = a4.y;
-  const float4* tr = p.tpn + (size_t)ic * kPanRec;
+  const float4* tr = p.tpn + (size_t)i * kPanRec;
   const float4 c0 = tr[0], c1 = tr[1], c2 = tr[2], c4 = tr[4];
   const Tri t0{c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w, c2.x};
   const float b1[3] = {p.sb1[j], p.sb1[p.nsp + j], p.sb1[2 * p.nsp + j]};
@@ -463,16 +461,11 @@ __global__ void __launch_bounds__(BLOCK) pan_coef_kernel(const PanCoefArgs p) {
     }
   }
 
-  if (i >= p.ntp) counts[0] = counts[1] = 0u;
-  add_counts(p.counts, counts);
-  if (i >= p.ntp) return;
-
   const float t1x = p.tb1[i], t1y = p.tb1[p.ntp + i], t1z = p.tb1[2 * p.ntp + i];
   const float t2x = p.tb2[i], t2y = p.tb2[p.ntp + i], t2z = p.tb2[2 * p.ntp + i];
   const float tnx = p.tnrm[i], tny = p.tnrm[p.ntp + i], tnz = p.tnrm[2 * p.ntp + i];
   const float fac = (float)(1.0 / (4.0 * 3.14159265358979323846));  // src/Coefficients.h:448
   const float twopi = (float)(2.0 * 3.14159265358979323846);
-  const size_t nrows = (size_t)3 * p.ntp;
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     const float ru = R.v[3 * k], rv = R.v[3 * k + 1], rw = R.v[3 * k + 2];
@@ -484,8 +477,73 @@ __global__ void __launch_bounds__(BLOCK) pan_coef_kernel(const PanCoefArgs p) {
       m1 = k == 0 ? twopi : 0.0f;
       m2 = k == 2 ? twopi : 0.0f;
     }
+    m[k][0] = m0 * fac; m[k][1] = m1 * fac; m[k][2] = m2 * fac;
+  }
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pan_coef_kernel(const PanCoefArgs p) {
+  const int64_t j = p.j0 + blockIdx.x;                              // source panel = column block
+  const int64_t i = (int64_t)blockIdx.y * BLOCK + threadIdx.x;      // target panel = row block
+  const int64_t ic = min(i, p.ntp - 1);
+  unsigned counts[2] = {0u, 0u};
+  float m[3][3];
+  coef_block(p, ic, j, counts, m);
+  if (i >= p.ntp) counts[0] = counts[1] = 0u;
+  add_counts(p.counts, counts);
+  if (i >= p.ntp) return;
+  const size_t nrows = (size_t)3 * p.ntp;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
     float* col = p.coeffs + ((size_t)(p.col_offset + (j - p.j0)) * 3 + k) * nrows + (size_t)3 * i;
-    col[0] = m0 * fac; col[1] = m1 * fac; col[2] = m2 * fac;
+    col[0] = m[k][0]; col[1] = m[k][1]; col[2] = m[k][2];
+  }
+}
+
+// Matrix-free product y = A x with the same blocks: the (3 ntp) x (3 nsp) influence matrix of
+// panels_on_panels_coeff (src/Coefficients.h:169-483) applied to a vector of panel unknowns without ever being stored -
+// what BEM<S,I>::solve's GMRES needs from A (src/BEM.h:182-202) once (3 np)^2 floats no longer fit (the reference caps
+// the panel count for that reason, src/Simulation.cpp:675). One thread owns one target panel (3 rows) and walks a slice
+// [j0, j1) of the source panels in index order, FP64 row sums; blockIdx.y slices meet in slabs added in slice order by
+// pan_matvec_finish_kernel - deterministic, no atomics.
+struct PanMatvecArgs {
+  PanCoefArgs c;         // geometry (coeffs / col_offset unused)
+  const float* x;        // 3 nsp unknowns
+  int64_t i0, ni;        // this launch's rows: target panels [i0, i0 + ni)
+  double* partial;       // [nsplit][3][ni]
+  int nsplit;
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pan_matvec_kernel(const PanMatvecArgs p) {
+  const int64_t il = (int64_t)blockIdx.x * BLOCK + threadIdx.x;   // row block local to this launch
+  const int64_t ic = p.i0 + min(il, p.ni - 1);
+  const int64_t per = (p.c.nsp + p.nsplit - 1) / p.nsplit;
+  const int64_t j0 = (int64_t)blockIdx.y * per, j1 = min(p.c.nsp, j0 + per);
+  unsigned counts[2] = {0u, 0u};
+  double y0 = 0.0, y1 = 0.0, y2 = 0.0;
+  for (int64_t j = j0; j < j1; ++j) {
+    float m[3][3];
+    coef_block(p.c, ic, j, counts, m);
+    const float x0 = p.x[3 * j], x1 = p.x[3 * j + 1], x2 = p.x[3 * j + 2];
+    y0 += (double)m[0][0] * x0 + (double)m[1][0] * x1 + (double)m[2][0] * x2;
+    y1 += (double)m[0][1] * x0 + (double)m[1][1] * x1 + (double)m[2][1] * x2;
+    y2 += (double)m[0][2] * x0 + (double)m[1][2] * x1 + (double)m[2][2] * x2;
+  }
+  if (il >= p.ni) counts[0] = counts[1] = 0u;
+  add_counts(p.c.counts, counts);
+  if (il >= p.ni) return;
+  double* slab = p.partial + (size_t)blockIdx.y * 3 * p.ni;
+  slab[il] = y0; slab[p.ni + il] = y1; slab[2 * p.ni + il] = y2;
+}
+
+__global__ void pan_matvec_finish_kernel(int nsplit, int64_t ntp, const double* partial, float* y) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntp) return;
+  for (int r = 0; r < 3; ++r) {
+    double acc = 0.0;
+    for (int s = 0; s < nsplit; ++s) acc += partial[((size_t)s * 3 + r) * ntp + i];
+    y[3 * i + r] = (float)acc;
   }
 }
 

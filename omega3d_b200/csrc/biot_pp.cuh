@@ -30,6 +30,12 @@
 #ifndef O3D_PP_TRACE
 #define O3D_PP_TRACE 1    // 1: recover the wz gradient slot from the trace-free identity instead of accumulating it
 #endif
+#ifndef O3D_PP_POW
+#define O3D_PP_POW 2      // 1: uniform-radius path forms r3 and bbb from odd powers of rs (two packed instructions fewer);
+#endif                    // 2: ... with the two constants as 32-bit broadcast operands and the searched statement order
+#ifndef O3D_PP_BODY_FILE
+#define O3D_PP_BODY_FILE "pp_body_velgrad_uni.inc"
+#endif
 #ifndef O3D_PP_MINB
 #define O3D_PP_MINB 3     // __launch_bounds__ min CTAs per SM for pp2_kernel (caps registers at 168)
 #endif
@@ -276,18 +282,53 @@ template <bool GRAD, bool UNI>
 __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
                                              const float2 tx, const float2 ty, const float2 tz, const float2 tr2,
                                              float2 (&acc)[PPAcc<GRAD>::N]) {
+#if O3D_PP_POW
+#if O3D_PP_POW == 2
+  // scalar constants: ptxas reads them as 32-bit broadcast operands (.F32) instead of 64-bit pairs
+  const float k15 = 1.5f * tr2.x, k75 = -7.5f * tr2.x;
+  const float2 tk = f2(k15, k15), tk5 = f2(k75, k75);
+#else
+  const float2 tk = __fmul2_rn(f2(1.5f, 1.5f), tr2), tk5 = __fmul2_rn(f2(-7.5f, -7.5f), tr2);   // UNI only; loop-invariant (hoisted)
+#endif
+#endif
+#if O3D_PP_POW == 2
+  // the velocity+gradient, uniform-radius body lives in its own file: its statement ORDER is machine-searched
+  // (tools/tune_order.py overrides O3D_PP_BODY_FILE with candidate orders)
+  if constexpr (GRAD && UNI) {
+#include O3D_PP_BODY_FILE
+    return;
+  }
+#endif
   const float2 dx = __fadd2_rn(tx, f2(q0.x, q0.y));
   const float2 dy = __fadd2_rn(ty, f2(q0.z, q0.w));
   const float2 dz = __fadd2_rn(tz, f2(q1.x, q1.y));
   const float2 r2 = UNI ? tr2 : __fadd2_rn(tr2, f2(q1.z, q1.w));   // UNI: tr2 already holds sr^2 + tr^2
   const float2 wx = f2(q2.x, q2.y), wy = f2(q2.z, q2.w), wz = f2(q3.x, q3.y);
   const float2 d2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, r2)));
-  const float2 top = __ffma2_rn(f2(1.5f, 1.5f), r2, d2);
   const float2 rs = f2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
   const float2 rs2 = __fmul2_rn(rs, rs);
+#if O3D_PP_POW
+  // UNI: k = 1.5 r2 is a kernel-wide constant (tk), and with top = d2 + k:
+  //   r3  = top rs^5           = rs^3 + k rs^5                  (d2 rs^5 = rs^3)
+  //   bbb = rs^5 (2 - 5 top rs^2) = rs^5 (-3 - 5 k rs^2)
+  // two packed instructions fewer than forming top, rs^4 and top*rs^2; every term keeps one sign (no cancellation).
+  float2 dn5, r3, top;
+  if constexpr (UNI) {
+    const float2 rs3 = __fmul2_rn(rs2, rs);
+    dn5 = __fmul2_rn(rs3, rs2);
+    r3 = __ffma2_rn(tk, dn5, rs3);
+  } else {
+    top = __ffma2_rn(f2(1.5f, 1.5f), r2, d2);
+    const float2 rs4 = __fmul2_rn(rs2, rs2);
+    dn5 = __fmul2_rn(rs4, rs);
+    r3 = __fmul2_rn(top, dn5);
+  }
+#else
+  const float2 top = __ffma2_rn(f2(1.5f, 1.5f), r2, d2);
   const float2 rs4 = __fmul2_rn(rs2, rs2);
   const float2 dn5 = __fmul2_rn(rs4, rs);
   const float2 r3 = __fmul2_rn(top, dn5);
+#endif
   // c = (dz wy - dy wz, dx wz - dz wx, dy wx - dx wy)
   const float2 t1 = __fmul2_rn(dy, wz);
   const float2 t2 = __fmul2_rn(dx, wz);                       // < wz
@@ -304,7 +345,13 @@ __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, c
   acc[1] = __ffma2_rn(r3, cy, acc[1]);                        // < r3
   acc[2] = __ffma2_rn(r3, cz, acc[2]);                        // < r3
   if constexpr (GRAD) {
+#if O3D_PP_POW
+    float2 bbb;
+    if constexpr (UNI) bbb = __fmul2_rn(dn5, __ffma2_rn(tk5, rs2, f2(-3.0f, -3.0f)));        // tk5 = -5 k
+    else bbb = __fmul2_rn(dn5, __ffma2_rn(f2(-5.0f, -5.0f), __fmul2_rn(top, rs2), f2(2.0f, 2.0f)));
+#else
     const float2 bbb = __fmul2_rn(dn5, __ffma2_rn(f2(-5.0f, -5.0f), __fmul2_rn(top, rs2), f2(2.0f, 2.0f)));
+#endif
     cz = __fmul2_rn(bbb, cz);                                 // < cz
     cy = __fmul2_rn(bbb, cy);                                 // < bbb
     cx = __fmul2_rn(bbb, cx);                                 // < bbb

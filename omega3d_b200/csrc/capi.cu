@@ -287,6 +287,22 @@ bool run_fma_probe(Device& d, double* tflops, double* ms_out) {
   return true;
 }
 
+// ---- matrix-free BEM operator (include/o3d_cuda.h: o3d_bem_op) ---------------------------------------
+struct BemDev {
+  DevBuf bases, spanels, tpanels, x, y, work, cnt;
+  int64_t i0 = 0, ni = 0;    // target-panel rows of this device
+};
+
+}  // namespace
+
+struct o3d_bem_op {
+  int64_t nsp = 0, ntp = 0;
+  int self = 0;
+  std::vector<BemDev> dev;
+};
+
+namespace {
+
 // ---- device-resident particle collections (include/o3d_cuda.h: o3d_particles) ------------------------
 // Row layout of one per-device state block (rows of `cap` floats; only this device's slice is stored):
 enum { kRowX = 0, kRowS = 3, kRowR = 6, kRowE = 7, kRowU = 8, kRowG = 11, kRowsMain = 20 };
@@ -1283,6 +1299,136 @@ int o3d_cuda_particles_stats(o3d_ctx* c, o3d_particles* p, float* max_str, float
   if (max_str) *max_str = std::sqrt(ms);   // ElementBase::get_max_str returns sqrt of the largest |s|^2
   if (max_elong) *max_elong = me;
   return collect(c);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Matrix-free BEM operator: y = A x with A the panels_on_panels_coeff block
+int o3d_cuda_bem_op_create(o3d_ctx* c, int64_t snn, const float* snx, const float* sny, const float* snz, int64_t nsp,
+                           const uint32_t* sidx, const float* sb1, const float* sb2, const float* sarea, int64_t tnn,
+                           const float* tnx, const float* tny, const float* tnz, int64_t ntp, const uint32_t* tidx,
+                           const float* tb1, const float* tb2, const float* tnrm, const float* tarea, int self,
+                           o3d_bem_op** out) {
+  if (!out) return fail(c, O3D_ERR_INVALID, "bem_op_create: NULL output");
+  *out = nullptr;
+  if (!check_counts(c, nsp, ntp) || nsp == 0 || ntp == 0 || snn < 0 || tnn < 0 || snn >= (int64_t(1) << 31) || tnn >= (int64_t(1) << 31))
+    return fail(c, O3D_ERR_INVALID, "bem_op_create: bad context or counts");
+  if (!snx || !sny || !snz || !sidx || !sb1 || !sb2 || !sarea || !tnx || !tny || !tnz || !tidx || !tb1 || !tb2 || !tnrm || !tarea)
+    return fail(c, O3D_ERR_INVALID, "bem_op_create: NULL array");
+  if (self && nsp != ntp) return fail(c, O3D_ERR_INVALID, "bem_op_create: self block must be square");
+  if (!valid_indices(sidx, nsp, snn) || !valid_indices(tidx, ntp, tnn)) return fail(c, O3D_ERR_INVALID, "bem_op_create: node index out of range");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  o3d_bem_op* op = new o3d_bem_op();
+  op->nsp = nsp; op->ntp = ntp; op->self = self;
+  op->dev.resize(c->dev.size());
+  const int ndev = (int)c->dev.size();
+  for (int k = 0; k < ndev; ++k) {
+    Device& d = c->dev[k];
+    BemDev& q = op->dev[k];
+    int64_t i1;
+    partition(ntp, ndev, k, &q.i0, &i1);
+    q.ni = i1 - q.i0;
+    if (q.ni == 0) continue;
+    auto go = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      cudaStream_t st = d.stream;
+      O3D_TRY(d, q.bases.ensure(((size_t)6 * nsp + (size_t)9 * ntp) * 4));
+      O3D_TRY(d, q.x.ensure((size_t)3 * nsp * 4));
+      O3D_TRY(d, q.y.ensure((size_t)3 * q.ni * 4));
+      O3D_TRY(d, q.cnt.ensure(2 * sizeof(unsigned long long)));
+      float* db = q.bases.as<float>();
+      O3D_TRY(d, cudaMemcpyAsync(db, sb1, (size_t)3 * nsp * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemcpyAsync(db + 3 * nsp, sb2, (size_t)3 * nsp * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemcpyAsync(db + 6 * nsp, tb1, (size_t)3 * ntp * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemcpyAsync(db + 6 * nsp + 3 * ntp, tb2, (size_t)3 * ntp * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemcpyAsync(db + 6 * nsp + 6 * ntp, tnrm, (size_t)3 * ntp * 4, cudaMemcpyHostToDevice, st));
+      if (!upload_panels(d, st, q.spanels, snn, snx, sny, snz, nsp, sidx, nullptr, nullptr, nullptr, sarea, nullptr)) return false;
+      O3D_TRY(d, cudaStreamSynchronize(st));   // d.geom is reused by the second upload
+      if (!upload_panels(d, st, q.tpanels, tnn, tnx, tny, tnz, ntp, tidx, nullptr, nullptr, nullptr, tarea, nullptr)) return false;
+      O3D_TRY(d, cudaStreamSynchronize(st));
+      return true;
+    };
+    if (!go()) break;
+  }
+  const int rc = collect(c);
+  if (rc != O3D_OK) {
+    o3d_cuda_bem_op_destroy(c, op);
+    return rc;
+  }
+  *out = op;
+  return O3D_OK;
+}
+
+void o3d_cuda_bem_op_destroy(o3d_ctx* c, o3d_bem_op* op) {
+  if (!op) return;
+  for (size_t k = 0; k < op->dev.size(); ++k) {
+    if (c && k < c->dev.size()) cudaSetDevice(c->dev[k].id);
+    BemDev& q = op->dev[k];
+    for (DevBuf* b : {&q.bases, &q.spanels, &q.tpanels, &q.x, &q.y, &q.work, &q.cnt}) b->release();
+  }
+  delete op;
+}
+
+int o3d_cuda_bem_op_apply(o3d_ctx* c, o3d_bem_op* op, const float* x, float* y, double* flops_out) {
+  if (!c || !op || !x || !y || op->dev.size() != c->dev.size()) return fail(c, O3D_ERR_INVALID, "bem_op_apply: bad argument");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0, d.counts[0] = d.counts[1] = 0;
+  const int64_t nsp = op->nsp, ntp = op->ntp;
+  const int ndev = (int)c->dev.size();
+  // enqueue on every device, then wait: the devices work concurrently
+  for (int k = 0; k < ndev; ++k) {
+    Device& d = c->dev[k];
+    BemDev& q = op->dev[k];
+    if (q.ni == 0) continue;
+    auto go = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      cudaStream_t st = d.stream;
+      O3D_TRY(d, cudaEventRecord(d.ev[0], st));
+      O3D_TRY(d, cudaMemcpyAsync(q.x.p, x, (size_t)3 * nsp * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemsetAsync(q.cnt.p, 0, 2 * sizeof(unsigned long long), st));
+      O3D_TRY(d, cudaEventRecord(d.ev[1], st));
+      float* db = q.bases.as<float>();
+      PanMatvecArgs a{};
+      a.c.spn = q.spanels.as<float4>();
+      a.c.tpn = q.tpanels.as<float4>();
+      a.c.nsp = nsp; a.c.ntp = ntp;
+      a.c.sb1 = db; a.c.sb2 = db + 3 * nsp;
+      a.c.tb1 = db + 6 * nsp; a.c.tb2 = db + 6 * nsp + 3 * ntp; a.c.tnrm = db + 6 * nsp + 6 * ntp;
+      a.c.self = op->self;
+      a.c.counts = q.cnt.as<unsigned long long>();
+      a.x = q.x.as<float>();
+      a.i0 = q.i0; a.ni = q.ni;
+      constexpr int B = 64;
+      const int64_t gx = (q.ni + B - 1) / B;
+      a.nsplit = pan_nsplit(d, gx, nsp);
+      O3D_TRY(d, q.work.ensure((size_t)a.nsplit * 3 * q.ni * sizeof(double)));
+      a.partial = q.work.as<double>();
+      pan_matvec_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
+      O3D_TRY(d, cudaGetLastError());
+      pan_matvec_finish_kernel<<<(unsigned)((q.ni + 255) / 256), 256, 0, st>>>(a.nsplit, q.ni, a.partial, q.y.as<float>());
+      O3D_TRY(d, cudaGetLastError());
+      d.launches += 2;
+      O3D_TRY(d, cudaEventRecord(d.ev[2], st));
+      O3D_TRY(d, cudaMemcpyAsync(y + 3 * q.i0, q.y.p, (size_t)3 * q.ni * 4, cudaMemcpyDeviceToHost, st));
+      O3D_TRY(d, cudaMemcpyAsync(d.counts, q.cnt.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      O3D_TRY(d, cudaEventRecord(d.ev[3], st));
+      return true;
+    };
+    if (!go()) break;
+  }
+  for (int k = 0; k < ndev; ++k) {
+    Device& d = c->dev[k];
+    if (op->dev[k].ni == 0 || d.status != cudaSuccess) continue;
+    cudaSetDevice(d.id);
+    finish_timing(d);
+  }
+  const int rc = collect(c);
+  if (rc == O3D_OK && flops_out) {
+    // the traversal costs what panels_on_panels_coeff costs (src/Kernels.h:1250-1292 counts, three unit strengths),
+    // plus 18 flops per block for the product
+    double leaves = 0, splits = 0;
+    for (Device& d : c->dev) leaves += (double)d.counts[0], splits += (double)d.counts[1];
+    *flops_out = 3.0 * ((leaves + splits) * 31.0 + leaves * 37.0 + splits * 42.0) + 27.0 * (double)nsp * (double)ntp;
+  }
+  return rc;
 }
 
 int o3d_cuda_set_graphs(o3d_ctx* c, int on) {

@@ -1,0 +1,200 @@
+#!/usr/bin/env python
+"""Offline search over the statement order of the packed velocity+gradient interaction (development tool, no GPU).
+
+The inner loop of pp2_kernel is bound by the FP32 pipe, and what separates one legal ordering of its ~35 packed
+instructions from another is how many of them need a third register-file cycle (tools/sass_rf_model.py; the model has
+tracked B200 measurements to ~1 % three times: profiles/r01_variants_*.txt). ptxas keeps much of the source order of
+independent instructions, so this script writes the body of pp_interact2<GRAD=true, UNI=true> as a random topological
+order of its dataflow graph (with random operand swaps of the commutative products), compiles only that kernel
+(~1.3 s) and scores the SASS with the model. The best orders are then timed on the GPU (kbench) before one is adopted.
+
+usage: tune_order.py [trials] [seed] [jobs]      -> prints the best bodies; writes /tmp/kv/best_<k>.inc
+"""
+import os
+import random
+import re
+import subprocess
+import sys
+from concurrent.futures import ProcessPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import sass_rf_model as M  # noqa: E402
+
+WORK = "/tmp/kv"
+
+# (result, op, a, b, c) - c None for 2-operand ops. Names starting with '-' are negated operands.
+# acc updates read and write acc[k]. Commutative operand pairs (a, b) may be swapped.
+STMTS = [
+    ("dx", "add", "tx", "sx", None), ("dy", "add", "ty", "sy", None), ("dz", "add", "tz", "sz", None),
+    ("a1", "fma", "dz", "dz", "r2"), ("a2", "fma", "dy", "dy", "a1"), ("d2", "fma", "dx", "dx", "a2"),
+    ("rs", "rsq", "d2", None, None),
+    ("rs2", "mul", "rs", "rs", None), ("rs3", "mul", "rs2", "rs", None), ("dn5", "mul", "rs3", "rs2", None),
+    ("r3", "fma", "tk", "dn5", "rs3"),
+    ("t1", "mul", "dy", "wz", None), ("t2", "mul", "dx", "wz", None), ("t3", "mul", "dx", "wy", None),
+    ("cx", "fma", "dz", "wy", "-t1"), ("cy", "fma", "-dz", "wx", "t2"), ("cz", "fma", "dy", "wx", "-t3"),
+    ("acc[12]", "fma", "r3", "wx", "acc[12]"), ("acc[13]", "fma", "r3", "wy", "acc[13]"), ("acc[14]", "fma", "r3", "wz", "acc[14]"),
+    ("acc[0]", "fma", "r3", "cx", "acc[0]"), ("acc[1]", "fma", "r3", "cy", "acc[1]"), ("acc[2]", "fma", "r3", "cz", "acc[2]"),
+    ("w", "fma", "tk5", "rs2", "m3"), ("bbb", "mul", "dn5", "w", None),
+    ("bx", "mul", "bbb", "cx", None), ("by", "mul", "bbb", "cy", None), ("bz", "mul", "bbb", "cz", None),
+    ("acc[3]", "fma", "dx", "bx", "acc[3]"), ("acc[4]", "fma", "dx", "by", "acc[4]"), ("acc[5]", "fma", "dx", "bz", "acc[5]"),
+    ("acc[6]", "fma", "dy", "bx", "acc[6]"), ("acc[7]", "fma", "dy", "by", "acc[7]"), ("acc[8]", "fma", "dy", "bz", "acc[8]"),
+    ("acc[9]", "fma", "dz", "bx", "acc[9]"), ("acc[10]", "fma", "dz", "by", "acc[10]"),
+]
+INPUTS = {"tx", "ty", "tz", "sx", "sy", "sz", "r2", "tk", "tk5", "m3", "wx", "wy", "wz"} | {f"acc[{k}]" for k in range(15)}
+
+PRELUDE = """    const float2 sx = f2(q0.x, q0.y), sy = f2(q0.z, q0.w), sz = f2(q1.x, q1.y);
+    const float2 wx = f2(q2.x, q2.y), wy = f2(q2.z, q2.w), wz = f2(q3.x, q3.y);
+    const float2 r2 = tr2, m3 = f2(-3.0f, -3.0f);
+"""
+
+
+def emit(order, swaps):
+    out = [PRELUDE]
+    for idx in order:
+        res, op, a, b, c = STMTS[idx]
+        if idx in swaps and op in ("mul", "fma", "add"):
+            a, b = b, a
+        def v(x):
+            return f"neg2({x[1:]})" if x.startswith("-") else x
+        decl = "" if res.startswith("acc[") else "const float2 "
+        if op == "add":
+            out.append(f"    {decl}{res} = __fadd2_rn({v(a)}, {v(b)});\n")
+        elif op == "mul":
+            out.append(f"    {decl}{res} = __fmul2_rn({v(a)}, {v(b)});\n")
+        elif op == "fma":
+            out.append(f"    {decl}{res} = __ffma2_rn({v(a)}, {v(b)}, {v(c)});\n")
+        elif op == "rsq":
+            out.append(f"    {decl}{res} = f2(rsqrt_approx({a}.x), rsqrt_approx({a}.y));\n")
+    return "".join(out)
+
+
+def deps(idx):
+    _, _, a, b, c = STMTS[idx]
+    names = {x.lstrip("-") for x in (a, b, c) if x}
+    return {k for k, st in enumerate(STMTS) if st[0] in names and not st[0].startswith("acc[")} - {idx}
+
+
+DEPS = [deps(i) for i in range(len(STMTS))]
+
+
+def operands(idx):
+    _, _, a, b, c = STMTS[idx]
+    return {x.lstrip("-") for x in (a, b) if x}
+
+
+def random_order(rng, chain_bias):
+    done, order = set(), []
+    prev = None
+    while len(order) < len(STMTS):
+        ready = [i for i in range(len(STMTS)) if i not in done and DEPS[i] <= done]
+        pick = None
+        if prev is not None and rng.random() < chain_bias:
+            share = [i for i in ready if operands(i) & operands(prev)]
+            if share:
+                pick = rng.choice(share)
+        if pick is None:
+            pick = rng.choice(ready)
+        order.append(pick)
+        done.add(pick)
+        prev = pick
+    return order
+
+
+def score(args):
+    k, order, swaps, extra = args
+    body = os.path.join(WORK, f"body_{k}.inc")
+    with open(body, "w") as f:
+        f.write(emit(order, swaps))
+    cu = os.path.join(WORK, f"one_{k}.cu")
+    with open(cu, "w") as f:
+        f.write('#include "biot_pp.cuh"\nusing namespace o3d;\ntemplate __global__ void o3d::pp2_kernel<2, true, 128>(const PPArgs);\n')
+    cubin = os.path.join(WORK, f"one_{k}.cubin")
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I" + os.path.join(ROOT, "omega3d_b200", "csrc"),
+           "-DO3D_PP_POW=2", f'-DO3D_PP_BODY_FILE="{body}"', "-Xptxas", "-v", "-cubin", cu, "-o", cubin] + extra
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        return None
+    regs = int(re.search(r"Used (\d+) registers", r.stderr).group(1))
+    spill = "0 bytes spill stores" not in r.stderr
+    ins = M.kernel_sass(cubin, "pp2_kernel")
+    j, i = M.hot_loop(ins)
+    bodyins = [t for _, t in ins[j:i + 1]]
+    n, three, tot, other = M.model(bodyins)
+    nm = sum(1 for t in bodyins if t.startswith("MUFU"))
+    per_pair = (tot + other) / (nm / 2.0)        # modelled cycles per (target, source pair)
+    return per_pair, n, three, tot + other, regs, spill
+
+
+def legal(order):
+    pos = {s: k for k, s in enumerate(order)}
+    return all(pos[d] < pos[i] for i in order for d in DEPS[i])
+
+
+def mutate(rng, order, swaps):
+    order, swaps = list(order), set(swaps)
+    for _ in range(rng.choice([1, 1, 2, 3])):
+        if rng.random() < 0.25:
+            swaps ^= {rng.randrange(len(STMTS))}
+            continue
+        for _ in range(50):
+            i = rng.randrange(len(order))
+            j = rng.randrange(len(order))
+            cand = list(order)
+            cand.insert(j, cand.pop(i))
+            if legal(cand):
+                order = cand
+                break
+    return order, frozenset(swaps)
+
+
+def climb(rounds, seed, jobs):
+    """Hill climbing from the hand-written order: `jobs` mutants per round, keep the best if it improves."""
+    rng = random.Random(seed)
+    best = (list(range(len(STMTS))), frozenset())
+    best_r = score((0, best[0], best[1], []))
+    print("start", best_r)
+    for rnd in range(rounds):
+        muts = [mutate(rng, *best) for _ in range(jobs)]
+        with ProcessPoolExecutor(jobs) as ex:
+            res = list(ex.map(score, [(k + 1, m[0], m[1], []) for k, m in enumerate(muts)]))
+        ok = [(r, m) for r, m in zip(res, muts) if r is not None and not r[5]]
+        if not ok:
+            continue
+        r, m = min(ok, key=lambda t: t[0][0])
+        if r[0] <= best_r[0]:
+            if r[0] < best_r[0]:
+                print(f"round {rnd}: {r}", flush=True)
+            best, best_r = m, r
+    with open(os.path.join(WORK, f"climb_{seed}.inc"), "w") as f:
+        f.write(emit(best[0], best[1]))
+    print("final", best_r, "->", os.path.join(WORK, f"climb_{seed}.inc"))
+
+
+def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "climb":
+        return climb(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 8)
+    trials = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    jobs = int(sys.argv[3]) if len(sys.argv) > 3 else 8
+    os.makedirs(WORK, exist_ok=True)
+    rng = random.Random(seed)
+    cands = [(0, list(range(len(STMTS))), frozenset(), [])]          # the hand-written order
+    for k in range(1, trials):
+        order = random_order(rng, rng.choice([0.0, 0.5, 0.8, 0.95]))
+        swaps = frozenset(i for i in range(len(STMTS)) if rng.random() < 0.3)
+        cands.append((k, order, swaps, []))
+    with ProcessPoolExecutor(jobs) as ex:
+        res = list(ex.map(score, cands))
+    ranked = sorted((r, c) for r, c in zip(res, cands) if r is not None and not r[5])
+    print(f"hand-written order: {res[0]}")
+    for rank, (r, c) in enumerate(ranked[:5]):
+        print(f"#{rank}: cycles/pair {r[0]:.2f}  fp32 {r[1]}  three-read {r[2]}  cycles/trip {r[3]}  regs {r[4]}   (candidate {c[0]})")
+        with open(os.path.join(WORK, f"best_{seed}_{rank}.inc"), "w") as f:
+            f.write(emit(c[1], c[2]))
+    worst = ranked[-1][0]
+    print(f"worst: cycles/pair {worst[0]:.2f}; spread {worst[0] / ranked[0][0][0] - 1:.1%} over {len(ranked)} orders")
+
+
+if __name__ == "__main__":
+    main()
