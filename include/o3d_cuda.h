@@ -201,6 +201,21 @@ int o3d_cuda_bem_op_create(o3d_ctx* ctx, int64_t snn, const float* snx, const fl
 int o3d_cuda_bem_op_apply(o3d_ctx* ctx, o3d_bem_op* op, const float* x, float* y, double* flops_out);
 void o3d_cuda_bem_op_destroy(o3d_ctx* ctx, o3d_bem_op* op);
 
+/* ---- particle x panel closest-point loops ----------------------------------------------- */
+/* Panels: nodes nx,ny,nz (nn), 3 node indices per panel, unit normals nrm as x|y|z rows of np (Surfaces::get_norm).
+ * Particle positions tx,ty,tz (nt) are updated in place; *num = how many were moved. Results are bit-identical to the
+ * reference's scalar loops (same panel order, same unfused float arithmetic).
+ * o3d_cuda_reflect_pts: reflect_panp2<S> (src/Reflect.h:194-311) - particles under the surface are mirrored out.
+ * o3d_cuda_clear_inner_pts: clear_inner_panp2<S> (src/Reflect.h:446-620) with _method = 1, the only one the
+ * reference calls - particles lower than cutoff_mult * ips above the surface are pushed out to that height.
+ * Any other method: O3D_ERR_UNSUPPORTED. */
+int o3d_cuda_reflect_pts(o3d_ctx* ctx, int64_t nn, const float* nx, const float* ny, const float* nz, int64_t np,
+                         const uint32_t* idx, const float* nrm, int64_t nt, float* tx, float* ty, float* tz,
+                         int64_t* num_reflected);
+int o3d_cuda_clear_inner_pts(o3d_ctx* ctx, int method, int64_t nn, const float* nx, const float* ny, const float* nz,
+                             int64_t np, const uint32_t* idx, const float* nrm, int64_t nt, float* tx, float* ty,
+                             float* tz, float cutoff_mult, float ips, int64_t* num_moved);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* When on, o3d_cuda_pts_on_pts_dev brackets its dominant kernel with CUDA events on the launching stream;
  * o3d_cuda_dev_kernel_ms waits for the last such launch and returns its device time in milliseconds. */

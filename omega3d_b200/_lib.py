@@ -48,6 +48,9 @@ SYMBOLS = {
                                        c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, POINTER(c_void_p)]),
     "o3d_cuda_bem_op_apply": (c_int, [c_void_p, c_void_p, _P, _P, POINTER(c_double)]),
     "o3d_cuda_bem_op_destroy": (None, [c_void_p, c_void_p]),
+    "o3d_cuda_reflect_pts": (c_int, [c_void_p, c_int64, _P, _P, _P, c_int64, _P, _P, c_int64, _P, _P, _P, POINTER(c_int64)]),
+    "o3d_cuda_clear_inner_pts": (c_int, [c_void_p, c_int, c_int64, _P, _P, _P, c_int64, _P, _P, c_int64, _P, _P, _P,
+                                         ctypes.c_float, ctypes.c_float, POINTER(c_int64)]),
     "o3d_cuda_set_graphs": (c_int, [c_void_p, c_int]),
     "o3d_cuda_particles_graph_active": (c_int, [c_void_p]),
     "o3d_cuda_set_profiling": (c_int, [c_void_p, c_int]),

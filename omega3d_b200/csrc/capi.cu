@@ -16,6 +16,7 @@
 #include "biot_panel.cuh"
 #include "biot_pp.cuh"
 #include "convect.cuh"
+#include "reflect.cuh"
 
 using namespace o3d;
 
@@ -1429,6 +1430,92 @@ int o3d_cuda_bem_op_apply(o3d_ctx* c, o3d_bem_op* op, const float* x, float* y, 
     *flops_out = 3.0 * ((leaves + splits) * 31.0 + leaves * 37.0 + splits * 42.0) + 27.0 * (double)nsp * (double)ntp;
   }
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Particle x panel closest-point loops: reflect_panp2 and clear_inner_panp2 (method 1)
+namespace {
+int closest_point_pass(o3d_ctx* c, const char* who, int mode, float cutoff, int64_t nn, const float* nx, const float* ny,
+                       const float* nz, int64_t np, const uint32_t* idx, const float* nrm, int64_t nt, float* tx, float* ty,
+                       float* tz, int64_t* num_moved) {
+  if (!check_counts(c, np, nt) || nn < 0 || nn >= (int64_t(1) << 31)) return fail(c, O3D_ERR_INVALID, std::string(who) + ": bad context or counts");
+  if (np > 0 && (!nx || !ny || !nz || !idx || !nrm)) return fail(c, O3D_ERR_INVALID, std::string(who) + ": NULL panel array");
+  if (nt > 0 && (!tx || !ty || !tz)) return fail(c, O3D_ERR_INVALID, std::string(who) + ": NULL particle array");
+  if (np > 0 && !valid_indices(idx, np, nn)) return fail(c, O3D_ERR_INVALID, std::string(who) + ": node index out of range");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0, d.counts[0] = d.counts[1] = 0;
+  if (num_moved) *num_moved = 0;
+  if (np == 0 || nt == 0) return collect(c);
+  const int ndev = (int)c->dev.size();
+  const int64_t npad = ((np + kRefTile - 1) / kRefTile) * kRefTile;
+  for_each_device(c, [&](int k) {
+    Device& d = c->dev[k];
+    int64_t t0, t1;
+    partition(nt, ndev, k, &t0, &t1);
+    const int64_t n = t1 - t0;
+    if (n == 0) return true;
+    O3D_TRY(d, cudaSetDevice(d.id));
+    cudaStream_t st = d.stream;
+    O3D_TRY(d, d.geom.ensure(((size_t)3 * nn + (size_t)6 * np) * 4));
+    O3D_TRY(d, d.panels.ensure((size_t)npad * 3 * sizeof(float4)));
+    O3D_TRY(d, d.targ.ensure((size_t)3 * n * 4));
+    float* g = d.geom.as<float>();
+    uint32_t* gidx = reinterpret_cast<uint32_t*>(g + 3 * nn);
+    float* gnrm = g + 3 * nn + 3 * np;
+    float* dt = d.targ.as<float>();
+    O3D_TRY(d, cudaEventRecord(d.ev[0], st));
+    O3D_TRY(d, cudaMemcpyAsync(g, nx, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
+    O3D_TRY(d, cudaMemcpyAsync(g + nn, ny, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
+    O3D_TRY(d, cudaMemcpyAsync(g + 2 * nn, nz, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
+    O3D_TRY(d, cudaMemcpyAsync(gidx, idx, (size_t)3 * np * 4, cudaMemcpyHostToDevice, st));
+    O3D_TRY(d, cudaMemcpyAsync(gnrm, nrm, (size_t)3 * np * 4, cudaMemcpyHostToDevice, st));
+    float* hx[3] = {tx, ty, tz};
+    for (int a = 0; a < 3; ++a) O3D_TRY(d, cudaMemcpyAsync(dt + (size_t)a * n, hx[a] + t0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (!zero_counts(d, st)) return false;
+    O3D_TRY(d, cudaEventRecord(d.ev[1], st));
+    ref_pack_kernel<<<(unsigned)((npad + 127) / 128), 128, 0, st>>>(np, npad, g, g + nn, g + 2 * nn, gidx, gnrm, d.panels.as<float4>());
+    O3D_TRY(d, cudaGetLastError());
+    ReflectArgs a{};
+    a.pan = d.panels.as<float4>();
+    a.np = np;
+    a.ntiles = (int)(npad / kRefTile);
+    a.nt = n;
+    a.tx = dt; a.ty = dt + n; a.tz = dt + 2 * n;
+    a.mode = mode;
+    a.cutoff = cutoff;
+    a.count = d.cnt.as<unsigned long long>();
+    constexpr int B = 128;
+    reflect_kernel<B><<<(unsigned)((n + B - 1) / B), B, 0, st>>>(a);
+    O3D_TRY(d, cudaGetLastError());
+    d.launches += 2;
+    O3D_TRY(d, cudaEventRecord(d.ev[2], st));
+    for (int a2 = 0; a2 < 3; ++a2) O3D_TRY(d, cudaMemcpyAsync(hx[a2] + t0, dt + (size_t)a2 * n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (!fetch_counts(d, st)) return false;
+    O3D_TRY(d, cudaEventRecord(d.ev[3], st));
+    return finish_timing(d);
+  });
+  const int rc = collect(c);
+  if (rc == O3D_OK && num_moved) {
+    unsigned long long m = 0;
+    for (Device& d : c->dev) m += d.counts[0];
+    *num_moved = (int64_t)m;
+  }
+  return rc;
+}
+}  // namespace
+
+int o3d_cuda_reflect_pts(o3d_ctx* c, int64_t nn, const float* nx, const float* ny, const float* nz, int64_t np,
+                         const uint32_t* idx, const float* nrm, int64_t nt, float* tx, float* ty, float* tz, int64_t* num_reflected) {
+  return closest_point_pass(c, "reflect_pts", 0, 0.0f, nn, nx, ny, nz, np, idx, nrm, nt, tx, ty, tz, num_reflected);
+}
+
+int o3d_cuda_clear_inner_pts(o3d_ctx* c, int method, int64_t nn, const float* nx, const float* ny, const float* nz, int64_t np,
+                             const uint32_t* idx, const float* nrm, int64_t nt, float* tx, float* ty, float* tz, float cutoff_mult,
+                             float ips, int64_t* num_moved) {
+  // method 0 (table-driven cropping of strength, src/Reflect.h:547-567) has no caller in the reference: every call site
+  // passes 1 (src/Convection.h:260-556, src/Diffusion.h:306, src/Simulation.cpp:839)
+  if (method != 1) return fail(c, O3D_ERR_UNSUPPORTED, "clear_inner_pts: only method 1 (push out, keep strength) is implemented");
+  const float cutoff = cutoff_mult * ips;   // float product, as "_cutoff_mult*_ips" with S = float (src/Reflect.h:537)
+  return closest_point_pass(c, "clear_inner_pts", 1, cutoff, nn, nx, ny, nz, np, idx, nrm, nt, tx, ty, tz, num_moved);
 }
 
 int o3d_cuda_set_graphs(o3d_ctx* c, int on) {

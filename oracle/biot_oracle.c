@@ -468,3 +468,112 @@ void o3d_oracle_stats(int64_t n, const float* s, const float* elong, float* max_
   *max_str = sqrtf(ms);
   *max_elong = me;
 }
+
+/* =====================================================================================================
+ * Particle x panel closest-point loops (src/Reflect.h). Float throughout; "1.0 / x" is a double division
+ * stored into a float, as in the reference.
+ * ===================================================================================================== */
+#include <float.h>
+
+typedef struct { float distsq, cpx, cpy, cpz; } closest_t;
+
+static inline float dot3(const float a[3], const float b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; } /* src/MathHelper.h:195-198 */
+static inline void cross3(const float a[3], const float b[3], float r[3]) {                                       /* :208-214 */
+  r[0] = a[1] * b[2] - a[2] * b[1];
+  r[1] = a[2] * b[0] - a[0] * b[2];
+  r[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+/* one edge test of panel_point_distance, src/Reflect.h:107-159 */
+static inline void closest_edge(const float a[3], const float e[3], const float dt[3], closest_t* r) {
+  const float inv = (float)(1.0 / dot3(e, e));
+  float rx[3];
+  cross3(e, dt, rx);
+  const float d = dot3(rx, rx) * inv;
+  if (d < r->distsq) {
+    const float t = dot3(e, dt) * inv;
+    if (0.0 < t && t < 1.0) {
+      r->distsq = d;
+      r->cpx = a[0] + t * e[0]; r->cpy = a[1] + t * e[1]; r->cpz = a[2] + t * e[2];
+    }
+  }
+}
+
+/* src/Reflect.h:55-188 */
+static closest_t panel_point_distance(const float s0[3], const float s1[3], const float s2[3], const float n[3], const float t[3]) {
+  closest_t r = {9.9e+9f, 0.f, 0.f, 0.f};
+  const float dt0[3] = {t[0] - s0[0], t[1] - s0[1], t[2] - s0[2]};
+  const float d0 = dot3(dt0, dt0);
+  if (d0 < r.distsq) { r.distsq = d0; r.cpx = s0[0]; r.cpy = s0[1]; r.cpz = s0[2]; }
+  const float dt1[3] = {t[0] - s1[0], t[1] - s1[1], t[2] - s1[2]};
+  const float d1 = dot3(dt1, dt1);
+  if (d1 < r.distsq) { r.distsq = d1; r.cpx = s1[0]; r.cpy = s1[1]; r.cpz = s1[2]; }
+  const float dt2[3] = {t[0] - s2[0], t[1] - s2[1], t[2] - s2[2]};
+  const float d2 = dot3(dt2, dt2);
+  if (d2 < r.distsq) { r.distsq = d2; r.cpx = s2[0]; r.cpy = s2[1]; r.cpz = s2[2]; }
+  const float e01[3] = {s1[0] - s0[0], s1[1] - s0[1], s1[2] - s0[2]};
+  closest_edge(s0, e01, dt0, &r);
+  const float e12[3] = {s2[0] - s1[0], s2[1] - s1[1], s2[2] - s1[2]};
+  closest_edge(s1, e12, dt1, &r);
+  const float e20[3] = {s0[0] - s2[0], s0[1] - s2[1], s0[2] - s2[2]};
+  closest_edge(s2, e20, dt2, &r);
+  float in[3];
+  cross3(n, e01, in); const float in01 = dot3(dt0, in);
+  cross3(n, e12, in); const float in12 = dot3(dt1, in);
+  cross3(n, e20, in); const float in20 = dot3(dt2, in);
+  if (in01 > 0.0 && in12 > 0.0 && in20 > 0.0) {
+    const float td = dot3(dt0, n);
+    r.distsq = td * td;
+    r.cpx = t[0] - n[0] * td; r.cpy = t[1] - n[1] * td; r.cpz = t[2] - n[2] * td;
+  }
+  return r;
+}
+
+/* mode 0: reflect_panp2 (src/Reflect.h:194-311); mode 1: clear_inner_panp2 with _method 1 (:446-620).
+ * nodes SoA, idx 3 per panel, nrm SoA 3 x np; x 3 x nt SoA in/out. Returns the number of particles moved. */
+int64_t o3d_oracle_closest_pass(int mode, int64_t np, const float* nx, const float* ny, const float* nz, const uint32_t* idx,
+                                const float* nrm, int64_t nt, float* x, float cutoff_mult, float ips) {
+  const float eps = 10.0f * FLT_EPSILON;
+  int64_t moved = 0;
+#pragma omp parallel for schedule(static) reduction(+ : moved)
+  for (int64_t i = 0; i < nt; ++i) {
+    const float t[3] = {x[i], x[nt + i], x[2 * nt + i]};
+    float mindist = FLT_MAX, cnt = 0.0f, dfirst = 0.0f;
+    float ns[3] = {0, 0, 0}, cs[3] = {0, 0, 0};
+    for (int64_t j = 0; j < np; ++j) {
+      const uint32_t a = idx[3 * j], b = idx[3 * j + 1], c = idx[3 * j + 2];
+      const float s0[3] = {nx[a], ny[a], nz[a]}, s1[3] = {nx[b], ny[b], nz[b]}, s2[3] = {nx[c], ny[c], nz[c]};
+      const float n[3] = {nrm[j], nrm[np + j], nrm[2 * np + j]};
+      const closest_t r = panel_point_distance(s0, s1, s2, n, t);
+      if (r.distsq < mindist - eps) {                 /* :226-234 the hit list restarts */
+        mindist = r.distsq; cnt = 1.0f; dfirst = r.distsq;
+        ns[0] = n[0]; ns[1] = n[1]; ns[2] = n[2];
+        cs[0] = r.cpx; cs[1] = r.cpy; cs[2] = r.cpz;
+      } else if (r.distsq < mindist + eps) {           /* :236-242 a tie joins it */
+        cnt = cnt + 1.0f;
+        ns[0] = ns[0] + n[0]; ns[1] = ns[1] + n[1]; ns[2] = ns[2] + n[2];
+        cs[0] = cs[0] + r.cpx; cs[1] = cs[1] + r.cpy; cs[2] = cs[2] + r.cpz;
+      }
+    }
+    if (cnt == 0.0f) continue;
+    const float len = (float)(1.0 / sqrtf(ns[0] * ns[0] + ns[1] * ns[1] + ns[2] * ns[2]));   /* normalizeVec */
+    const float m[3] = {ns[0] * len, ns[1] * len, ns[2] * len};
+    const float cp[3] = {cs[0] / cnt, cs[1] / cnt, cs[2] / cnt};
+    const float dx[3] = {t[0] - cp[0], t[1] - cp[1], t[2] - cp[2]};
+    if (mode == 0) {
+      const float dotp = dot3(m, dx);
+      if (dotp < 0.0) {
+        const float dist = sqrtf(dfirst);
+        for (int d = 0; d < 3; ++d) x[d * nt + i] = cp[d] + dist * m[d];
+        moved += 1;
+      }
+    } else {
+      const float dotp = dot3(m, dx) - cutoff_mult * ips;
+      if (dotp < 0.0) {
+        for (int d = 0; d < 3; ++d) x[d * nt + i] = t[d] - dotp * m[d];
+        moved += 1;
+      }
+    }
+  }
+  return moved;
+}

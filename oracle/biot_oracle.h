@@ -68,6 +68,11 @@ void o3d_oracle_advect(int order, int nsteps, double dt, const double* fs, int64
                        float* elong, float* u, float* ug);
 void o3d_oracle_stats(int64_t n, const float* s, const float* elong, float* max_str, float* max_elong);
 
+/* ---- particle x panel closest-point loops: reflect_panp2 (mode 0, src/Reflect.h:194-311) and clear_inner_panp2 with
+ * _method 1 (mode 1, :446-620). nodes SoA, idx 3 per panel, nrm SoA 3 x np, x 3 x nt in/out. Returns particles moved. */
+int64_t o3d_oracle_closest_pass(int mode, int64_t np, const float* nx, const float* ny, const float* nz, const uint32_t* idx,
+                                const float* nrm, int64_t nt, float* x, float cutoff_mult, float ips);
+
 void o3d_oracle_set_threads(int n);
 int o3d_oracle_max_threads(void);
 

@@ -62,6 +62,8 @@ class Restatement:
         L.o3d_oracle_move.argtypes = [c_int, c_int64, c_double, c_void_p, c_void_p, c_void_p] + [c_void_p] * 4
         L.o3d_oracle_advect.argtypes = [c_int, c_int, c_double, c_void_p, c_int64] + [c_void_p] * 6
         L.o3d_oracle_stats.argtypes = [c_int64] + [c_void_p] * 4
+        L.o3d_oracle_closest_pass.argtypes = [c_int, c_int64] + [c_void_p] * 5 + [c_int64, c_void_p, c_float, c_float]
+        L.o3d_oracle_closest_pass.restype = c_int64
 
     def set_threads(self, n):
         self.lib.o3d_oracle_set_threads(int(n))
@@ -91,6 +93,16 @@ class Restatement:
         a, b = c_float(), c_float()
         self.lib.o3d_oracle_stats(s.shape[1], _p(s), _p(elong), ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
+
+    def reflect(self, nodes, idx, nrm, x):
+        """reflect_panp2: nodes (3,nn) SoA, idx (np,3), nrm (3,np); x (3,nt) updated in place. Returns particles moved."""
+        return int(self.lib.o3d_oracle_closest_pass(0, idx.shape[0], _p(nodes[0]), _p(nodes[1]), _p(nodes[2]), _p(idx), _p(nrm),
+                                                    x.shape[1], _p(x), 0.0, 0.0))
+
+    def clear_inner(self, nodes, idx, nrm, x, cutoff_mult, ips):
+        """clear_inner_panp2 with _method 1."""
+        return int(self.lib.o3d_oracle_closest_pass(1, idx.shape[0], _p(nodes[0]), _p(nodes[1]), _p(nodes[2]), _p(idx), _p(nrm),
+                                                    x.shape[1], _p(x), cutoff_mult, ips))
 
     def max_threads(self):
         return int(self.lib.o3d_oracle_max_threads())
@@ -164,6 +176,11 @@ class Reference:
             L.o3d_ref_move.argtypes = [c_int, c_int, c_double, c_void_p] + [c_void_p] * 10
             L.o3d_ref_advect.argtypes = [c_int, c_int, c_double, c_void_p, c_int] + [c_void_p] * 6
             L.o3d_ref_stats.argtypes = [c_int] + [c_void_p] * 4
+        if hasattr(L, "o3d_ref_reflect"):
+            L.o3d_ref_reflect.argtypes = [c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
+            L.o3d_ref_reflect.restype = c_long
+            L.o3d_ref_clear_inner.argtypes = [c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_float]
+            L.o3d_ref_clear_inner.restype = c_long
         if hasattr(L, "o3d_ref_has_features") and L.o3d_ref_has_features():
             L.o3d_ref_singular_ring.argtypes = [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_long]
             L.o3d_ref_singular_ring.restype = c_long
@@ -197,6 +214,15 @@ class Reference:
         a, b = c_float(), c_float()
         self.lib.o3d_ref_stats(s.shape[1], _p(s), _p(elong), ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
+
+    # ---- particle x panel closest-point loops (src/Reflect.h) ----
+    def reflect(self, nodes_i, idx, x):
+        """reflect_panp2 on nodes_i (nn,3) interleaved, idx (np,3); x (3,nt) in place. Returns particles moved."""
+        return int(self.lib.o3d_ref_reflect(nodes_i.shape[0], _p(nodes_i), idx.shape[0], _p(idx), x.shape[1], _p(x)))
+
+    def clear_inner(self, method, nodes_i, idx, x, rad, cutoff_mult, ips):
+        return int(self.lib.o3d_ref_clear_inner(method, nodes_i.shape[0], _p(nodes_i), idx.shape[0], _p(idx), x.shape[1], _p(x),
+                                                _p(rad), cutoff_mult, ips))
 
     # ---- initial conditions from the reference's feature generators (src/FlowFeature.cpp) ----
     def has_features(self) -> bool:

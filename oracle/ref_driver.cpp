@@ -21,6 +21,8 @@
 #include "Collection.h"  // must precede Influence.h (ElementBase.h -> GlComputeState.h -> Collection.h cycle)
 #include "Influence.h"
 #include "Coefficients.h"
+#include <chrono>
+#include "Reflect.h"
 #ifdef USE_CUDA
 #include "O3DCudaConvection.h"   // what the patched Convection.h includes (integration/omega3d_use_cuda.patch)
 #endif
@@ -433,3 +435,42 @@ long o3d_ref_thick_ring(const float* c3, const float* n3, float majrad, float mi
 #else
 extern "C" int o3d_ref_has_features() { return 0; }
 #endif
+
+// ---- particle x panel closest-point loops: the reference's reflect_panp2 / clear_inner_panp2 (src/Reflect.h:194-311,
+// :446-620) on its real containers. x is 3 x nt SoA, updated in place. Returns the number of particles whose position
+// changed (the reference only prints its count).
+extern "C" {
+long o3d_ref_reflect(int nn, const float* nodes, int np, const uint32_t* idx, int nt, float* x) {
+  Mute m(g_mute);
+  std::vector<float> val(3 * (size_t)np, 0.0f), zs(3 * (size_t)nt, 0.0f);
+  Surfaces<float> surf = make_surfaces(nn, nodes, np, idx, val.data(), reactive);
+  Points<float> pts = make_points(nt, x, x + nt, x + 2 * (size_t)nt, zs.data(), nullptr, active, lagrangian);
+  reflect_panp2<float>(surf, pts);
+  long moved = 0;
+  auto& px = pts.get_pos();
+  for (int i = 0; i < nt; ++i) {
+    bool ch = false;
+    for (int d = 0; d < 3; ++d) { ch = ch || px[d][i] != x[(size_t)d*nt + i]; }
+    moved += ch;
+  }
+  for (int d = 0; d < 3; ++d) std::memcpy(x + (size_t)d*nt, px[d].data(), sizeof(float)*nt);
+  return moved;
+}
+long o3d_ref_clear_inner(int method, int nn, const float* nodes, int np, const uint32_t* idx, int nt, float* x,
+                         const float* rad, float cutoff_mult, float ips) {
+  Mute m(g_mute);
+  std::vector<float> val(3 * (size_t)np, 0.0f), zs(3 * (size_t)nt, 0.0f);
+  Surfaces<float> surf = make_surfaces(nn, nodes, np, idx, val.data(), reactive);
+  Points<float> pts = make_points(nt, x, x + nt, x + 2 * (size_t)nt, zs.data(), rad, active, lagrangian);
+  clear_inner_panp2<float>(method, surf, pts, cutoff_mult, ips);
+  long moved = 0;
+  auto& px = pts.get_pos();
+  for (int i = 0; i < nt; ++i) {
+    bool ch = false;
+    for (int d = 0; d < 3; ++d) { ch = ch || px[d][i] != x[(size_t)d*nt + i]; }
+    moved += ch;
+  }
+  for (int d = 0; d < 3; ++d) std::memcpy(x + (size_t)d*nt, px[d].data(), sizeof(float)*nt);
+  return moved;
+}
+}  // extern "C"

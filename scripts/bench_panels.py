@@ -81,6 +81,33 @@ def main():
         cpu_rate, err = npan * npan / dt, float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
     emit("panels_on_panels_coeff", npan * npan, t["kernel_ms"], ctx.flops, cpu_rate, err)
 
+    # matrix-free A x with the same blocks
+    from omega3d_b200 import bem as B
+    op = B.PanelOperator(rs, rs, ctx)
+    xv = rng.random(3 * npan, dtype=f32) - f32(0.5)
+    op.matvec(xv)
+    y = op.matvec(xv)
+    t = ctx.last_timing()
+    err = float(np.max(np.abs(y - a.reshape(3 * npan, 3 * npan).T.astype(np.float64) @ xv)) / np.max(np.abs(y)))
+    emit("bem_operator_matvec", npan * npan, t["kernel_ms"], op.flops, None, err)
+
+    # particle x panel closest-point loops: 149 flops per pair by the reference's count
+    from omega3d_b200 import reflect as R
+    for name, fn, ofn in (("reflect_panp2", lambda p_: R.reflect_panp2(rs, p_, ctx), lambda xx: res.reflect(rs.x, rs.idx, rs.nrm, xx)),
+                          ("clear_inner_panp2", lambda p_: R.clear_inner_panp2(1, rs, p_, 0.2, 0.05, ctx),
+                           lambda xx: res.clear_inner(rs.x, rs.idx, rs.nrm, xx, 0.2, 0.05))):
+        pts = I.Points(x.copy(), s, 0.05, I.active, I.lagrangian)
+        fn(I.Points(x.copy(), s, 0.05, I.active, I.lagrangian))   # warm-up
+        moved = fn(pts)
+        t = ctx.last_timing()
+        xs = np.ascontiguousarray(x[:, sel])
+        t0 = time.perf_counter(); ofn(xs); dt = time.perf_counter() - t0
+        same = bool(np.array_equal(pts.x[:, sel], xs))
+        print(json.dumps({"routine": name, "panels": npan, "particles": n, "pairs_per_s": npan * n / (t["kernel_ms"] * 1e-3),
+                          "kernel_ms": t["kernel_ms"], "gflops_reference_count": 149.0 * npan * n / (t["kernel_ms"] * 1e-3) * 1e-9,
+                          "cpu_pairs_per_s": npan * sel.size / dt, "cpu_cores": res.max_threads(), "moved": moved,
+                          "bit_identical_to_oracle_on_sample": same}), flush=True)
+
 
 if __name__ == "__main__":
     main()

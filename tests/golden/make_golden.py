@@ -83,14 +83,47 @@ def convection(ref):
     np.savez_compressed(os.path.join(OUT, "convection.npz"), **g)
 
 
+def reflect(ref):
+    """tests/golden/reflect.npz: the reference's reflect_panp2 / clear_inner_panp2 (src/Reflect.h) on its real
+    Surfaces<float> / Points<float>: the 320-panel sphere of flow_over_sphere.json and a particle cloud around and
+    inside it, with particles placed under nodes and edge midpoints so that the tie branch of the hit list runs."""
+    rng = np.random.Generator(np.random.MT19937(2718))
+    nodes_i, idx = W.icosphere(2, 0.5)
+    val = np.zeros((idx.shape[0], 3), f32)
+    area, ts, b1, b2, nrm = ref.surface_props(nodes_i, idx, val)
+    nodes = np.ascontiguousarray(nodes_i.T)
+    nt = 3000
+    x = ((rng.random((3, nt), dtype=f32) - f32(0.5)) * f32(1.4)).astype(f32)
+    x[:, :60] = (nodes[:, :60] * f32(0.98)).astype(f32)                                             # under nodes: 5-6 panels tie
+    x[:, 60:120] = ((nodes[:, idx[:60, 0]] + nodes[:, idx[:60, 1]]) * f32(0.495)).astype(f32)       # under edge midpoints: 2 tie
+    x[:, 120:180] = (nodes[:, 100:160] * f32(1.01)).astype(f32)                                     # just outside
+    g = {"nodes_i": nodes_i, "idx": idx, "nrm": nrm, "x0": x}
+    a = x.copy()
+    g["reflect_moved"] = np.int64(ref.reflect(nodes_i, idx, a))
+    g["reflect_x"] = a
+    cm, ips = f32(0.5 / np.sqrt(2.0 * np.pi)), f32(0.0894427)        # the call of src/Convection.h:260 with the sphere case's ips
+    a = x.copy()
+    g["clear_moved"] = np.int64(ref.clear_inner(1, nodes_i, idx, a, np.full(nt, 0.03, f32), cm, ips))
+    g["clear_x"], g["clear_cm"], g["clear_ips"] = a, cm, ips
+    a = g["reflect_x"].copy()                                         # Diffusion.h:292-306: reflect, then clear
+    g["both_moved"] = np.int64(ref.clear_inner(1, nodes_i, idx, a, np.full(nt, 0.03, f32), f32(0.2), f32(0.05)))
+    g["both_x"] = a
+    np.savez_compressed(os.path.join(OUT, "reflect.npz"), **g)
+
+
 def main():
     oracle_py.build(want_ref=True)
     ref = oracle_py.Reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "reflect":
+        reflect(ref)
+        print("reflect.npz", os.path.getsize(os.path.join(OUT, "reflect.npz")))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "convection":
         convection(ref)
         print("convection.npz", os.path.getsize(os.path.join(OUT, "convection.npz")))
         return
     convection(ref)
+    reflect(ref)
     rng = np.random.Generator(np.random.MT19937(99))
 
     # ---- single-interaction known answers (src/Kernels.h) ----

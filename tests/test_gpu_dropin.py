@@ -114,3 +114,18 @@ def test_convection_through_reference_points(dropin, order):
     tol = {"x": 1e-6, "s": 2e-5, "elong": 1e-5, "u": VEL_TOL, "ug": GRAD_TOL}
     for a, b, name in zip(gpu_step, cpu, ("x", "s", "elong", "u", "ug")):
         assert rel_err(a, b) <= tol[name], name
+
+
+def test_reflect_and_clear_inner_through_reference_functions(dropin):
+    """The patched reflect_panp2 / clear_inner_panp2 (src/Reflect.h + integration hunk) take no ExecEnv: in a -DUSE_CUDA
+    build the default back end decides, so calling the reference's own functions here runs the CUDA arm. The fixtures
+    are what the unpatched reference returned on the CPU - the comparison is bit for bit."""
+    if not hasattr(dropin.lib, "o3d_ref_reflect"):
+        pytest.skip("stale drop-in build")
+    g = golden("reflect.npz")
+    x = g["x0"].copy()
+    assert dropin.reflect(g["nodes_i"], g["idx"], x) == int(g["reflect_moved"])
+    assert np.array_equal(x, g["reflect_x"])
+    x = g["x0"].copy()
+    n = dropin.clear_inner(1, g["nodes_i"], g["idx"], x, np.full(x.shape[1], 0.03, f32), float(g["clear_cm"]), float(g["clear_ips"]))
+    assert n == int(g["clear_moved"]) and np.array_equal(x, g["clear_x"])

@@ -171,7 +171,63 @@ def climb(rounds, seed, jobs):
     print("final", best_r, "->", os.path.join(WORK, f"climb_{seed}.inc"))
 
 
+def parse_body(path):
+    """Recover (order, swaps) from a body file written by emit()."""
+    order, swaps = [], set()
+    for line in open(path):
+        m = re.match(r"\s+(?:const float2 )?([\w\[\]]+) = (__f\w+2_rn|f2)\((.*)\);", line)
+        if not m or m.group(1) in ("sx", "wx", "r2"):
+            continue
+        res = m.group(1)
+        idx = next(k for k, st in enumerate(STMTS) if st[0] == res)
+        order.append(idx)
+        if STMTS[idx][1] in ("mul", "fma", "add"):
+            first = m.group(3).split(",")[0].strip()
+            a = STMTS[idx][2]
+            want = f"neg2({a[1:]})" if a.startswith("-") else a
+            if first != want:
+                swaps.add(idx)
+    assert sorted(order) == list(range(len(STMTS))), "body file does not hold every statement once"
+    return order, frozenset(swaps)
+
+
+def anneal(minutes, seed, jobs, start_file=None):
+    """Simulated annealing (parallel tempering-lite): `jobs` mutants of the current state per round, Metropolis
+    acceptance on the best of them; remembers the best state ever seen."""
+    import math
+    import time
+    rng = random.Random(seed)
+    cur = parse_body(start_file) if start_file else (list(range(len(STMTS))), frozenset())
+    cur_r = score((0, cur[0], cur[1], []))
+    best, best_r = cur, cur_r
+    print("start", cur_r, flush=True)
+    t_end = time.time() + 60 * minutes
+    rnd = 0
+    while time.time() < t_end:
+        frac = max(0.0, (t_end - time.time()) / (60 * minutes))
+        temp = 0.05 + 0.6 * frac                     # in cycles/pair
+        muts = [mutate(rng, *cur) for _ in range(jobs)]
+        with ProcessPoolExecutor(jobs) as ex:
+            res = list(ex.map(score, [(k + 1, m[0], m[1], []) for k, m in enumerate(muts)]))
+        ok = [(r, m) for r, m in zip(res, muts) if r is not None and not r[5]]
+        rnd += 1
+        if not ok:
+            continue
+        r, m = min(ok, key=lambda t: t[0][0])
+        if r[0] <= cur_r[0] or rng.random() < math.exp(-(r[0] - cur_r[0]) / temp):
+            cur, cur_r = m, r
+        if r[0] < best_r[0]:
+            best, best_r = m, r
+            print(f"round {rnd}: {r}", flush=True)
+            with open(os.path.join(WORK, f"anneal_{seed}.inc"), "w") as f:
+                f.write(emit(best[0], best[1]))
+    print("final", best_r, flush=True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "anneal":
+        return anneal(float(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 8,
+                      sys.argv[5] if len(sys.argv) > 5 else None)
     if len(sys.argv) > 1 and sys.argv[1] == "climb":
         return climb(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 8)
     trials = int(sys.argv[1]) if len(sys.argv) > 1 else 64
