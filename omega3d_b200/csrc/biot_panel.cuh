@@ -126,16 +126,11 @@ __device__ __forceinline__ bool pan_node(float cx, float cy, float cz, float thr
   return false;
 }
 
-// Whole (panel, point) pair. (wx,wy,wz,q) = total panel strengths; thr0 = 4 sqrt(area); c0 = centroid.
-// counts[0] += leaves, counts[1] += splits.
+// Levels 1..3 of a (panel, point) pair whose level-0 node was NOT well separated. (wx,wy,wz,q) = total panel
+// strengths; thr0 = 4 sqrt(area). counts[0] += leaves, counts[1] += splits (the level-0 split included).
 template <bool GRAD>
-__device__ __forceinline__ void pan_on_point(const Tri& p0, float c0x, float c0y, float c0z, float thr0, float wx,
-                                             float wy, float wz, float q, float tx, float ty, float tz,
-                                             float (&acc)[PanAcc<GRAD>::N], unsigned (&counts)[2]) {
-  if (pan_node<GRAD>(c0x, c0y, c0z, thr0, false, tx, ty, tz, wx, wy, wz, q, acc)) {
-    counts[0] += 1;
-    return;
-  }
+__device__ __forceinline__ void pan_subdivide(const Tri& p0, float thr0, float wx, float wy, float wz, float q, float tx,
+                                              float ty, float tz, float (&acc)[PanAcc<GRAD>::N], unsigned (&counts)[2]) {
   counts[1] += 1;
   const Mids m0 = tri_mids(p0);
   const float w1x = wx * 0.25f, w1y = wy * 0.25f, w1z = wz * 0.25f, q1 = q * 0.25f, thr1 = thr0 * 0.5f;
@@ -170,6 +165,18 @@ __device__ __forceinline__ void pan_on_point(const Tri& p0, float c0x, float c0y
       }
     }
   }
+}
+
+// Whole (panel, point) pair: level-0 node, then the subdivision if it was not well separated.
+template <bool GRAD>
+__device__ __forceinline__ void pan_on_point(const Tri& p0, float c0x, float c0y, float c0z, float thr0, float wx,
+                                             float wy, float wz, float q, float tx, float ty, float tz,
+                                             float (&acc)[PanAcc<GRAD>::N], unsigned (&counts)[2]) {
+  if (pan_node<GRAD>(c0x, c0y, c0z, thr0, false, tx, ty, tz, wx, wy, wz, q, acc)) {
+    counts[0] += 1;
+    return;
+  }
+  pan_subdivide<GRAD>(p0, thr0, wx, wy, wz, q, tx, ty, tz, acc, counts);
 }
 
 // Fold a tile's FP32 partials into the FP64 sums (u v w | ux vx wx | uy vy wy | uz vz wz) and clear them.
@@ -269,12 +276,25 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_kernel(const PanPtsArgs p) {
     const float4* g = p.pan + (size_t)k * (kPanTile * kPanRec);
     for (int e = threadIdx.x; e < kPanTile * kPanRec; e += BLOCK) tile[e] = g[e];
     __syncthreads();
+    // Two phases per tile, so that lanes whose pair needs the deep (divergent) subdivision run it TOGETHER instead of
+    // one or two at a time while the rest of the warp waits: (A) every panel's level-0 test and, where it is well
+    // separated, its single leaf - convergent, warp-broadcast reads; pairs that are not are remembered in a 64-bit
+    // mask (kPanTile = 64); (B) each lane walks its own mask in ascending panel order. Per target this only reorders
+    // the FP32 terms inside one tile (far leaves first); leaf and split counts are unchanged.
+    unsigned long long near = 0ull;
 #pragma unroll 1
     for (int j = 0; j < kPanTile; ++j) {
+      const float4 r2 = tile[j * kPanRec + 2], r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
+      if (pan_node<GRAD>(r3.y, r3.z, r3.w, r4.x, false, tx, ty, tz, r2.y, r2.z, r2.w, r3.x, acc)) counts[0] += 1;
+      else near |= 1ull << j;
+    }
+    while (near) {
+      const int j = __ffsll((long long)near) - 1;
+      near &= near - 1ull;
       const float4 r0 = tile[j * kPanRec], r1 = tile[j * kPanRec + 1], r2 = tile[j * kPanRec + 2],
                    r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
       const Tri t{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
-      pan_on_point<GRAD>(t, r3.y, r3.z, r3.w, r4.x, r2.y, r2.z, r2.w, r3.x, tx, ty, tz, acc, counts);
+      pan_subdivide<GRAD>(t, r4.x, r2.y, r2.z, r2.w, r3.x, tx, ty, tz, acc, counts);
     }
     pan_promote<GRAD>(acc, sum);
   }
@@ -339,13 +359,30 @@ __global__ void __launch_bounds__(BLOCK) pts_pan_kernel(const PtsPanArgs p) {
     for (int e = threadIdx.x; e < kTile * 2; e += BLOCK) tile[e] = g[e];
     __syncthreads();
     const int cnt = (int)min((int64_t)kTile, p.ns - (int64_t)k * kTile);
+    // same two phases as pan_pts_kernel, 64 particles at a time: (A) level-0 test + leaf where well separated,
+    // (B) every lane subdivides against the particles it marked, together
 #pragma unroll 1
-    for (int j = 0; j < cnt; ++j) {
-      const int pr = j >> 1, h = j & 1;
-      const float4 q0 = tile[4 * pr], q1 = tile[4 * pr + 1], q2 = tile[4 * pr + 2], q3 = tile[4 * pr + 3];
-      const float px = -(h ? q0.y : q0.x), py = -(h ? q0.w : q0.z), pz = -(h ? q1.y : q1.x);
-      const float wx = h ? q2.y : q2.x, wy = h ? q2.w : q2.z, wz = h ? q3.y : q3.x;
-      pan_on_point<false>(t, cx, cy, cz, thr0, wx, wy, wz, 0.0f, px, py, pz, acc, counts);
+    for (int c0 = 0; c0 < cnt; c0 += 64) {
+      const int cn = min(64, cnt - c0);
+      unsigned long long near = 0ull;
+#pragma unroll 1
+      for (int jj = 0; jj < cn; ++jj) {
+        const int j = c0 + jj, pr = j >> 1, h = j & 1;
+        const float4 q0 = tile[4 * pr], q1 = tile[4 * pr + 1], q2 = tile[4 * pr + 2], q3 = tile[4 * pr + 3];
+        const float px = -(h ? q0.y : q0.x), py = -(h ? q0.w : q0.z), pz = -(h ? q1.y : q1.x);
+        const float wx = h ? q2.y : q2.x, wy = h ? q2.w : q2.z, wz = h ? q3.y : q3.x;
+        if (pan_node<false>(cx, cy, cz, thr0, false, px, py, pz, wx, wy, wz, 0.0f, acc)) counts[0] += 1;
+        else near |= 1ull << jj;
+      }
+      while (near) {
+        const int jj = __ffsll((long long)near) - 1;
+        near &= near - 1ull;
+        const int j = c0 + jj, pr = j >> 1, h = j & 1;
+        const float4 q0 = tile[4 * pr], q1 = tile[4 * pr + 1], q2 = tile[4 * pr + 2], q3 = tile[4 * pr + 3];
+        const float px = -(h ? q0.y : q0.x), py = -(h ? q0.w : q0.z), pz = -(h ? q1.y : q1.x);
+        const float wx = h ? q2.y : q2.x, wy = h ? q2.w : q2.z, wz = h ? q3.y : q3.x;
+        pan_subdivide<false>(t, thr0, wx, wy, wz, 0.0f, px, py, pz, acc, counts);
+      }
     }
     sum[0] += (double)acc[0]; sum[1] += (double)acc[1]; sum[2] += (double)acc[2];
     acc[0] = acc[1] = acc[2] = 0.f;

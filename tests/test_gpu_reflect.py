@@ -65,7 +65,9 @@ def test_against_oracle_other_sizes(cuda_ctx, restate, levels, nt):
     assert np.array_equal(p.x, ref)
     # size-independent property: after both passes every particle is outside the body and above the cutoff layer
     rad = np.sqrt((p.x.astype(np.float64) ** 2).sum(0))
-    assert rad.min() > 0.5 * 0.97      # faceted sphere: inradius of the facets is slightly under 0.5
+    tri = surf.x[:, surf.idx].astype(np.float64)                       # (3, np, 3 nodes)
+    inradius = np.abs((tri.mean(axis=2) * surf.nrm).sum(0)).min()      # the faceted sphere's inscribed radius
+    assert rad.min() > inradius
 
 
 def test_empty_inputs(cuda_ctx):
