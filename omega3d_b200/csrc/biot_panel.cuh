@@ -253,7 +253,13 @@ template <bool GRAD, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) pan_pts_kernel(const PanPtsArgs p) {
   constexpr int NA = PanAcc<GRAD>::N;
   constexpr int NS = GRAD ? 12 : 3;
-  __shared__ alignas(16) float4 tile[kPanTile * kPanRec];
+  // every WARP streams the panel tiles through its own 5 KB of shared memory and synchronises only with itself:
+  // the work per tile varies from warp to warp (how many of its pairs subdivide), and a CTA-wide barrier per tile
+  // made every warp wait for the slowest one (ncu: 4.2 barrier-stall cycles per issued instruction, profiles/
+  // r01_pan_pts_ncu.txt). The second copy of a tile comes out of L2.
+  __shared__ alignas(16) float4 tiles[BLOCK / 32][kPanTile * kPanRec];
+  float4* tile = tiles[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
 
   const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
   const int k0 = blockIdx.y * per;
@@ -272,10 +278,11 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_kernel(const PanPtsArgs p) {
   for (int k = 0; k < NS; ++k) sum[k] = 0.0;
 
   for (int k = k0; k < k1; ++k) {
-    __syncthreads();
+    __syncwarp();
     const float4* g = p.pan + (size_t)k * (kPanTile * kPanRec);
-    for (int e = threadIdx.x; e < kPanTile * kPanRec; e += BLOCK) tile[e] = g[e];
-    __syncthreads();
+#pragma unroll
+    for (int e = lane; e < kPanTile * kPanRec; e += 32) tile[e] = g[e];
+    __syncwarp();
     // Two phases per tile, so that lanes whose pair needs the deep (divergent) subdivision run it TOGETHER instead of
     // one or two at a time while the rest of the warp waits: (A) every panel's level-0 test and, where it is well
     // separated, its single leaf - convergent, warp-broadcast reads; pairs that are not are remembered in a 64-bit
@@ -337,7 +344,10 @@ struct PtsPanArgs {
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) pts_pan_kernel(const PtsPanArgs p) {
-  __shared__ alignas(128) float4 tile[kTile * 2];
+  // warp-private particle tiles, synchronised per warp (see pan_pts_kernel)
+  __shared__ alignas(128) float4 tiles[BLOCK / 32][kTile * 2];
+  float4* tile = tiles[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
   const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
   const int k0 = blockIdx.y * per;
   const int k1 = min(p.ntiles, k0 + per);
@@ -354,10 +364,11 @@ __global__ void __launch_bounds__(BLOCK) pts_pan_kernel(const PtsPanArgs p) {
   unsigned counts[2] = {0u, 0u};
 
   for (int k = k0; k < k1; ++k) {
-    __syncthreads();
+    __syncwarp();
     const float4* g = p.src + (size_t)k * (kTile * 2);
-    for (int e = threadIdx.x; e < kTile * 2; e += BLOCK) tile[e] = g[e];
-    __syncthreads();
+#pragma unroll 4
+    for (int e = lane; e < kTile * 2; e += 32) tile[e] = g[e];
+    __syncwarp();
     const int cnt = (int)min((int64_t)kTile, p.ns - (int64_t)k * kTile);
     // same two phases as pan_pts_kernel, 64 particles at a time: (A) level-0 test + leaf where well separated,
     // (B) every lane subdivides against the particles it marked, together
