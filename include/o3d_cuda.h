@@ -216,6 +216,16 @@ int o3d_cuda_clear_inner_pts(o3d_ctx* ctx, int method, int64_t nn, const float* 
                              int64_t np, const uint32_t* idx, const float* nrm, int64_t nt, float* tx, float* ty,
                              float* tz, float cutoff_mult, float ips, int64_t* num_moved);
 
+/* ---- field output -------------------------------------------------------------------------- */
+/* The `.vtu` file of Points<S>::write_vtk (src/Points.h:851-1039, src/VtkXmlWriter.h:36-148), byte for byte: FieldData
+ * TimeValue, positions, vertex cells, circulation (strengths), radius, velocity, base64 DataArrays. Host arrays, SoA.
+ * sx/sy/sz and r NULL: inert points (the reference's "fldpt_" files). o3d_cuda_particles_write_vtu downloads a resident
+ * collection and writes it. File naming ("part_%02d_%05d.vtu") is the caller's. */
+int o3d_cuda_write_points_vtu(const char* path, int64_t n, const float* x, const float* y, const float* z,
+                              const float* sx, const float* sy, const float* sz, const float* r, const float* u,
+                              const float* v, const float* w, double time);
+int o3d_cuda_particles_write_vtu(o3d_ctx* ctx, o3d_particles* p, const char* path, double time);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* When on, o3d_cuda_pts_on_pts_dev brackets its dominant kernel with CUDA events on the launching stream;
  * o3d_cuda_dev_kernel_ms waits for the last such launch and returns its device time in milliseconds. */

@@ -51,6 +51,8 @@ SYMBOLS = {
     "o3d_cuda_reflect_pts": (c_int, [c_void_p, c_int64, _P, _P, _P, c_int64, _P, _P, c_int64, _P, _P, _P, POINTER(c_int64)]),
     "o3d_cuda_clear_inner_pts": (c_int, [c_void_p, c_int, c_int64, _P, _P, _P, c_int64, _P, _P, c_int64, _P, _P, _P,
                                          ctypes.c_float, ctypes.c_float, POINTER(c_int64)]),
+    "o3d_cuda_write_points_vtu": (c_int, [c_char_p, c_int64] + [_P] * 10 + [c_double]),
+    "o3d_cuda_particles_write_vtu": (c_int, [c_void_p, c_void_p, c_char_p, c_double]),
     "o3d_cuda_set_graphs": (c_int, [c_void_p, c_int]),
     "o3d_cuda_particles_graph_active": (c_int, [c_void_p]),
     "o3d_cuda_set_profiling": (c_int, [c_void_p, c_int]),

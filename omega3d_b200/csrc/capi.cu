@@ -17,6 +17,7 @@
 #include "biot_pp.cuh"
 #include "convect.cuh"
 #include "reflect.cuh"
+#include "vtu_writer.h"
 
 using namespace o3d;
 
@@ -1516,6 +1517,33 @@ int o3d_cuda_clear_inner_pts(o3d_ctx* c, int method, int64_t nn, const float* nx
   if (method != 1) return fail(c, O3D_ERR_UNSUPPORTED, "clear_inner_pts: only method 1 (push out, keep strength) is implemented");
   const float cutoff = cutoff_mult * ips;   // float product, as "_cutoff_mult*_ips" with S = float (src/Reflect.h:537)
   return closest_point_pass(c, "clear_inner_pts", 1, cutoff, nn, nx, ny, nz, np, idx, nrm, nt, tx, ty, tz, num_moved);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Field output: the reference's Points::write_vtk file, byte for byte (csrc/vtu_writer.h)
+int o3d_cuda_write_points_vtu(const char* path, int64_t n, const float* x, const float* y, const float* z, const float* sx,
+                              const float* sy, const float* sz, const float* r, const float* u, const float* v, const float* w,
+                              double time) {
+  if (!path || n <= 0 || n >= (int64_t(1) << 31) || !x || !y || !z || !u || !v || !w) return O3D_ERR_INVALID;
+  if ((sx || sy || sz) && !(sx && sy && sz)) return O3D_ERR_INVALID;
+  const float* xs[3] = {x, y, z};
+  const float* ss[3] = {sx, sy, sz};
+  const float* us[3] = {u, v, w};
+  return write_points_vtu(path, n, xs, sx ? ss : nullptr, r, us, time) ? O3D_OK : O3D_ERR_INVALID;
+}
+
+int o3d_cuda_particles_write_vtu(o3d_ctx* c, o3d_particles* p, const char* path, double time) {
+  if (!c || !p || !path || p->n <= 0) return fail(c, O3D_ERR_INVALID, "particles_write_vtu: bad argument or empty collection");
+  const size_t n = (size_t)p->n;
+  std::vector<float> h(10 * n);
+  float* a = h.data();
+  const int rc = o3d_cuda_particles_download(c, p, a, a + n, a + 2 * n, a + 3 * n, a + 4 * n, a + 5 * n, a + 6 * n, nullptr, a + 7 * n,
+                                             a + 8 * n, a + 9 * n, nullptr);
+  if (rc != O3D_OK) return rc;
+  if (o3d_cuda_write_points_vtu(path, p->n, a, a + n, a + 2 * n, a + 3 * n, a + 4 * n, a + 5 * n, a + 6 * n, a + 7 * n, a + 8 * n, a + 9 * n,
+                                time) != O3D_OK)
+    return fail(c, O3D_ERR_INVALID, std::string("particles_write_vtu: cannot write ") + path);
+  return O3D_OK;
 }
 
 int o3d_cuda_set_graphs(o3d_ctx* c, int on) {

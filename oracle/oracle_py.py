@@ -181,6 +181,8 @@ class Reference:
             L.o3d_ref_reflect.restype = c_long
             L.o3d_ref_clear_inner.argtypes = [c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_float]
             L.o3d_ref_clear_inner.restype = c_long
+        if hasattr(L, "o3d_ref_write_vtk"):
+            L.o3d_ref_write_vtk.argtypes = [c_int] + [c_void_p] * 4 + [c_int, c_int, c_double, ctypes.c_char_p]
         if hasattr(L, "o3d_ref_has_features") and L.o3d_ref_has_features():
             L.o3d_ref_singular_ring.argtypes = [c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p, c_long]
             L.o3d_ref_singular_ring.restype = c_long
@@ -223,6 +225,13 @@ class Reference:
     def clear_inner(self, method, nodes_i, idx, x, rad, cutoff_mult, ips):
         return int(self.lib.o3d_ref_clear_inner(method, nodes_i.shape[0], _p(nodes_i), idx.shape[0], _p(idx), x.shape[1], _p(x),
                                                 _p(rad), cutoff_mult, ips))
+
+    def write_vtk(self, x, s, r, u, index, frameno, time, directory):
+        """Points<float>::write_vtk -> <directory>/part_<index>_<frameno>.vtu; returns the file's bytes."""
+        rc = self.lib.o3d_ref_write_vtk(x.shape[1], _p(x), _p(s), _p(r), _p(u), index, frameno, float(time), directory.encode())
+        assert rc == 0
+        with open(os.path.join(directory, f"part_{index:02d}_{frameno:05d}.vtu"), "rb") as f:
+            return f.read()
 
     # ---- initial conditions from the reference's feature generators (src/FlowFeature.cpp) ----
     def has_features(self) -> bool:

@@ -474,3 +474,16 @@ long o3d_ref_clear_inner(int method, int nn, const float* nodes, int np, const u
   return moved;
 }
 }  // extern "C"
+
+// ---- Points<float>::write_vtk (src/Points.h:851-1039): writes part_<index>_<frame>.vtu into `dir`. Returns 0.
+extern "C" int o3d_ref_write_vtk(int n, const float* x, const float* s, const float* r, const float* u, int index, int frameno,
+                                 double time, const char* dir) {
+  Mute m(g_mute);
+  Points<float> p = make_points(n, x, x + n, x + 2 * (size_t)n, s, r, active, lagrangian);
+  auto& pu = p.get_vel();
+  for (int d = 0; d < 3; ++d) std::memcpy(pu[d].data(), u + (size_t)d*n, sizeof(float)*n);
+  char cwd[4096];
+  if (!getcwd(cwd, sizeof cwd) || chdir(dir) != 0) return -1;
+  p.write_vtk((size_t)index, (size_t)frameno, time);
+  return chdir(cwd);
+}

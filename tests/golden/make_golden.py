@@ -111,9 +111,30 @@ def reflect(ref):
     np.savez_compressed(os.path.join(OUT, "reflect.npz"), **g)
 
 
+def vtk(ref):
+    """tests/golden/vtk.npz: the bytes of the file the reference's Points<float>::write_vtk writes (src/Points.h:851-1039)."""
+    import tempfile
+    rng = np.random.Generator(np.random.MT19937(31))
+    g = {}
+    for n in (1, 37):
+        x = (rng.random((3, n), dtype=f32) - f32(0.5)).astype(f32)
+        s = (rng.random((3, n), dtype=f32) - f32(0.5)).astype(f32)
+        r = (f32(0.01) + rng.random(n, dtype=f32) * f32(0.1)).astype(f32)
+        u = (rng.random((3, n), dtype=f32) - f32(0.5)).astype(f32)
+        with tempfile.TemporaryDirectory() as d:
+            data = ref.write_vtk(x, s, r, u, 3, 42, 0.0625 * n, d)
+        g.update({f"x{n}": x, f"s{n}": s, f"r{n}": r, f"u{n}": u, f"time{n}": np.float64(0.0625 * n),
+                  f"file{n}": np.frombuffer(data, np.uint8)})
+    np.savez_compressed(os.path.join(OUT, "vtk.npz"), **g)
+
+
 def main():
     oracle_py.build(want_ref=True)
     ref = oracle_py.Reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "vtk":
+        vtk(ref)
+        print("vtk.npz", os.path.getsize(os.path.join(OUT, "vtk.npz")))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "reflect":
         reflect(ref)
         print("reflect.npz", os.path.getsize(os.path.join(OUT, "reflect.npz")))
@@ -124,6 +145,7 @@ def main():
         return
     convection(ref)
     reflect(ref)
+    vtk(ref)
     rng = np.random.Generator(np.random.MT19937(99))
 
     # ---- single-interaction known answers (src/Kernels.h) ----

@@ -260,3 +260,19 @@ def test_two_device_resident_equals_one_device(cuda_ctx):
         for k in oa:
             assert np.array_equal(oa[k], ob[k]), (order, k)   # tile-aligned blocks: the same packed stream on any device count
     ctx2.close()
+
+
+def test_resident_collection_writes_the_reference_vtu(cuda_ctx, tmp_path):
+    """o3d_cuda_particles_write_vtu: the file written straight from HBM equals the reference-format file written from
+    the downloaded arrays (whose writer is pinned byte for byte in tests/test_vtk.py)."""
+    from omega3d_b200 import vtk as V
+    g = golden("convection.npz")
+    d = C.DeviceParticles(cuda_ctx).upload(g["adv_x"], g["adv_s"], g["adv_r"])
+    d.advect(2, 0.0, 0.05, g["adv_fs"], 1)
+    a = V.write_resident_vtk(d, 0, 1, 0.05, str(tmp_path))
+    out = d.download()
+    p = I.Points(out["x"], out["s"], out["r"], I.active, I.lagrangian)
+    p.u[:] = out["u"]
+    (tmp_path / "host").mkdir()
+    b = V.write_vtk(p, 0, 1, 0.05, str(tmp_path / "host"))
+    assert open(a, "rb").read() == open(b, "rb").read()
