@@ -226,6 +226,14 @@ int o3d_cuda_write_points_vtu(const char* path, int64_t n, const float* x, const
                               const float* v, const float* w, double time);
 int o3d_cuda_particles_write_vtu(o3d_ctx* ctx, o3d_particles* p, const char* path, double time);
 
+/* ---- kernel selection ---------------------------------------------------------------------------------- */
+/* The particles-on-points kernel exists twice in the library, from the same source: as compiled, and post-processed at
+ * the SASS level (tools/sass_patch.py: longer operand-reuse chains; same instructions, same results bit for bit, ~2 %
+ * faster). The post-processed copy is the default (environment O3D_CUDA_TUNED=0 starts contexts on the other);
+ * this switch exists so that tests and profiles can compare the two. o3d_cuda_tuned_kernels: 1 if on. */
+int o3d_cuda_set_tuned_kernels(o3d_ctx* ctx, int on);
+int o3d_cuda_tuned_kernels(const o3d_ctx* ctx);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* When on, o3d_cuda_pts_on_pts_dev brackets its dominant kernel with CUDA events on the launching stream;
  * o3d_cuda_dev_kernel_ms waits for the last such launch and returns its device time in milliseconds. */

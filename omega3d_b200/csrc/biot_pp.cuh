@@ -36,6 +36,12 @@
 #ifndef O3D_PP_BODY_FILE
 #define O3D_PP_BODY_FILE "pp_body_velgrad_uni.inc"
 #endif
+#ifndef O3D_PP_JOINT
+#define O3D_PP_JOINT 0    // 1: the velocity+gradient, uniform-radius loop body covers BOTH register-blocked targets in one
+#endif                    //    machine-searched statement order (O3D_PP_JOINT_FILE), so reuse chains can span the targets
+#ifndef O3D_PP_JOINT_FILE
+#define O3D_PP_JOINT_FILE "pp_body_velgrad_uni_joint.inc"
+#endif
 #ifndef O3D_PP_MINB
 #define O3D_PP_MINB 3     // __launch_bounds__ min CTAs per SM for pp2_kernel (caps registers at 168)
 #endif
@@ -47,6 +53,13 @@
 #endif
 
 namespace o3d {
+
+// Product launch configuration of pp2_kernel (capi.cu launches these two instantiations; pp_tuned.cu compiles the same
+// two into the cubin that tools/sass_patch.py post-processes): 128-thread CTAs, 2 register-blocked targets per thread
+// with gradients, 4 without.
+constexpr int kPPBlock = 128;
+constexpr int kPPTgrad = 2;
+constexpr int kPPTvel = 4;
 
 constexpr int kPPUnrollGrad = O3D_PP_UNROLL_GRAD;
 constexpr int kPPUnrollVel = O3D_PP_UNROLL_VEL;
@@ -391,8 +404,17 @@ __device__ __forceinline__ void pp2_tiles(const PPArgs& p, const int k0, const i
 #pragma unroll(U)
     for (int j = 0; j < kTile / 2; ++j) {
       const float4 q0 = s[4 * j], q1 = s[4 * j + 1], q2 = s[4 * j + 2], q3 = s[4 * j + 3];
+#if O3D_PP_JOINT
+      if constexpr (GRAD && UNI && T == 2) {
+        const float k15 = 1.5f * tr2[0].x, k75 = -7.5f * tr2[0].x;   // 32-bit broadcast operands, as in pp_interact2
+        const float2 tk = f2(k15, k15), tk5 = f2(k75, k75);
+#include O3D_PP_JOINT_FILE
+      } else
+#endif
+      {
 #pragma unroll
-      for (int t = 0; t < T; ++t) pp_interact2<GRAD, UNI>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tr2[t], acc[t]);
+        for (int t = 0; t < T; ++t) pp_interact2<GRAD, UNI>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tr2[t], acc[t]);
+      }
     }
 #pragma unroll
     for (int t = 0; t < T; ++t) {

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -18,6 +19,7 @@
 #include "convect.cuh"
 #include "reflect.cuh"
 #include "vtu_writer.h"
+#include "pp2_tuned_cubin.h"   // generated (csrc/Makefile): pp_tuned.cu -> cubin -> tools/sass_patch.py -> byte array
 
 using namespace o3d;
 
@@ -79,6 +81,7 @@ struct Device {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // h2d start, compute start, compute end, d2h end
   cudaEvent_t evk[2] = {nullptr, nullptr};                   // around the dominant kernel of a *_dev call
   bool profile = false;
+  bool tuned = true;                                         // launch pp2_kernel from the post-processed cubin (TunedKernels)
   DevBuf src, packed, targ, out, work, geom, panels, tpanels, cnt, rng;
   unsigned long long counts[2] = {0, 0};  // leaves, splits of the last panel call on this device
   // result of the last call on this device
@@ -163,6 +166,37 @@ bool finish_timing(Device& d) {
   return true;
 }
 
+// ---- the post-processed copies of the two product pp2_kernel instantiations ---------------------------------
+// Same source (csrc/pp_tuned.cu -> biot_pp.cuh), compiled to a cubin and passed through tools/sass_patch.py, which
+// only lengthens the operand-reuse chains of adjacent packed FP32 instructions: identical instructions and results,
+// about 2 % fewer FMA-pipe cycles. Loaded once per process; a load failure is an error of o3d_cuda_create, not a
+// silent switch to the linked copies (those stay reachable through o3d_cuda_set_tuned_kernels(ctx, 0) for A/B tests).
+static_assert(kPPTgrad == 2 && kPPTvel == 4 && kPPBlock == 128, "kernel names below spell these template arguments");
+struct TunedKernels {
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t grad = nullptr, vel = nullptr;
+  cudaError_t status = cudaSuccess;
+  const char* where = "";
+};
+const TunedKernels& tuned_kernels() {
+  static const TunedKernels t = [] {
+    TunedKernels k;
+    k.status = cudaLibraryLoadData(&k.lib, o3d_pp2_tuned_cubin, nullptr, nullptr, 0, nullptr, nullptr, 0);
+    k.where = "cudaLibraryLoadData(pp2_tuned.cubin)";
+    if (k.status == cudaSuccess) {
+      k.status = cudaLibraryGetKernel(&k.grad, k.lib, "_ZN3o3d10pp2_kernelILi2ELb1ELi128EEEvNS_6PPArgsE");
+      k.where = "cudaLibraryGetKernel(pp2_kernel<2,true,128>)";
+    }
+    if (k.status == cudaSuccess) {
+      k.status = cudaLibraryGetKernel(&k.vel, k.lib, "_ZN3o3d10pp2_kernelILi4ELb0ELi128EEEvNS_6PPArgsE");
+      k.where = "cudaLibraryGetKernel(pp2_kernel<4,false,128>)";
+    }
+    if (k.status != cudaSuccess) cudaGetLastError();
+    return k;
+  }();
+  return t;
+}
+
 // ---- launch-shape selection for particles -> points ------------------------------------------------
 // Product configuration (profiles/r01_*: packed FFMA2 kernel, 128-thread CTAs): vel+grad keeps 2 targets
 // per thread, velocity-only 4. When the target count cannot fill the GPU the source range is split over
@@ -172,10 +206,6 @@ struct PPShape {
   dim3 grid;
   size_t work_bytes;
 };
-constexpr int kPPBlock = 128;
-constexpr int kPPTgrad = 2;
-constexpr int kPPTvel = 4;
-
 // CTAs resident per SM (register-limited: 162 / 128 regs x 128 threads) for the two product kernels
 constexpr int kPPResidentGrad = 3;
 constexpr int kPPResidentVel = 4;
@@ -237,10 +267,15 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   d.launches += 1;
   a.radius_range = d.rng.as<uint32_t>();
   if (d.profile) O3D_TRY(d, cudaEventRecord(d.evk[0], st));
-  if (grad)
+  if (d.tuned) {
+    const TunedKernels& tk = tuned_kernels();
+    void* params[] = {&a};
+    O3D_TRY(d, cudaLaunchKernel((const void*)(grad ? tk.grad : tk.vel), s.grid, dim3(kPPBlock), params, 0, st));
+  } else if (grad) {
     pp2_kernel<kPPTgrad, true, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a);
-  else
+  } else {
     pp2_kernel<kPPTvel, false, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a);
+  }
   O3D_TRY(d, cudaGetLastError());
   if (d.profile) O3D_TRY(d, cudaEventRecord(d.evk[1], st));
   d.launches += 1;
@@ -604,6 +639,8 @@ int o3d_cuda_create(o3d_ctx** out, int ndev, const int* devices) {
   if (have < 1 || ndev > have) return O3D_ERR_NODEVICE;
   o3d_ctx* c = new o3d_ctx();
   c->dev.resize(ndev);
+  const char* env_tuned = getenv("O3D_CUDA_TUNED");          // "0": start with the linked copies of pp2_kernel
+  const bool want_tuned = !(env_tuned && env_tuned[0] == '0');
   for (int k = 0; k < ndev; ++k) {
     Device& d = c->dev[k];
     d.id = devices ? devices[k] : k;
@@ -622,6 +659,12 @@ int o3d_cuda_create(o3d_ctx** out, int ndev, const int* devices) {
       o3d_cuda_destroy(c);
       return O3D_ERR_CUDA;
     }
+    d.tuned = want_tuned;
+  }
+  if (tuned_kernels().status != cudaSuccess) {               // no silent fallback: the library is broken
+    fprintf(stderr, "o3d_cuda_create: %s failed: %s\n", tuned_kernels().where, cudaGetErrorString(tuned_kernels().status));
+    o3d_cuda_destroy(c);
+    return O3D_ERR_CUDA;
   }
   *out = c;
   return O3D_OK;
@@ -1553,6 +1596,14 @@ int o3d_cuda_set_graphs(o3d_ctx* c, int on) {
 }
 
 int o3d_cuda_particles_graph_active(const o3d_particles* p) { return p && !p->dev.empty() && p->dev[0].graph != nullptr; }
+
+int o3d_cuda_set_tuned_kernels(o3d_ctx* c, int on) {
+  if (!c) return O3D_ERR_INVALID;
+  for (Device& d : c->dev) d.tuned = on != 0;
+  return O3D_OK;
+}
+
+int o3d_cuda_tuned_kernels(const o3d_ctx* c) { return c && !c->dev.empty() && c->dev[0].tuned; }
 
 int o3d_cuda_set_profiling(o3d_ctx* c, int on) {
   if (!c) return O3D_ERR_INVALID;

@@ -6,6 +6,9 @@
 #include <cstdlib>
 #include <random>
 #include <vector>
+#include <string>
+#include <cstring>
+#include <cuda.h>
 #include "../biot_pp.cuh"
 
 using namespace o3d;
@@ -98,6 +101,54 @@ int main(int argc, char** argv) {
   };
 #define RUN_S(T, B, G, SPLIT) run("scalar" #G, pp_kernel<T, G, B>, T, B, G, pk, SPLIT)
 #define RUN_P(T, B, G, SPLIT) run("packed" #G, pp2_kernel<T, G, B>, T, B, G, pk2, SPLIT)
+  // KBENCH_CUBIN=a.cubin[:b.cubin...]: time pp2_kernel<2,true,128> loaded from cubin files (tools/sass_patch.py output)
+  // through the driver API, next to the copy linked into this binary.
+  if (const char* list = getenv("KBENCH_CUBIN")) {
+    std::string all(list);
+    size_t pos = 0;
+    while (pos <= all.size()) {
+      size_t e = all.find(':', pos);
+      if (e == std::string::npos) e = all.size();
+      const std::string path = all.substr(pos, e - pos);
+      pos = e + 1;
+      if (path.empty()) continue;
+      CUmodule mod; CUfunction fn;
+      if (cuModuleLoad(&mod, path.c_str()) != CUDA_SUCCESS) { printf("cannot load %s\n", path.c_str()); continue; }
+      if (cuModuleGetFunction(&fn, mod, "_ZN3o3d10pp2_kernelILi2ELb1ELi128EEEvNS_6PPArgsE") != CUDA_SUCCESS) { printf("no kernel in %s\n", path.c_str()); continue; }
+      PPArgs a{};
+      a.src = pk2; a.ntiles = (int)(npad / kTile); a.nsplit = 1; a.nt = n;
+      a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
+      a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = out + 3 * (size_t)n; a.tug_stride = n;
+      a.partial = partial; a.sign = 1.0f; a.radius_range = no_uniform ? nullptr : range;
+      const int T = 2, BLOCK = 128;
+      const unsigned grid = (n + BLOCK * T - 1) / (BLOCK * T);
+      float best = 1e30f;
+      for (int r = 0; r < reps + 1; ++r) {
+        CHECK(cudaMemset(out, 0, (size_t)n * 12 * 4));
+        cudaEventRecord(e0);
+        void* params[] = {&a};
+        if (cuLaunchKernel(fn, grid, 1, 1, BLOCK, 1, 1, 0, 0, params, nullptr) != CUDA_SUCCESS) { printf("launch failed\n"); break; }
+        cudaEventRecord(e1);
+        CHECK(cudaDeviceSynchronize());
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 && ms < best) best = ms;
+      }
+      std::vector<float> o((size_t)n * 12);
+      CHECK(cudaMemcpy(o.data(), out, (size_t)n * 12 * 4, cudaMemcpyDeviceToHost));
+      double eu = 0, eg = 0;
+      for (int c = 0; c < nchk; ++c) {
+        const int i = (int)((long long)c * n / nchk);
+        for (int k = 0; k < 3; ++k) eu = std::fmax(eu, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
+        for (int k = 3; k < 12; ++k) eg = std::fmax(eg, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
+      }
+      // checksum over ALL outputs: a patched file must reproduce the linked kernel bit for bit
+      unsigned long long h = 1469598103934665603ull;
+      for (size_t q = 0; q < o.size(); ++q) { unsigned v; memcpy(&v, &o[q], 4); h = (h ^ v) * 1099511628211ull; }
+      const double ips = (double)n * n / (best * 1e-3);
+      printf("cubin %-40s %8.3f ms  %.3e int/s  %6.2f TFLOP/s@70  err u %.2e g %.2e  fnv %016llx\n", path.c_str(), best, ips, ips * 70e-12, eu / umax, eg / gmax, h);
+    }
+    if (getenv("KBENCH_CUBIN_ONLY")) return 0;
+  }
   RUN_S(1, 256, true, 1);
   RUN_S(2, 256, true, 1);
   RUN_S(2, 128, true, 1);

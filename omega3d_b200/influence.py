@@ -279,6 +279,13 @@ class CudaContext:
         self.check(self.lib.o3d_cuda_device_props(self.h, k, byref(sm), byref(khz), byref(peak)))
         return {"sm_count": sm.value, "clock_khz": khz.value, "fp32_peak": peak.value}
 
+    def set_tuned_kernels(self, on: bool):
+        """Particles-on-points kernel from the SASS-post-processed cubin (default) or as compiled; same results bit for bit."""
+        self.check(self.lib.o3d_cuda_set_tuned_kernels(self.h, int(on)))
+
+    def tuned_kernels(self) -> bool:
+        return bool(self.lib.o3d_cuda_tuned_kernels(self.h))
+
     def last_timing(self):
         k, a, b, n = c_double(), c_double(), c_double(), c_int()
         self.check(self.lib.o3d_cuda_last_timing(self.h, byref(k), byref(a), byref(b), byref(n)))

@@ -279,3 +279,31 @@ def test_two_device_context_equals_one_device(cuda_ctx):
     assert rel_err(pb, pa) <= 2e-7
     assert np.array_equal(I.panels_on_panels_coeff(surf, surf, cuda_ctx), I.panels_on_panels_coeff(surf, surf, ctx2))
     ctx2.close()
+
+
+# ---- the SASS-post-processed copies of pp2_kernel (tools/sass_patch.py) against the copies as compiled -------------
+@pytest.mark.parametrize("ns,nt", [(3, 5), (1000, 777), (4099, 2050), (70000, 40000)])
+@pytest.mark.parametrize("grad", [True, False])
+@pytest.mark.parametrize("uniform", [True, False])
+def test_tuned_kernels_bit_identical(cuda_ctx, ns, nt, grad, uniform):
+    """The post-pass only sets operand-reuse bits and clears yield hints: every output bit must be the same."""
+    sx, ss, r0 = W.random_cloud(ns, seed=900 + ns)
+    tx, _, _ = W.random_cloud(nt, seed=950 + nt)
+    sr = r0 if uniform else W.varied_radii(ns, 901, 0.5 * ns ** (-1 / 3), 2.0 * ns ** (-1 / 3))
+    tr = np.full(nt, r0[0], f32) if uniform else W.varied_radii(nt, 902, 0.5 * ns ** (-1 / 3), 2.0 * ns ** (-1 / 3))
+    out = []
+    assert cuda_ctx.tuned_kernels()
+    try:
+        for on in (True, False):
+            cuda_ctx.set_tuned_kernels(on)
+            assert cuda_ctx.tuned_kernels() == on
+            u = np.full((3, nt), 0.25, f32)
+            g = np.full((9, nt), -0.5, f32) if grad else None
+            cuda_ctx.pts_on_pts(sx, sr, ss, tx, tr, u, g)
+            out.append((u, g))
+    finally:
+        cuda_ctx.set_tuned_kernels(True)
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    if grad:
+        assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32))
+    assert np.all(np.isfinite(out[0][0]))

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import sass_rf_model as M  # noqa: E402
 
-WORK = "/tmp/kv"
+WORK = os.environ.get("O3D_TUNE_WORK", "/tmp/kv")
 
 # (result, op, a, b, c) - c None for 2-operand ops. Names starting with '-' are negated operands.
 # acc updates read and write acc[k]. Commutative operand pairs (a, b) may be swapped.
@@ -43,10 +43,38 @@ STMTS = [
 ]
 INPUTS = {"tx", "ty", "tz", "sx", "sy", "sz", "r2", "tk", "tk5", "m3", "wx", "wy", "wz"} | {f"acc[{k}]" for k in range(15)}
 
+# O3D_TUNE_JOINT=1: search ONE order over the statements of both register-blocked targets (T = 2) - the source operands
+# (wx wy wz sx sy sz and the constants) are shared between the two, so operand-reuse chains can span the targets.
+JOINT = os.environ.get("O3D_TUNE_JOINT", "0") == "1"
+PATCHED = os.environ.get("O3D_TUNE_PATCHED", "0") == "1"     # score the SASS after the reuse-chain post-pass
+SHARED = {"sx", "sy", "sz", "r2", "tk", "tk5", "m3", "wx", "wy", "wz"}
+
+
+def _rename(name, t):
+    if name is None:
+        return None
+    neg = name.startswith("-")
+    n = name.lstrip("-")
+    if n in SHARED:
+        out = n
+    elif n in ("tx", "ty", "tz"):
+        out = f"{n}[{t}]"
+    elif n.startswith("acc["):
+        out = f"acc[{t}]{n[3:]}"
+    else:
+        out = n + "AB"[t]
+    return ("-" if neg else "") + out
+
+
+if JOINT:
+    STMTS = [(_rename(r, t), op, _rename(a, t), _rename(b, t), _rename(c, t)) for t in (0, 1) for (r, op, a, b, c) in STMTS]
+
 PRELUDE = """    const float2 sx = f2(q0.x, q0.y), sy = f2(q0.z, q0.w), sz = f2(q1.x, q1.y);
     const float2 wx = f2(q2.x, q2.y), wy = f2(q2.z, q2.w), wz = f2(q3.x, q3.y);
     const float2 r2 = tr2, m3 = f2(-3.0f, -3.0f);
 """
+if JOINT:
+    PRELUDE = PRELUDE.replace("r2 = tr2,", "r2 = tr2[0],")
 
 
 def emit(order, swaps):
@@ -112,9 +140,18 @@ def score(args):
     cubin = os.path.join(WORK, f"one_{k}.cubin")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I" + os.path.join(ROOT, "omega3d_b200", "csrc"),
            "-DO3D_PP_POW=2", f'-DO3D_PP_BODY_FILE="{body}"', "-Xptxas", "-v", "-cubin", cu, "-o", cubin] + extra
+    if JOINT:
+        cmd[cmd.index("-DO3D_PP_POW=2") + 1] = "-DO3D_PP_JOINT=1"
+        cmd.append(f'-DO3D_PP_JOINT_FILE="{body}"')
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         return None
+    if PATCHED:                                   # score what tools/sass_patch.py makes of it
+        pc = os.path.join(WORK, f"one_{k}_p.cubin")
+        if subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_patch.py"), cubin, pc, "pp2_kernel"],
+                          capture_output=True, text=True).returncode != 0:
+            return None
+        cubin = pc
     regs = int(re.search(r"Used (\d+) registers", r.stderr).group(1))
     spill = "0 bytes spill stores" not in r.stderr
     ins = M.kernel_sass(cubin, "pp2_kernel")
