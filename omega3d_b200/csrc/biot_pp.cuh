@@ -37,8 +37,8 @@
 #define O3D_PP_BODY_FILE "pp_body_velgrad_uni.inc"
 #endif
 #ifndef O3D_PP_JOINT
-#define O3D_PP_JOINT 0    // 1: the velocity+gradient, uniform-radius loop body covers BOTH register-blocked targets in one
-#endif                    //    machine-searched statement order (O3D_PP_JOINT_FILE), so reuse chains can span the targets
+#define O3D_PP_JOINT 0    // 1 (tools/tune_order.py, O3D_TUNE_JOINT=1 only): the velocity+gradient, uniform-radius loop body covers
+#endif                    //    BOTH register-blocked targets in one searched statement order, written by the tool to O3D_PP_JOINT_FILE
 #ifndef O3D_PP_JOINT_FILE
 #define O3D_PP_JOINT_FILE "pp_body_velgrad_uni_joint.inc"
 #endif

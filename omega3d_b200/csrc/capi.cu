@@ -206,9 +206,9 @@ struct PPShape {
   dim3 grid;
   size_t work_bytes;
 };
-// CTAs resident per SM (register-limited: 162 / 128 regs x 128 threads) for the two product kernels
+// CTAs resident per SM (register-limited: 162 / 158 registers x 128 threads, lib/ptxas.log) for the two product kernels
 constexpr int kPPResidentGrad = 3;
-constexpr int kPPResidentVel = 4;
+constexpr int kPPResidentVel = 3;
 
 PPShape pp_shape(const Device& d, int64_t ntiles, int64_t nt, bool grad) {
   const int per_cta = kPPBlock * (grad ? kPPTgrad : kPPTvel);

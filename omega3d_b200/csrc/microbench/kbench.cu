@@ -114,38 +114,44 @@ int main(int argc, char** argv) {
       if (path.empty()) continue;
       CUmodule mod; CUfunction fn;
       if (cuModuleLoad(&mod, path.c_str()) != CUDA_SUCCESS) { printf("cannot load %s\n", path.c_str()); continue; }
-      if (cuModuleGetFunction(&fn, mod, "_ZN3o3d10pp2_kernelILi2ELb1ELi128EEEvNS_6PPArgsE") != CUDA_SUCCESS) { printf("no kernel in %s\n", path.c_str()); continue; }
-      PPArgs a{};
-      a.src = pk2; a.ntiles = (int)(npad / kTile); a.nsplit = 1; a.nt = n;
-      a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
-      a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = out + 3 * (size_t)n; a.tug_stride = n;
-      a.partial = partial; a.sign = 1.0f; a.radius_range = no_uniform ? nullptr : range;
-      const int T = 2, BLOCK = 128;
-      const unsigned grid = (n + BLOCK * T - 1) / (BLOCK * T);
-      float best = 1e30f;
-      for (int r = 0; r < reps + 1; ++r) {
-        CHECK(cudaMemset(out, 0, (size_t)n * 12 * 4));
-        cudaEventRecord(e0);
-        void* params[] = {&a};
-        if (cuLaunchKernel(fn, grid, 1, 1, BLOCK, 1, 1, 0, 0, params, nullptr) != CUDA_SUCCESS) { printf("launch failed\n"); break; }
-        cudaEventRecord(e1);
-        CHECK(cudaDeviceSynchronize());
-        float ms; cudaEventElapsedTime(&ms, e0, e1);
-        if (r > 0 && ms < best) best = ms;
+      struct { const char* sym; int T; bool grad; } kinds[] = {{"_ZN3o3d10pp2_kernelILi2ELb1ELi128EEEvNS_6PPArgsE", 2, true},
+                                                             {"_ZN3o3d10pp2_kernelILi4ELb0ELi128EEEvNS_6PPArgsE", 4, false}};
+      for (auto& kd : kinds) {
+        if (cuModuleGetFunction(&fn, mod, kd.sym) != CUDA_SUCCESS) continue;
+        PPArgs a{};
+        a.src = pk2; a.ntiles = (int)(npad / kTile); a.nsplit = 1; a.nt = n;
+        a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
+        a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = kd.grad ? out + 3 * (size_t)n : nullptr; a.tug_stride = n;
+        a.partial = partial; a.sign = 1.0f; a.radius_range = no_uniform ? nullptr : range;
+        const int T = kd.T, BLOCK = 128;
+        const unsigned grid = (n + BLOCK * T - 1) / (BLOCK * T);
+        float best = 1e30f;
+        for (int r = 0; r < reps + 1; ++r) {
+          CHECK(cudaMemset(out, 0, (size_t)n * 12 * 4));
+          cudaEventRecord(e0);
+          void* params[] = {&a};
+          if (cuLaunchKernel(fn, grid, 1, 1, BLOCK, 1, 1, 0, 0, params, nullptr) != CUDA_SUCCESS) { printf("launch failed\n"); break; }
+          cudaEventRecord(e1);
+          CHECK(cudaDeviceSynchronize());
+          float ms; cudaEventElapsedTime(&ms, e0, e1);
+          if (r > 0 && ms < best) best = ms;
+        }
+        std::vector<float> o((size_t)n * 12);
+        CHECK(cudaMemcpy(o.data(), out, (size_t)n * 12 * 4, cudaMemcpyDeviceToHost));
+        double eu = 0, eg = 0;
+        for (int c = 0; c < nchk; ++c) {
+          const int i = (int)((long long)c * n / nchk);
+          for (int k = 0; k < 3; ++k) eu = std::fmax(eu, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
+          if (kd.grad) for (int k = 3; k < 12; ++k) eg = std::fmax(eg, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
+        }
+        // checksum over ALL outputs: a patched file must reproduce the linked kernel bit for bit
+        unsigned long long h = 1469598103934665603ull;
+        for (size_t q = 0; q < o.size(); ++q) { unsigned v; memcpy(&v, &o[q], 4); h = (h ^ v) * 1099511628211ull; }
+        const double ips = (double)n * n / (best * 1e-3);
+        const int fl = kd.grad ? 70 : 33;
+        printf("cubin %-36s %s %8.3f ms  %.3e int/s  %6.2f TFLOP/s@%d  err u %.2e g %.2e  fnv %016llx\n", path.c_str(), kd.grad ? "velgrad" : "vel    ",
+               best, ips, ips * fl * 1e-12, fl, eu / umax, eg / gmax, h);
       }
-      std::vector<float> o((size_t)n * 12);
-      CHECK(cudaMemcpy(o.data(), out, (size_t)n * 12 * 4, cudaMemcpyDeviceToHost));
-      double eu = 0, eg = 0;
-      for (int c = 0; c < nchk; ++c) {
-        const int i = (int)((long long)c * n / nchk);
-        for (int k = 0; k < 3; ++k) eu = std::fmax(eu, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
-        for (int k = 3; k < 12; ++k) eg = std::fmax(eg, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
-      }
-      // checksum over ALL outputs: a patched file must reproduce the linked kernel bit for bit
-      unsigned long long h = 1469598103934665603ull;
-      for (size_t q = 0; q < o.size(); ++q) { unsigned v; memcpy(&v, &o[q], 4); h = (h ^ v) * 1099511628211ull; }
-      const double ips = (double)n * n / (best * 1e-3);
-      printf("cubin %-40s %8.3f ms  %.3e int/s  %6.2f TFLOP/s@70  err u %.2e g %.2e  fnv %016llx\n", path.c_str(), best, ips, ips * 70e-12, eu / umax, eg / gmax, h);
     }
     if (getenv("KBENCH_CUBIN_ONLY")) return 0;
   }
