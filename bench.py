@@ -281,6 +281,9 @@ def run_ours(args, rank, world, local_rank):
         "tflops_at_70": value * FLOPS_PER_INTERACTION * 1e-12,
         "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_nominal, "unit": "TFLOP/s", "frac": achieved / peak_nominal,
                      "traffic": dram_traffic(n, nloc),
+                     "traffic_note": "ncu dram bytes read+write of one launch (profiles/pp2_dram_traffic.json); algorithmic bytes "
+                                     f"{32 * n + 16 * nloc + 96 * nloc}; at 1M the launch splits the sources 4 ways to fill its last wave and "
+                                     "writes 403 MB of FP64 partial slabs (0.06 ms at HBM speed in a 1170 ms launch)",
                      "peak_source": f"{props['sm_count']} SMs x 128 FP32 lanes x 2 x {f_max / 1e6:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                     "MEASURED_PEAKS.json carries no FP32 figure - the path is FP32-pipe bound (arithmetic intensity ~1e6 flop/B), "
                                     "not HBM or tensor bound",

@@ -11,10 +11,13 @@ import re
 import subprocess
 import sys
 from collections import Counter
+import shutil
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 
 
 def kernels(path):
-    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    out = subprocess.run([CUOBJDUMP, "-sass", path], capture_output=True, text=True).stdout
     res = {}
     for b in re.split(r"\n\s*Function : ", out)[1:]:
         name = b.split("\n", 1)[0].strip()

@@ -13,10 +13,13 @@ usage: sass_rf_model.py <lib.so|exe> <kernel-name-substring>
 import re
 import subprocess
 import sys
+import shutil
+
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
 
 
 def kernel_sass(path, name):
-    out = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+    out = subprocess.run([CUOBJDUMP, "-sass", path], capture_output=True, text=True).stdout
     blocks = re.split(r"\n\s*Function : ", out)
     for b in blocks:
         if name in b.split("\n", 1)[0]:

@@ -47,6 +47,8 @@ INPUTS = {"tx", "ty", "tz", "sx", "sy", "sz", "r2", "tk", "tk5", "m3", "wx", "wy
 # (wx wy wz sx sy sz and the constants) are shared between the two, so operand-reuse chains can span the targets.
 JOINT = os.environ.get("O3D_TUNE_JOINT", "0") == "1"
 PATCHED = os.environ.get("O3D_TUNE_PATCHED", "0") == "1"     # score the SASS after the reuse-chain post-pass
+T0 = float(os.environ.get("O3D_TUNE_TEMP", "0.6"))
+EXTRA = os.environ.get("O3D_TUNE_EXTRA", "").split()         # extra nvcc flags for every candidate, e.g. -DO3D_PP_UNROLL_GRAD=1
 SHARED = {"sx", "sy", "sz", "r2", "tk", "tk5", "m3", "wx", "wy", "wz"}
 
 
@@ -139,7 +141,7 @@ def score(args):
         f.write('#include "biot_pp.cuh"\nusing namespace o3d;\ntemplate __global__ void o3d::pp2_kernel<2, true, 128>(const PPArgs);\n')
     cubin = os.path.join(WORK, f"one_{k}.cubin")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I" + os.path.join(ROOT, "omega3d_b200", "csrc"),
-           "-DO3D_PP_POW=2", f'-DO3D_PP_BODY_FILE="{body}"', "-Xptxas", "-v", "-cubin", cu, "-o", cubin] + extra
+           "-DO3D_PP_POW=2", f'-DO3D_PP_BODY_FILE="{body}"', "-Xptxas", "-v", "-cubin", cu, "-o", cubin] + extra + EXTRA
     if JOINT:
         cmd[cmd.index("-DO3D_PP_POW=2") + 1] = "-DO3D_PP_JOINT=1"
         cmd.append(f'-DO3D_PP_JOINT_FILE="{body}"')
@@ -168,11 +170,40 @@ def legal(order):
     return all(pos[d] < pos[i] for i in order for d in DEPS[i])
 
 
+def slot_operands(idx, swaps):
+    """(slot a, slot b) operand names of a statement as emitted (after its optional swap), negation stripped."""
+    _, op, a, b, _ = STMTS[idx]
+    if op == "rsq":
+        return (None, None)
+    if idx in swaps:
+        a, b = b, a
+    return (a.lstrip("-") if a else None, b.lstrip("-") if b else None)
+
+
 def mutate(rng, order, swaps):
+    """One to three random edits: flip an operand swap, move a statement to a random legal place, or ("chain" move) put a
+    statement next to one that reads the same operand in the same slot - the shape an operand-reuse chain has."""
     order, swaps = list(order), set(swaps)
     for _ in range(rng.choice([1, 1, 2, 3])):
-        if rng.random() < 0.25:
+        r = rng.random()
+        if r < 0.2:
             swaps ^= {rng.randrange(len(STMTS))}
+            continue
+        if r < 0.6:
+            for _ in range(50):
+                i = rng.randrange(len(order))
+                oa = slot_operands(order[i], swaps)
+                mates = [k for k in range(len(order)) if k != i and any(x is not None and x == y for x, y in zip(oa, slot_operands(order[k], swaps)))]
+                if not mates:
+                    continue
+                k = rng.choice(mates)
+                cand = list(order)
+                st = cand.pop(k)
+                pos = cand.index(order[i]) + rng.choice([0, 1])
+                cand.insert(pos, st)
+                if legal(cand):
+                    order = cand
+                    break
             continue
         for _ in range(50):
             i = rng.randrange(len(order))
@@ -242,7 +273,7 @@ def anneal(minutes, seed, jobs, start_file=None):
     rnd = 0
     while time.time() < t_end:
         frac = max(0.0, (t_end - time.time()) / (60 * minutes))
-        temp = 0.05 + 0.6 * frac                     # in cycles/pair
+        temp = T0 * (0.08 + frac)                    # in cycles per (target, source pair); O3D_TUNE_TEMP sets T0
         muts = [mutate(rng, *cur) for _ in range(jobs)]
         with ProcessPoolExecutor(jobs) as ex:
             res = list(ex.map(score, [(k + 1, m[0], m[1], []) for k, m in enumerate(muts)]))
