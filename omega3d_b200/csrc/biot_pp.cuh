@@ -312,6 +312,25 @@ __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, c
     return;
   }
 #endif
+  // the other three instantiations: searched orders where one has been adopted (same statements as the formula order below)
+#ifdef O3D_PP_BODY_FILE_GEN
+  if constexpr (GRAD && !UNI) {
+#include O3D_PP_BODY_FILE_GEN
+    return;
+  }
+#endif
+#ifdef O3D_PP_BODY_FILE_VEL
+  if constexpr (!GRAD && UNI) {
+#include O3D_PP_BODY_FILE_VEL
+    return;
+  }
+#endif
+#ifdef O3D_PP_BODY_FILE_VELGEN
+  if constexpr (!GRAD && !UNI) {
+#include O3D_PP_BODY_FILE_VELGEN
+    return;
+  }
+#endif
   const float2 dx = __fadd2_rn(tx, f2(q0.x, q0.y));
   const float2 dy = __fadd2_rn(ty, f2(q0.z, q0.w));
   const float2 dz = __fadd2_rn(tz, f2(q1.x, q1.y));

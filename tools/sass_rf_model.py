@@ -46,6 +46,19 @@ def hot_loop(ins):
     return best
 
 
+def hot_loops(ins):
+    """All innermost loops that contain MUFU.RSQ, as (first, last) instruction indices."""
+    mufu = [i for i, (_, t) in enumerate(ins) if t.startswith("MUFU.RSQ")]
+    loops = []
+    for i, (addr, t) in enumerate(ins):
+        m = re.search(r"BRA(?:\.U)?\s+(?:!?U?P\d+,\s*)?0x([0-9a-f]+)", t)
+        if m and int(m.group(1), 16) < addr:
+            j = next(k for k, (a, _) in enumerate(ins) if a == int(m.group(1), 16))
+            if any(j <= q <= i for q in mufu):
+                loops.append((j, i))
+    return [l for l in loops if not any(o != l and l[0] <= o[0] and o[1] <= l[1] for o in loops)]
+
+
 def model(body):
     cache, tot, n, three, other = {}, 0, 0, 0, 0
     for t in body:

@@ -43,6 +43,36 @@ STMTS = [
 ]
 INPUTS = {"tx", "ty", "tz", "sx", "sy", "sz", "r2", "tk", "tk5", "m3", "wx", "wy", "wz"} | {f"acc[{k}]" for k in range(15)}
 
+# O3D_TUNE_VARIANT selects which instantiation of pp_interact2 is searched (default: velocity+gradient, uniform radii):
+#   gen    velocity+gradient, per-particle radii (38 statements)      -> -DO3D_PP_BODY_FILE_GEN,    pp2_kernel<2,true,128>
+#   vel    velocity only, uniform radii (19)                          -> -DO3D_PP_BODY_FILE_VEL,    pp2_kernel<4,false,128>
+#   velgen velocity only, per-particle radii (21)                     -> -DO3D_PP_BODY_FILE_VELGEN, pp2_kernel<4,false,128>
+VARIANT = os.environ.get("O3D_TUNE_VARIANT", "uni")
+_GEOM = [("dx", "add", "tx", "sx", None), ("dy", "add", "ty", "sy", None), ("dz", "add", "tz", "sz", None)]
+_D2 = [("a1", "fma", "dz", "dz", "r2"), ("a2", "fma", "dy", "dy", "a1"), ("d2", "fma", "dx", "dx", "a2"), ("rs", "rsq", "d2", None, None)]
+_CROSS = [("t1", "mul", "dy", "wz", None), ("t2", "mul", "dx", "wz", None), ("t3", "mul", "dx", "wy", None),
+          ("cx", "fma", "dz", "wy", "-t1"), ("cy", "fma", "-dz", "wx", "t2"), ("cz", "fma", "dy", "wx", "-t3")]
+_VEL = [("acc[0]", "fma", "r3", "cx", "acc[0]"), ("acc[1]", "fma", "r3", "cy", "acc[1]"), ("acc[2]", "fma", "r3", "cz", "acc[2]")]
+_ANTI = [("acc[12]", "fma", "r3", "wx", "acc[12]"), ("acc[13]", "fma", "r3", "wy", "acc[13]"), ("acc[14]", "fma", "r3", "wz", "acc[14]")]
+_GRAD = [("bx", "mul", "bbb", "cx", None), ("by", "mul", "bbb", "cy", None), ("bz", "mul", "bbb", "cz", None),
+         ("acc[3]", "fma", "dx", "bx", "acc[3]"), ("acc[4]", "fma", "dx", "by", "acc[4]"), ("acc[5]", "fma", "dx", "bz", "acc[5]"),
+         ("acc[6]", "fma", "dy", "bx", "acc[6]"), ("acc[7]", "fma", "dy", "by", "acc[7]"), ("acc[8]", "fma", "dy", "bz", "acc[8]"),
+         ("acc[9]", "fma", "dz", "bx", "acc[9]"), ("acc[10]", "fma", "dz", "by", "acc[10]")]
+# per-particle radii: r2 = sr^2 + tr^2 per pair, top = d2 + 1.5 r2, dn5 = rs^4 rs, r3 = top dn5, bbb = dn5 (2 - 5 top rs^2)
+_CORE_GEN = [("r2", "add", "tr2", "sr2", None), ("rs2", "mul", "rs", "rs", None), ("top", "fma", "c15", "r2", "d2"),
+             ("rs4", "mul", "rs2", "rs2", None), ("dn5", "mul", "rs4", "rs", None), ("r3", "mul", "top", "dn5", None)]
+_BBB_GEN = [("tq", "mul", "top", "rs2", None), ("w", "fma", "m5", "tq", "p2"), ("bbb", "mul", "dn5", "w", None)]
+_CORE_UNI = [("rs2", "mul", "rs", "rs", None), ("rs3", "mul", "rs2", "rs", None), ("dn5", "mul", "rs3", "rs2", None), ("r3", "fma", "tk", "dn5", "rs3")]
+if VARIANT == "gen":
+    STMTS = _GEOM + [_CORE_GEN[0]] + _D2 + _CORE_GEN[1:] + _CROSS + _ANTI + _VEL + _BBB_GEN + _GRAD
+elif VARIANT == "vel":
+    STMTS = _GEOM + _D2 + _CORE_UNI + _CROSS + _VEL
+elif VARIANT == "velgen":
+    STMTS = _GEOM + [_CORE_GEN[0]] + _D2 + _CORE_GEN[1:] + _CROSS + _VEL
+KERNEL = "pp2_kernel<2, true, 128>" if VARIANT in ("uni", "gen") else "pp2_kernel<4, false, 128>"
+BODY_MACRO = {"uni": "O3D_PP_BODY_FILE", "gen": "O3D_PP_BODY_FILE_GEN", "vel": "O3D_PP_BODY_FILE_VEL", "velgen": "O3D_PP_BODY_FILE_VELGEN"}[VARIANT]
+PER_BODY = len([st for st in STMTS if st[1] != "rsq"])        # packed instructions per (target, source pair): picks the loop
+
 # O3D_TUNE_JOINT=1: search ONE order over the statements of both register-blocked targets (T = 2) - the source operands
 # (wx wy wz sx sy sz and the constants) are shared between the two, so operand-reuse chains can span the targets.
 JOINT = os.environ.get("O3D_TUNE_JOINT", "0") == "1"
@@ -75,6 +105,9 @@ PRELUDE = """    const float2 sx = f2(q0.x, q0.y), sy = f2(q0.z, q0.w), sz = f2(
     const float2 wx = f2(q2.x, q2.y), wy = f2(q2.z, q2.w), wz = f2(q3.x, q3.y);
     const float2 r2 = tr2, m3 = f2(-3.0f, -3.0f);
 """
+if VARIANT in ("gen", "velgen"):
+    PRELUDE = PRELUDE.replace("const float2 r2 = tr2, m3 = f2(-3.0f, -3.0f);",
+                              "const float2 sr2 = f2(q1.z, q1.w), c15 = f2(1.5f, 1.5f), m5 = f2(-5.0f, -5.0f), p2 = f2(2.0f, 2.0f);")
 if JOINT:
     PRELUDE = PRELUDE.replace("r2 = tr2,", "r2 = tr2[0],")
 
@@ -138,10 +171,10 @@ def score(args):
         f.write(emit(order, swaps))
     cu = os.path.join(WORK, f"one_{k}.cu")
     with open(cu, "w") as f:
-        f.write('#include "biot_pp.cuh"\nusing namespace o3d;\ntemplate __global__ void o3d::pp2_kernel<2, true, 128>(const PPArgs);\n')
+        f.write('#include "biot_pp.cuh"\nusing namespace o3d;\ntemplate __global__ void o3d::' + KERNEL + '(const PPArgs);\n')
     cubin = os.path.join(WORK, f"one_{k}.cubin")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I" + os.path.join(ROOT, "omega3d_b200", "csrc"),
-           "-DO3D_PP_POW=2", f'-DO3D_PP_BODY_FILE="{body}"', "-Xptxas", "-v", "-cubin", cu, "-o", cubin] + extra + EXTRA
+           "-DO3D_PP_POW=2", f'-D{BODY_MACRO}="{body}"', "-Xptxas", "-v", "-cubin", cu, "-o", cubin] + extra + EXTRA
     if JOINT:
         cmd[cmd.index("-DO3D_PP_POW=2") + 1] = "-DO3D_PP_JOINT=1"
         cmd.append(f'-DO3D_PP_JOINT_FILE="{body}"')
@@ -157,10 +190,16 @@ def score(args):
     regs = int(re.search(r"Used (\d+) registers", r.stderr).group(1))
     spill = "0 bytes spill stores" not in r.stderr
     ins = M.kernel_sass(cubin, "pp2_kernel")
-    j, i = M.hot_loop(ins)
-    bodyins = [t for _, t in ins[j:i + 1]]
-    n, three, tot, other = M.model(bodyins)
-    nm = sum(1 for t in bodyins if t.startswith("MUFU"))
+    best = None
+    for j, i in M.hot_loops(ins):                # the kernel holds a uniform-radius and a per-particle-radius loop
+        bodyins = [t for _, t in ins[j:i + 1]]
+        n, three, tot, other = M.model(bodyins)
+        nm = sum(1 for t in bodyins if t.startswith("MUFU"))
+        if nm and abs(n / (nm / 2.0) - PER_BODY) < 0.5:
+            best = (n, three, tot, other, nm)
+    if best is None:
+        return None
+    n, three, tot, other, nm = best
     per_pair = (tot + other) / (nm / 2.0)        # modelled cycles per (target, source pair)
     return per_pair, n, three, tot + other, regs, spill
 
@@ -244,7 +283,7 @@ def parse_body(path):
     order, swaps = [], set()
     for line in open(path):
         m = re.match(r"\s+(?:const float2 )?([\w\[\]]+) = (__f\w+2_rn|f2)\((.*)\);", line)
-        if not m or m.group(1) in ("sx", "wx", "r2"):
+        if not m or line.lstrip().startswith(("const float2 sx =", "const float2 wx =", "const float2 r2 = tr2", "const float2 sr2 = f2(q1")):
             continue
         res = m.group(1)
         idx = next(k for k, st in enumerate(STMTS) if st[0] == res)
