@@ -34,7 +34,16 @@
 #define O3D_PP_POW 2      // 1: uniform-radius path forms r3 and bbb from odd powers of rs (two packed instructions fewer);
 #endif                    // 2: ... with the two constants as 32-bit broadcast operands and the searched statement order
 #ifndef O3D_PP_BODY_FILE
-#define O3D_PP_BODY_FILE "pp_body_velgrad_uni.inc"
+#define O3D_PP_BODY_FILE "pp_body_velgrad_uni.inc"       // velocity + gradient, uniform radii (the 1M-16M benchmark path)
+#endif
+#ifndef O3D_PP_BODY_FILE_GEN
+#define O3D_PP_BODY_FILE_GEN "pp_body_velgrad_gen.inc"   // velocity + gradient, per-particle radii
+#endif
+#ifndef O3D_PP_BODY_FILE_VEL
+#define O3D_PP_BODY_FILE_VEL "pp_body_vel_uni.inc"       // velocity only, uniform radii
+#endif
+#ifndef O3D_PP_BODY_FILE_VELGEN
+#define O3D_PP_BODY_FILE_VELGEN "pp_body_vel_gen.inc"    // velocity only, per-particle radii
 #endif
 #ifndef O3D_PP_JOINT
 #define O3D_PP_JOINT 0    // 1 (tools/tune_order.py, O3D_TUNE_JOINT=1 only): the velocity+gradient, uniform-radius loop body covers
@@ -311,21 +320,16 @@ __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, c
 #include O3D_PP_BODY_FILE
     return;
   }
-#endif
-  // the other three instantiations: searched orders where one has been adopted (same statements as the formula order below)
-#ifdef O3D_PP_BODY_FILE_GEN
+  // the other three instantiations, each in its own searched order (same statements as the formula order below, which
+  // is what O3D_PP_POW < 2 builds and what documents the dataflow)
   if constexpr (GRAD && !UNI) {
 #include O3D_PP_BODY_FILE_GEN
     return;
   }
-#endif
-#ifdef O3D_PP_BODY_FILE_VEL
   if constexpr (!GRAD && UNI) {
 #include O3D_PP_BODY_FILE_VEL
     return;
   }
-#endif
-#ifdef O3D_PP_BODY_FILE_VELGEN
   if constexpr (!GRAD && !UNI) {
 #include O3D_PP_BODY_FILE_VELGEN
     return;
