@@ -234,6 +234,24 @@ int o3d_cuda_particles_write_vtu(o3d_ctx* ctx, o3d_particles* p, const char* pat
 int o3d_cuda_set_tuned_kernels(o3d_ctx* ctx, int on);
 int o3d_cuda_tuned_kernels(const o3d_ctx* ctx);
 
+/* Core function of the particle kernels. The reference selects it per BUILD by moving the one active
+ * "#define USE_*_KERNEL" in src/CoreFunc.h:35-38; here it is a property of the context, Winckelmans-Leonard (the
+ * define the reference ships with) by default. integration/O3DCudaInfluence.h passes the value that matches the
+ * define its translation unit was compiled with, so the CUDA arm always follows the reference build it sits in.
+ * Applies to particles -> points (all four variants, host and *_dev entry points, resident particle collections)
+ * and to every flops_out figure (flops_t{v,p}_{grads,nograds}, src/CoreFunc.h); panel leaves evaluate the cores
+ * at zero radius, where all four coincide. A packed source stream (o3d_cuda_pack_sources_dev) carries the radius
+ * term of the core that was set when it was packed: set the core first, then pack, then evaluate.
+ * o3d_cuda_core_func returns the current value (-1 on a NULL context). */
+enum o3d_core_func {
+  O3D_CORE_WL = 0,   /* Winckelmans-Leonard      src/CoreFunc.h:241-289 */
+  O3D_CORE_RM = 1,   /* Rosenhead-Moore          src/CoreFunc.h:43-83   */
+  O3D_CORE_EXP = 2,  /* exponential              src/CoreFunc.h:86-238  */
+  O3D_CORE_V2 = 3    /* Vatistas n = 2           src/CoreFunc.h:292-341 */
+};
+int o3d_cuda_set_core_func(o3d_ctx* ctx, int core);
+int o3d_cuda_core_func(const o3d_ctx* ctx);
+
 /* ---- measurement helpers ----------------------------------------------------------------------------- */
 /* When on, o3d_cuda_pts_on_pts_dev brackets its dominant kernel with CUDA events on the launching stream;
  * o3d_cuda_dev_kernel_ms waits for the last such launch and returns its device time in milliseconds. */

@@ -29,6 +29,19 @@
 
 namespace o3d {
 
+// The core function of the reference build this header is compiled into: src/CoreFunc.h:35-38 leaves exactly one
+// USE_*_KERNEL defined (USE_WL_KERNEL as shipped) and src/Kernels.h includes it before the patched Influence.h /
+// Coefficients.h include this header, so the CUDA arm follows an edit of that line like every CPU arm does.
+#if defined(USE_RM_KERNEL)
+constexpr int kCudaCoreFunc = O3D_CORE_RM;
+#elif defined(USE_EXPONENTIAL_KERNEL)
+constexpr int kCudaCoreFunc = O3D_CORE_EXP;
+#elif defined(USE_V2_KERNEL)
+constexpr int kCudaCoreFunc = O3D_CORE_V2;
+#else
+constexpr int kCudaCoreFunc = O3D_CORE_WL;
+#endif
+
 // One context per process, created on first use. Devices: all visible GPUs, or the first
 // $O3D_CUDA_NDEV of them (targets are partitioned across them inside the library).
 inline o3d_ctx* cuda_context() {
@@ -45,6 +58,7 @@ inline o3d_ctx* cuda_context() {
         std::fprintf(stderr, "Omega3D gpu_cuda arm: no usable sm_100 device (o3d_cuda_create -> %d); there is no CPU fallback in this arm\n", rc);
         std::abort();
       }
+      o3d_cuda_set_core_func(ctx, kCudaCoreFunc);
     }
     ~Holder() { o3d_cuda_destroy(ctx); }
   };

@@ -57,6 +57,8 @@ SYMBOLS = {
     "o3d_cuda_particles_graph_active": (c_int, [c_void_p]),
     "o3d_cuda_set_tuned_kernels": (c_int, [c_void_p, c_int]),
     "o3d_cuda_tuned_kernels": (c_int, [c_void_p]),
+    "o3d_cuda_set_core_func": (c_int, [c_void_p, c_int]),
+    "o3d_cuda_core_func": (c_int, [c_void_p]),
     "o3d_cuda_set_profiling": (c_int, [c_void_p, c_int]),
     "o3d_cuda_dev_kernel_ms": (c_int, [c_void_p, POINTER(c_double)]),
     "o3d_cuda_probe_fp32_peak": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),

@@ -1,0 +1,243 @@
+// biot_pp_cores.cuh - particles -> points with the ALTERNATE core functions of the reference's src/CoreFunc.h.
+//
+// The reference picks its core function per build by moving one "#define USE_*_KERNEL" (src/CoreFunc.h:35-38);
+// Winckelmans-Leonard is the shipped one and has its own searched, SASS-post-processed kernel (biot_pp.cuh:
+// pp2_kernel). The other three - Rosenhead-Moore (:43-83), exponential (:86-238), Vatistas n=2 (:292-341) - run
+// through ppc_kernel below: the same tile ring (cp.async.bulk + mbarrier), the same packed record stream, the same
+// register blocking, FP32 tile sums promoted to FP64 once per tile and the same read-modify-write epilogue; only the
+// radial factors (r3, bbb) differ. Everything after them - c = w x d, u += r3 c, G += d (x) (bbb c), the
+// antisymmetric A = sum w r3 and the trace-free ninth slot - is core-independent (src/Kernels.h:155-193).
+//
+// The radius lane of a packed record holds what the selected core adds per SOURCE (pp_pack2_kernel, formed exactly
+// as the reference forms it) and each thread keeps the matching per-TARGET term:
+//     Rosenhead-Moore   r2 = |d|^2 + sr*sr + tr*tr            lane sr*sr          target tr*tr
+//     exponential       corefac = 1/(sr*sr*sr + tr*tr*tr)     lane sr*sr*sr       target tr*tr*tr
+//     Vatistas n=2      denom = |d|^4 + s2*s2 + t2*t2         lane (sr*sr)^2      target (tr*tr)^2
+// Singular targets (core_func(distsq, sr)) are the same formulas with a zero target term.
+#pragma once
+#include "biot_pp.cuh"
+
+namespace o3d {
+
+constexpr int kCoreWL = 0, kCoreRM = 1, kCoreEXP = 2, kCoreV2 = 3;   // == O3D_CORE_* (include/o3d_cuda.h)
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// what one particle's core radius contributes to the pair term, in the reference's operation order
+__host__ __device__ __forceinline__ float core_radius_term(const int core, const float r) {
+  const float r2 = r * r;
+  return core == kCoreEXP ? r2 * r : core == kCoreV2 ? r2 * r2 : r2;
+}
+
+// Exponential core, one lane (src/CoreFunc.h:114-128 exp_cond, :158-172 exp_bbb, :213-238). Branch-free selects: at
+// |d| = 0 the unselected operands are inf / NaN exactly as in the reference's scalar code, where they are never read
+// (reld3 = 0 takes the "< 0.001" arm: r3 = corefac, bbb = -1.5 * 0 * r3 * r3 = 0).
+template <bool GRAD>
+__device__ __forceinline__ void exp_core_lane(const float dsq, const float st, float& r3, float& bbb) {
+  const float dist = sqrt_approx(dsq);
+  const float d3 = dsq * dist;
+  const float cf = rcp_approx(st);
+  const float reld3 = d3 * cf;
+  const float ood3 = rcp_approx(d3);
+  const float e = expf(-reld3);
+  const bool far = reld3 > 16.0f, near = reld3 < 0.001f;
+  r3 = far ? ood3 : near ? cf : ood3 * (1.0f - e);
+  if constexpr (GRAD) {
+    const float oodsq = ood3 * dist;                      // 1 / |d|^2
+    const float b_far = -3.0f * r3 * oodsq;
+    const float b_near = -1.5f * dist * r3 * r3;
+    const float b_mid = 3.0f * (cf * e - r3) * oodsq;
+    bbb = far ? b_far : near ? b_near : b_mid;
+  }
+}
+
+// Two sources (one packed record pair) on one target. st = source lane + target term (see the table above).
+template <int CORE, bool GRAD>
+__device__ __forceinline__ void ppc_interact2(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
+                                              const float2 tx, const float2 ty, const float2 tz, const float2 tt,
+                                              float2 (&acc)[PPAcc<GRAD>::N]) {
+  const float2 dx = __fadd2_rn(tx, f2(q0.x, q0.y));
+  const float2 dy = __fadd2_rn(ty, f2(q0.z, q0.w));
+  const float2 dz = __fadd2_rn(tz, f2(q1.x, q1.y));
+  const float2 st = __fadd2_rn(tt, f2(q1.z, q1.w));
+  const float2 wx = f2(q2.x, q2.y), wy = f2(q2.z, q2.w), wz = f2(q3.x, q3.y);
+  float2 r3, bbb = f2(0.f, 0.f);
+  if constexpr (CORE == kCoreRM) {
+    // r3 = r2^-1.5, bbb = -3 r3 / r2 with r2 = |d|^2 + sr^2 + tr^2
+    const float2 r2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, st)));
+    const float2 rs = f2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
+    const float2 rs2 = __fmul2_rn(rs, rs);
+    r3 = __fmul2_rn(rs2, rs);
+    if constexpr (GRAD) bbb = __fmul2_rn(__fmul2_rn(f2(-3.0f, -3.0f), rs2), r3);
+  } else if constexpr (CORE == kCoreV2) {
+    // r3 = denom^-0.75, bbb = -3 r3 / sqrt(denom) with denom = |d|^4 + sr^4 + tr^4
+    const float2 dsq = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+    const float2 denom = __ffma2_rn(dsq, dsq, st);
+    const float2 rq = f2(rsqrt_approx(denom.x), rsqrt_approx(denom.y));     // denom^-1/2
+    const float2 sq = f2(sqrt_approx(rq.x), sqrt_approx(rq.y));             // denom^-1/4
+    r3 = __fmul2_rn(rq, sq);
+    if constexpr (GRAD) bbb = __fmul2_rn(__fmul2_rn(f2(-3.0f, -3.0f), rq), r3);
+  } else {
+    const float2 dsq = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+    exp_core_lane<GRAD>(dsq.x, st.x, r3.x, bbb.x);
+    exp_core_lane<GRAD>(dsq.y, st.y, r3.y, bbb.y);
+  }
+  // c = (dz wy - dy wz, dx wz - dz wx, dy wx - dx wy)
+  const float2 t1 = __fmul2_rn(dy, wz);
+  const float2 t2 = __fmul2_rn(dx, wz);
+  const float2 t3 = __fmul2_rn(dx, wy);
+  float2 cx = __ffma2_rn(dz, wy, neg2(t1));
+  float2 cy = __ffma2_rn(neg2(dz), wx, t2);
+  float2 cz = __ffma2_rn(dy, wx, neg2(t3));
+  if constexpr (GRAD) {
+    acc[12] = __ffma2_rn(r3, wx, acc[12]);
+    acc[13] = __ffma2_rn(r3, wy, acc[13]);
+    acc[14] = __ffma2_rn(r3, wz, acc[14]);
+  }
+  acc[0] = __ffma2_rn(r3, cx, acc[0]);
+  acc[1] = __ffma2_rn(r3, cy, acc[1]);
+  acc[2] = __ffma2_rn(r3, cz, acc[2]);
+  if constexpr (GRAD) {
+    cz = __fmul2_rn(bbb, cz);
+    cy = __fmul2_rn(bbb, cy);
+    cx = __fmul2_rn(bbb, cx);
+    acc[3]  = __ffma2_rn(dx, cx, acc[3]);
+    acc[4]  = __ffma2_rn(dx, cy, acc[4]);
+    acc[5]  = __ffma2_rn(dx, cz, acc[5]);
+    acc[8]  = __ffma2_rn(dy, cz, acc[8]);
+    acc[7]  = __ffma2_rn(dy, cy, acc[7]);
+    acc[6]  = __ffma2_rn(dy, cx, acc[6]);
+    acc[9]  = __ffma2_rn(dz, cx, acc[9]);
+    acc[10] = __ffma2_rn(dz, cy, acc[10]);
+    // acc[11] (wz slot): trace-free, recovered as -(ux + vy) per tile - d . (d x w) = 0 whatever the core
+  }
+}
+
+template <int CORE, int T, bool GRAD, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) ppc_kernel(const PPArgs p) {
+  constexpr int NS = GRAD ? 12 : 3;
+  constexpr int NA = PPAcc<GRAD>::N;
+  __shared__ alignas(128) float4 tile[2][kTile * 2];
+  __shared__ alignas(8) uint64_t full[2];
+
+  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int k0 = blockIdx.y * per;
+  const int k1 = min(p.ntiles, k0 + per);
+  const int nk = k1 - k0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      if (s < nk) {
+        mbar_expect_tx(&full[s], kTileBytes);
+        bulk_g2s(tile[s], p.src + (size_t)(k0 + s) * (kTile * 2), kTileBytes, &full[s]);
+      }
+  }
+
+  float2 tx[T], ty[T], tz[T], tt[T];
+  const int64_t base = (int64_t)blockIdx.x * (BLOCK * T) + threadIdx.x;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
+    tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
+    const float term = core_radius_term(CORE, p.tr ? p.tr[i] : 0.0f);
+    tt[t] = f2(term, term);
+  }
+
+  double sum[T][NS];
+  float2 acc[T][NA];
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+#pragma unroll
+    for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) acc[t][k] = f2(0.f, 0.f);
+  }
+
+  for (int k = 0; k < nk; ++k) {
+    const int buf = k & 1;
+    mbar_wait(&full[buf], (k >> 1) & 1);
+    const float4* __restrict__ s = tile[buf];
+#pragma unroll(CORE == kCoreEXP ? 1 : 2)
+    for (int j = 0; j < kTile / 2; ++j) {
+      const float4 q0 = s[4 * j], q1 = s[4 * j + 1], q2 = s[4 * j + 2], q3 = s[4 * j + 3];
+#pragma unroll
+      for (int t = 0; t < T; ++t) ppc_interact2<CORE, GRAD>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tt[t], acc[t]);
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      float h[NA];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) { h[q] = acc[t][q].x + acc[t][q].y; acc[t][q] = f2(0.f, 0.f); }
+      if constexpr (GRAD) h[11] = -(h[3] + h[7]);
+      pp_promote<GRAD>(h, sum[t]);
+    }
+    __syncthreads();  // every warp is done with tile[buf]; safe to refill
+    if (threadIdx.x == 0 && k + 2 < nk) {
+      mbar_expect_tx(&full[buf], kTileBytes);
+      bulk_g2s(tile[buf], p.src + (size_t)(k0 + k + 2) * (kTile * 2), kTileBytes, &full[buf]);
+    }
+  }
+
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const int64_t i = base + (int64_t)t * BLOCK;
+    if (i >= p.nt) continue;
+    if (p.nsplit > 1) {
+      double* slab = p.partial + (size_t)blockIdx.y * NS * p.nt;   // summed in slice order by pp_finish_kernel
+#pragma unroll
+      for (int k = 0; k < NS; ++k) slab[(size_t)k * p.nt + i] = sum[t][k];
+    } else {
+      const double sg = (double)p.sign;
+      p.tu[i] = (float)((double)p.tu[i] + sg * sum[t][0]);
+      p.tv[i] = (float)((double)p.tv[i] + sg * sum[t][1]);
+      p.tw[i] = (float)((double)p.tw[i] + sg * sum[t][2]);
+      if constexpr (GRAD) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          float* g = p.tug + (size_t)k * p.tug_stride + i;
+          *g = (float)((double)*g + sum[t][3 + k]);
+        }
+      }
+    }
+  }
+}
+
+// pp_pack2_kernel's record layout with the radius lane of the selected core (core_radius_term); padding records keep
+// zero strength and a unit lane: they add exactly 0 under every core.
+__global__ void ppc_pack2_kernel(int core, int64_t ns, int64_t ns_pad, const float* sx, const float* sy, const float* sz,
+                                 const float* sr, const float* wx, const float* wy, const float* wz, float4* out) {
+  const int64_t pr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // pair index
+  if (2 * pr >= ns_pad) return;
+  float x[2], y[2], z[2], rt[2], a[2], b[2], c[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t j = 2 * pr + h;
+    x[h] = y[h] = z[h] = 0.f; rt[h] = 1.f; a[h] = b[h] = c[h] = 0.f;
+    if (j < ns) {
+      x[h] = -sx[j]; y[h] = -sy[j]; z[h] = -sz[j]; rt[h] = core_radius_term(core, sr ? sr[j] : 0.0f);
+      a[h] = wx[j]; b[h] = wy[j]; c[h] = wz[j];
+    }
+  }
+  out[4 * pr + 0] = make_float4(x[0], x[1], y[0], y[1]);
+  out[4 * pr + 1] = make_float4(z[0], z[1], rt[0], rt[1]);
+  out[4 * pr + 2] = make_float4(a[0], a[1], b[0], b[1]);
+  out[4 * pr + 3] = make_float4(c[0], c[1], 0.f, 0.f);
+}
+
+}  // namespace o3d

@@ -16,6 +16,7 @@
 #include "../../include/o3d_cuda.h"
 #include "biot_panel.cuh"
 #include "biot_pp.cuh"
+#include "biot_pp_cores.cuh"
 #include "convect.cuh"
 #include "reflect.cuh"
 #include "vtu_writer.h"
@@ -82,6 +83,7 @@ struct Device {
   cudaEvent_t evk[2] = {nullptr, nullptr};                   // around the dominant kernel of a *_dev call
   bool profile = false;
   bool tuned = true;                                         // launch pp2_kernel from the post-processed cubin (TunedKernels)
+  int core = O3D_CORE_WL;                                    // core function of the particle kernels (o3d_cuda_set_core_func)
   DevBuf src, packed, targ, out, work, geom, panels, tpanels, cnt, rng;
   unsigned long long counts[2] = {0, 0};  // leaves, splits of the last panel call on this device
   // result of the last call on this device
@@ -210,6 +212,18 @@ struct PPShape {
 constexpr int kPPResidentGrad = 3;
 constexpr int kPPResidentVel = 3;
 
+// pair-term flops of the reference's core functions, src/CoreFunc.h: flops_tv_grads / flops_tp_grads /
+// flops_tv_nograds / flops_tp_nograds for WL (:251-288), Rosenhead-Moore (:50-82), exponential (:202-237), Vatistas (:304-340)
+double core_flops(int core, bool grad, bool blob) {
+  static const double t[4][4] = {{16, 14, 10, 8}, {9, 7, 7, 5}, {14, 11, 12, 9}, {13, 10, 11, 8}};
+  return t[core][(grad ? 0 : 2) + (blob ? 0 : 1)];
+}
+// flops per interaction as the reference's routines report them: flops_0v_0bg = 54 + tv_grads, _0pg = 54 + tp_grads,
+// _0b = 23 + tv_nograds, _0p = 23 + tp_nograds (src/Kernels.h:50,94,155,253); WL: 70 / 68 / 33 / 31
+double pp_pair_flops(int core, bool grad, bool blob) { return (grad ? 54.0 : 23.0) + core_flops(core, grad, blob); }
+// ... and of the panel leaves: flops_0vs_0pg = 79 + tp_grads, flops_0vs_0p = 29 + tp_nograds (src/Kernels.h:115,294); WL: 93 / 37
+double leaf_flops(int core, bool grad) { return (grad ? 79.0 : 29.0) + core_flops(core, grad, false); }
+
 PPShape pp_shape(const Device& d, int64_t ntiles, int64_t nt, bool grad) {
   const int per_cta = kPPBlock * (grad ? kPPTgrad : kPPTvel);
   const int64_t gx = (nt + per_cta - 1) / per_cta;
@@ -259,15 +273,27 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
     }
     a.partial = workspace;
   }
-  // radius ranges for the uniform-radius fast path (one pass over the records' r^2 lane and the target radii)
-  O3D_TRY(d, d.rng.ensure(4 * sizeof(uint32_t)));
-  O3D_TRY(d, cudaMemsetAsync(d.rng.p, 0, 4 * sizeof(uint32_t), st));
-  pp_scan_kernel<<<d.sm_count * 4, 256, 0, st>>>(nrec, packed, nt, tr, d.rng.as<uint32_t>());
-  O3D_TRY(d, cudaGetLastError());
-  d.launches += 1;
-  a.radius_range = d.rng.as<uint32_t>();
+  if (d.core == O3D_CORE_WL) {
+    // radius ranges for the uniform-radius fast path (one pass over the records' r^2 lane and the target radii)
+    O3D_TRY(d, d.rng.ensure(4 * sizeof(uint32_t)));
+    O3D_TRY(d, cudaMemsetAsync(d.rng.p, 0, 4 * sizeof(uint32_t), st));
+    pp_scan_kernel<<<d.sm_count * 4, 256, 0, st>>>(nrec, packed, nt, tr, d.rng.as<uint32_t>());
+    O3D_TRY(d, cudaGetLastError());
+    d.launches += 1;
+    a.radius_range = d.rng.as<uint32_t>();
+  }
   if (d.profile) O3D_TRY(d, cudaEventRecord(d.evk[0], st));
-  if (d.tuned) {
+  if (d.core != O3D_CORE_WL) {
+    // the alternate core functions of src/CoreFunc.h (csrc/biot_pp_cores.cuh); the stream was packed for d.core
+    a.radius_range = nullptr;
+#define O3D_PPC_LAUNCH(CORE)                                                                          \
+  if (grad) ppc_kernel<CORE, kPPTgrad, true, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a);               \
+  else      ppc_kernel<CORE, kPPTvel, false, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a)
+    if (d.core == O3D_CORE_RM) { O3D_PPC_LAUNCH(kCoreRM); }
+    else if (d.core == O3D_CORE_EXP) { O3D_PPC_LAUNCH(kCoreEXP); }
+    else { O3D_PPC_LAUNCH(kCoreV2); }
+#undef O3D_PPC_LAUNCH
+  } else if (d.tuned) {
     const TunedKernels& tk = tuned_kernels();
     void* params[] = {&a};
     O3D_TRY(d, cudaLaunchKernel((const void*)(grad ? tk.grad : tk.vel), s.grid, dim3(kPPBlock), params, 0, st));
@@ -291,7 +317,9 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
 bool launch_pack(Device& d, cudaStream_t st, int64_t ns, const float* sx, const float* sy, const float* sz,
                  const float* sr, const float* wx, const float* wy, const float* wz, float4* packed, int64_t nrec = 0) {
   const int64_t npad = nrec > 0 ? nrec : padded_sources(ns);
-  pp_pack2_kernel<<<(unsigned)((npad / 2 + 255) / 256), 256, 0, st>>>(ns, npad, sx, sy, sz, sr, wx, wy, wz, packed);
+  const unsigned blocks = (unsigned)((npad / 2 + 255) / 256);
+  if (d.core == O3D_CORE_WL) pp_pack2_kernel<<<blocks, 256, 0, st>>>(ns, npad, sx, sy, sz, sr, wx, wy, wz, packed);
+  else ppc_pack2_kernel<<<blocks, 256, 0, st>>>(d.core, ns, npad, sx, sy, sz, sr, wx, wy, wz, packed);   // radius lane of that core
   O3D_TRY(d, cudaGetLastError());
   d.launches += 1;
   return true;
@@ -354,6 +382,8 @@ struct PartDev {
   cudaGraphExec_t graph = nullptr;      // one captured advect step (single-device contexts)
   int64_t graph_n = -1;
   int graph_order = 0;
+  int graph_core = -1;                  // core function / kernel copy the captured launches belong to
+  bool graph_tuned = true;
   double graph_dt = 0, graph_fs[3] = {0, 0, 0};
   bool graph_failed = false;
   int launches_per_step = 0;
@@ -719,8 +749,8 @@ int o3d_cuda_pts_on_pts(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
       if (nt > 0 && !tug[k]) return fail(c, O3D_ERR_INVALID, "pts_on_pts: NULL gradient array");
   const bool grad = tug != nullptr;
   if (flops_out) {
-    // src/Influence.h:310 (0pg: 68), :366 (0p: 31), :475 (0bg: 70), :534 (0b: 33)
-    const double per = grad ? (tr ? 70.0 : 68.0) : (tr ? 33.0 : 31.0);
+    // src/Influence.h:310 (0pg: 68), :366 (0p: 31), :475 (0bg: 70), :534 (0b: 33) with the WL core
+    const double per = pp_pair_flops(c->dev[0].core, grad, tr != nullptr);
     *flops_out = (double)nt * ((grad ? 12.0 : 3.0) + per * (double)ns);
   }
   for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
@@ -907,7 +937,7 @@ int o3d_cuda_pan_on_pts(o3d_ctx* c, int64_t nn, const float* nx, const float* ny
     double leaves = 0, splits = 0;
     for (Device& d : c->dev) leaves += (double)d.counts[0], splits += (double)d.counts[1];
     leaves -= (double)nt * (double)(npad - np);  // padding records are always one leaf
-    *flops_out = (double)nt * (double)np * 4.0 + (leaves + splits) * 20.0 + leaves * (grad ? 93.0 : 37.0) +
+    *flops_out = (double)nt * (double)np * 4.0 + (leaves + splits) * 20.0 + leaves * leaf_flops(c->dev[0].core, grad) +
                  splits * 23.0 + (double)nt * (grad ? 12.0 : 3.0);
   }
   return rc;
@@ -978,7 +1008,8 @@ int o3d_cuda_pts_on_pan(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
   if (rc == O3D_OK && flops_out) {
     double leaves = 0, splits = 0;
     for (Device& d : c->dev) leaves += (double)d.counts[0], splits += (double)d.counts[1];
-    *flops_out = (double)ns * (double)np * 4.0 + (leaves + splits) * 20.0 + leaves * 37.0 + splits * 23.0 + 3.0 * (double)np;
+    *flops_out = (double)ns * (double)np * 4.0 + (leaves + splits) * 20.0 + leaves * leaf_flops(c->dev[0].core, false) +
+                 splits * 23.0 + 3.0 * (double)np;
   }
   return rc;
 }
@@ -1221,7 +1252,8 @@ int o3d_cuda_particles_find_vels(o3d_ctx* c, o3d_particles* p, const double* fs,
   if (!c || !p || !fs || p->dev.size() != c->dev.size()) return fail(c, O3D_ERR_INVALID, "particles_find_vels: bad argument");
   for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
   const double n = (double)p->n;
-  if (flops_out) *flops_out = want_grad ? n * (12.0 + 70.0 * n) : n * (3.0 + 33.0 * n);   // src/Influence.h:475,534
+  if (flops_out)   // src/Influence.h:475,534
+    *flops_out = want_grad ? n * (12.0 + pp_pair_flops(c->dev[0].core, true, true) * n) : n * (3.0 + pp_pair_flops(c->dev[0].core, false, true) * n);
   if (p->n == 0) return collect(c);
   if (part_find_vels(c, p, 0, fs, want_grad != 0, false)) part_sync_all(c, p);
   return collect(c);
@@ -1234,7 +1266,7 @@ int o3d_cuda_particles_advect(o3d_ctx* c, o3d_particles* p, int order, double ti
     return fail(c, O3D_ERR_INVALID, "particles_advect: bad argument");
   for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
   const double n = (double)p->n;
-  if (flops_out) *flops_out = (double)nsteps * order * n * (12.0 + 70.0 * n);
+  if (flops_out) *flops_out = (double)nsteps * order * n * (12.0 + pp_pair_flops(c->dev[0].core, true, true) * n);
   if (p->n == 0 || nsteps == 0) return collect(c);
   const int nd = (int)c->dev.size();
   auto run = [&]() {
@@ -1252,6 +1284,7 @@ int o3d_cuda_particles_advect(o3d_ctx* c, o3d_particles* p, int order, double ti
     Device& d0 = c->dev[0];
     PartDev& q0 = p->dev[0];
     const bool same = c->use_graphs && q0.graph && q0.graph_n == p->n && q0.graph_order == order && q0.graph_dt == dt &&
+                      q0.graph_core == d0.core && q0.graph_tuned == d0.tuned &&
                       q0.graph_fs[0] == fs[0] && q0.graph_fs[1] == fs[1] && q0.graph_fs[2] == fs[2];
     if (!same) part_release_graph(q0);
     int per_step = 0;
@@ -1284,6 +1317,7 @@ int o3d_cuda_particles_advect(o3d_ctx* c, o3d_particles* p, int order, double ti
           q0.graph_failed = true;
         } else {
           q0.graph_n = p->n; q0.graph_order = order; q0.graph_dt = dt;
+          q0.graph_core = d0.core; q0.graph_tuned = d0.tuned;
           for (int a = 0; a < 3; ++a) q0.graph_fs[a] = fs[a];
           q0.launches_per_step = per_step;
         }
@@ -1604,6 +1638,15 @@ int o3d_cuda_set_tuned_kernels(o3d_ctx* c, int on) {
 }
 
 int o3d_cuda_tuned_kernels(const o3d_ctx* c) { return c && !c->dev.empty() && c->dev[0].tuned; }
+
+int o3d_cuda_set_core_func(o3d_ctx* c, int core) {
+  if (!c) return O3D_ERR_INVALID;
+  if (core < O3D_CORE_WL || core > O3D_CORE_V2) return fail(c, O3D_ERR_INVALID, "set_core_func: unknown core function");
+  for (Device& d : c->dev) d.core = core;
+  return O3D_OK;
+}
+
+int o3d_cuda_core_func(const o3d_ctx* c) { return c && !c->dev.empty() ? c->dev[0].core : -1; }
 
 int o3d_cuda_set_profiling(o3d_ctx* c, int on) {
   if (!c) return O3D_ERR_INVALID;

@@ -66,6 +66,15 @@ class ExecEnv:
 
 
 # ---- src/ResultsType.h ---------------------------------------------------------------------------------
+class core_t(enum.IntEnum):
+    """The core functions of src/CoreFunc.h (USE_WL_KERNEL / USE_RM_KERNEL / USE_EXPONENTIAL_KERNEL / USE_V2_KERNEL,
+    :35-38); values are include/o3d_cuda.h's O3D_CORE_*."""
+    wl = 0
+    rm = 1
+    exp = 2
+    v2 = 3
+
+
 class results_t(enum.IntEnum):
     velonly = 1
     velandgrad = 2
@@ -285,6 +294,16 @@ class CudaContext:
 
     def tuned_kernels(self) -> bool:
         return bool(self.lib.o3d_cuda_tuned_kernels(self.h))
+
+    def set_core_func(self, core):
+        """Core function of the particle kernels: a core_t / its number / its name ("wl", "rm", "exp", "v2"). The
+        reference chooses it per build with the one active #define of src/CoreFunc.h:35-38 (USE_WL_KERNEL as shipped)."""
+        if isinstance(core, str):
+            core = core_t[core.lower()]
+        self.check(self.lib.o3d_cuda_set_core_func(self.h, int(core)))
+
+    def core_func(self) -> "core_t":
+        return core_t(self.lib.o3d_cuda_core_func(self.h))
 
     def last_timing(self):
         k, a, b, n = c_double(), c_double(), c_double(), c_int()

@@ -261,6 +261,91 @@ void o3d_oracle_pts_on_pts(int64_t ns, const float* sx, const float* sy, const f
   }
 }
 
+/* ---- the alternate core functions of src/CoreFunc.h (one is chosen per BUILD of the reference by moving the active
+ * "#define USE_*_KERNEL", :35-38). core: 0 Winckelmans-Leonard (:241-289, the shipped choice), 1 Rosenhead-Moore
+ * (:43-83), 2 exponential (:86-238), 3 Vatistas n=2 (:292-341). Scalar helpers: src/MathHelper.h:55-181. ---- */
+static inline float inv_pow_1p5(float x) { return 1.0f / (x * sqrtf(x)); }                               /* oor1p5 */
+static inline float inv_pow_0p75(float x) { const float sqd = sqrtf(x); return 1.0f / (sqd * sqrtf(sqd)); } /* oor0p75 */
+/* exp_cond (:114-128) and exp_bbb (:158-172), generic non-Vc templates */
+static inline float exp_cond(float ood3, float corefac, float reld3) {
+  if (reld3 > 16.0f) return ood3;
+  else if (reld3 < 0.001f) return corefac;
+  else return ood3 * (1.0f - expf(-reld3));
+}
+static inline float exp_bbb(float r3, float corefac, float reld3, float dist, float distsq) {
+  if (reld3 > 16.0f) return -3.0f * r3 / distsq;
+  else if (reld3 < 0.001f) return -1.5f * dist * r3 * r3;
+  else { const float e = expf(-reld3); return 3.0f * (corefac * e - r3) / distsq; }
+}
+/* velocity only; blob != 0: core_func(distsq, sr, tr), else core_func(distsq, sr) */
+static inline float alt_core(int core, int blob, float distsq, float sr, float tr) {
+  if (core == 1) {
+    const float r2 = blob ? distsq + sr * sr + tr * tr : distsq + sr * sr;
+    return inv_pow_1p5(r2);
+  } else if (core == 2) {
+    const float dist = sqrtf(distsq);
+    const float ood3 = 1.0f / (distsq * dist);
+    const float corefac = blob ? 1.0f / (sr * sr * sr + tr * tr * tr) : 1.0f / (sr * sr * sr);
+    const float reld3 = corefac / ood3;
+    return exp_cond(ood3, corefac, reld3);
+  } else if (core == 3) {
+    const float s2 = sr * sr, t2 = tr * tr;
+    const float denom = blob ? distsq * distsq + s2 * s2 + t2 * t2 : distsq * distsq + s2 * s2;
+    return inv_pow_0p75(denom);
+  }
+  return blob ? wl_core_blob(distsq, sr, tr) : wl_core_point(distsq, sr);
+}
+/* with the gradient factor */
+static inline void alt_core_grad(int core, int blob, float distsq, float sr, float tr, float* r3, float* bbb) {
+  if (core == 1) {
+    const float r2 = blob ? distsq + sr * sr + tr * tr : distsq + sr * sr;
+    *r3 = inv_pow_1p5(r2);
+    *bbb = -3.0f * (*r3) * (1.0f / r2);
+  } else if (core == 2) {
+    const float dist = sqrtf(distsq);
+    const float corefac = blob ? 1.0f / (sr * sr * sr + tr * tr * tr) : 1.0f / (sr * sr * sr);
+    const float d3 = distsq * dist;
+    const float reld3 = d3 * corefac;
+    const float ood3 = 1.0f / d3;
+    *r3 = exp_cond(ood3, corefac, reld3);
+    *bbb = exp_bbb(*r3, corefac, reld3, dist, distsq);
+  } else if (core == 3) {
+    const float s2 = sr * sr, t2 = tr * tr;
+    const float denom = blob ? distsq * distsq + s2 * s2 + t2 * t2 : distsq * distsq + s2 * s2;
+    *r3 = inv_pow_0p75(denom);
+    *bbb = -3.0f * (*r3) * (1.0f / sqrtf(denom));
+  } else if (blob) wl_core_blob_grad(distsq, sr, tr, r3, bbb);
+  else wl_core_point_grad(distsq, sr, r3, bbb);
+}
+
+/* particles -> points as o3d_oracle_pts_on_pts, for a build of the reference with core function `core` */
+void o3d_oracle_pts_on_pts_core(int core, int64_t ns, const float* sx, const float* sy, const float* sz, const float* sr,
+                                const float* ssx, const float* ssy, const float* ssz,
+                                int64_t nt, const float* tx, const float* ty, const float* tz, const float* tr,
+                                float* tu, float* tug) {
+  const int nacc = tug ? 12 : 3;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < nt; ++i) {
+    double acc[12] = {0};
+    const float trad = tr ? tr[i] : 0.0f;
+    for (int64_t j = 0; j < ns; ++j) {
+      const src_t s = {sx[j], sy[j], sz[j], sr[j], ssx[j], ssy[j], ssz[j], 0.0f};
+      const float dx = tx[i] - s.x, dy = ty[i] - s.y, dz = tz[i] - s.z;
+      const float distsq = dx * dx + dy * dy + dz * dz;
+      if (tug) {
+        float r3, bbb;
+        alt_core_grad(core, tr != NULL, distsq, s.r, trad, &r3, &bbb);
+        grad_body(&s, dx, dy, dz, r3, bbb, 0, acc);
+      } else {
+        const float k = alt_core(core, tr != NULL, distsq, s.r, trad);
+        const float cx = dz * s.wy - dy * s.wz, cy = dx * s.wz - dz * s.wx, cz = dy * s.wx - dx * s.wy;
+        acc[0] += (double)(k * cx); acc[1] += (double)(k * cy); acc[2] += (double)(k * cz);
+      }
+    }
+    flush_acc(nacc, acc, nt, i, tu, tug, 1.0);
+  }
+}
+
 /* src/Influence.h:728-775 (grads) and :826-864 (vel only); blob-target branches :989-1094 are the
  * same arithmetic (target radius is never used by panel kernels). Sheet strength = ts/area. */
 void o3d_oracle_pan_on_pts(int64_t np, const float* nx, const float* ny, const float* nz, const uint32_t* idx,
@@ -413,10 +498,15 @@ void o3d_oracle_move(int order, int64_t n, double dt, const double* wt, const fl
 }
 
 /* Convection::find_vels for a lone vortex-particle collection, src/Convection.h:130-184 */
+/* core function of the convection sequence below (a build-time choice in the reference, src/CoreFunc.h:35-38) */
+static int g_advect_core = 0;
+void o3d_oracle_set_advect_core(int core) { g_advect_core = core; }
+
 static void find_vels_one(int64_t n, const float* x, const float* s, const float* r, float* u, float* ug, const double* fs) {
   memset(u, 0, sizeof(float) * 3 * n);
   memset(ug, 0, sizeof(float) * 9 * n);
-  o3d_oracle_pts_on_pts(n, x, x + n, x + 2 * n, r, s, s + n, s + 2 * n, n, x, x + n, x + 2 * n, r, u, ug);
+  if (g_advect_core) o3d_oracle_pts_on_pts_core(g_advect_core, n, x, x + n, x + 2 * n, r, s, s + n, s + 2 * n, n, x, x + n, x + 2 * n, r, u, ug);
+  else o3d_oracle_pts_on_pts(n, x, x + n, x + 2 * n, r, s, s + n, s + 2 * n, n, x, x + n, x + 2 * n, r, u, ug);
   o3d_oracle_finalize_vels(n, u, ug, fs);
 }
 

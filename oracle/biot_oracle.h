@@ -36,6 +36,13 @@ void o3d_oracle_pts_on_pts(int64_t ns, const float* sx, const float* sy, const f
                            int64_t nt, const float* tx, const float* ty, const float* tz, const float* tr,
                            float* tu, float* tug);
 
+/* the same for a build of the reference with another core function (src/CoreFunc.h:35-38):
+ * core 0 Winckelmans-Leonard (shipped), 1 Rosenhead-Moore, 2 exponential, 3 Vatistas n=2. */
+void o3d_oracle_pts_on_pts_core(int core, int64_t ns, const float* sx, const float* sy, const float* sz, const float* sr,
+                                const float* ssx, const float* ssy, const float* ssz,
+                                int64_t nt, const float* tx, const float* ty, const float* tz, const float* tr,
+                                float* tu, float* tug);
+
 /* panels -> points (src/Influence.h:557-1099). nodes SoA (nx,ny,nz), idx 3 per panel, ts = total
  * vortex strength SoA 3 x np, area, sss = source-sheet strength or NULL. */
 void o3d_oracle_pan_on_pts(int64_t np, const float* nx, const float* ny, const float* nz, const uint32_t* idx,
@@ -66,6 +73,8 @@ void o3d_oracle_move(int order, int64_t n, double dt, const double* wt, const fl
 /* nsteps x Convection::advect (src/Convection.h:232-262, :349-425, :431-556) with no boundaries / field points. */
 void o3d_oracle_advect(int order, int nsteps, double dt, const double* fs, int64_t n, float* x, float* s, const float* r,
                        float* elong, float* u, float* ug);
+/* core function used by o3d_oracle_advect's evaluations (0 = Winckelmans-Leonard, the default; see o3d_oracle_pts_on_pts_core) */
+void o3d_oracle_set_advect_core(int core);
 void o3d_oracle_stats(int64_t n, const float* s, const float* elong, float* max_str, float* max_elong);
 
 /* ---- particle x panel closest-point loops: reflect_panp2 (mode 0, src/Reflect.h:194-311) and clear_inner_panp2 with

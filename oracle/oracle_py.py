@@ -51,6 +51,7 @@ class Restatement:
         self.lib = ctypes.CDLL(path)
         L = self.lib
         L.o3d_oracle_pts_on_pts.argtypes = [c_int64] + [c_void_p] * 7 + [c_int64] + [c_void_p] * 6
+        L.o3d_oracle_pts_on_pts_core.argtypes = [c_int, c_int64] + [c_void_p] * 7 + [c_int64] + [c_void_p] * 6
         L.o3d_oracle_pan_on_pts.argtypes = [c_int64] + [c_void_p] * 7 + [c_int64] + [c_void_p] * 5
         L.o3d_oracle_pts_on_pan.argtypes = [c_int64] + [c_void_p] * 6 + [c_int64] + [c_void_p] * 6
         L.o3d_oracle_pan_on_pan_coeff.argtypes = (
@@ -61,6 +62,7 @@ class Restatement:
         L.o3d_oracle_finalize_vels.argtypes = [c_int64, c_void_p, c_void_p, c_void_p]
         L.o3d_oracle_move.argtypes = [c_int, c_int64, c_double, c_void_p, c_void_p, c_void_p] + [c_void_p] * 4
         L.o3d_oracle_advect.argtypes = [c_int, c_int, c_double, c_void_p, c_int64] + [c_void_p] * 6
+        L.o3d_oracle_set_advect_core.argtypes = [c_int]
         L.o3d_oracle_stats.argtypes = [c_int64] + [c_void_p] * 4
         L.o3d_oracle_closest_pass.argtypes = [c_int, c_int64] + [c_void_p] * 5 + [c_int64, c_void_p, c_float, c_float]
         L.o3d_oracle_closest_pass.restype = c_int64
@@ -81,12 +83,16 @@ class Restatement:
         pg = (c_void_p * 3)(*[g.ctypes.data if g is not None else None for g in (list(ugs) + [None] * 3)[:3]])
         self.lib.o3d_oracle_move(order, n, float(dt), _p(wt), pu, pg, _p(x), _p(s), _p(elong), _p(uout))
 
-    def advect(self, order, nsteps, dt, fs, x, s, r, elong):
+    def advect(self, order, nsteps, dt, fs, x, s, r, elong, core=0):
         """nsteps x Convection::advect on one particle collection; returns (u, ug) as left in the collection."""
         n = x.shape[1]
         fs = np.asarray(fs, np.float64)
         u, ug = np.zeros((3, n), np.float32), np.zeros((9, n), np.float32)
-        self.lib.o3d_oracle_advect(order, nsteps, float(dt), _p(fs), n, _p(x), _p(s), _p(r), _p(elong), _p(u), _p(ug))
+        self.lib.o3d_oracle_set_advect_core(int(core))
+        try:
+            self.lib.o3d_oracle_advect(order, nsteps, float(dt), _p(fs), n, _p(x), _p(s), _p(r), _p(elong), _p(u), _p(ug))
+        finally:
+            self.lib.o3d_oracle_set_advect_core(0)
         return u, ug
 
     def stats(self, s, elong):
@@ -107,9 +113,15 @@ class Restatement:
     def max_threads(self):
         return int(self.lib.o3d_oracle_max_threads())
 
-    def pts_on_pts(self, sx, sr, ss, tx, tr, tu, tug):
-        """sx (3,ns), sr (ns,), ss (3,ns); tx (3,nt), tr (nt,)|None; tu (3,nt) and tug (9,nt)|None in/out."""
+    def pts_on_pts(self, sx, sr, ss, tx, tr, tu, tug, core=0):
+        """sx (3,ns), sr (ns,), ss (3,ns); tx (3,nt), tr (nt,)|None; tu (3,nt) and tug (9,nt)|None in/out.
+        core: 0 Winckelmans-Leonard (the shipped build), 1 Rosenhead-Moore, 2 exponential, 3 Vatistas n=2."""
         ns, nt = sx.shape[1], tx.shape[1]
+        if core:
+            self.lib.o3d_oracle_pts_on_pts_core(
+                int(core), ns, _p(sx[0]), _p(sx[1]), _p(sx[2]), _p(sr), _p(ss[0]), _p(ss[1]), _p(ss[2]),
+                nt, _p(tx[0]), _p(tx[1]), _p(tx[2]), _p(tr), _p(tu), _p(tug))
+            return
         self.lib.o3d_oracle_pts_on_pts(ns, _p(sx[0]), _p(sx[1]), _p(sx[2]), _p(sr), _p(ss[0]), _p(ss[1]), _p(ss[2]),
                                        nt, _p(tx[0]), _p(tx[1]), _p(tx[2]), _p(tr), _p(tu), _p(tug))
 
@@ -151,10 +163,16 @@ class Reference:
 
     TARG_FIELD, TARG_TRACER, TARG_BLOB = 0, 1, 2
 
-    def __init__(self, fast: bool = False, dropin: bool = False):
+    CORE_BUILDS = {0: "libo3d_ref.so", 1: "libo3d_ref_rm.so", 2: "libo3d_ref_exp.so", 3: "libo3d_ref_v2.so"}
+
+    def __init__(self, fast: bool = False, dropin: bool = False, core: int = 0):
         """dropin=True: the patched, -DUSE_CUDA build of the same driver (oracle/_ref/libo3d_dropin.so); call
-        set_accel(4) on it to route the reference's own routines into the CUDA arm."""
-        path = os.path.join(OUT, "libo3d_dropin.so" if dropin else "libo3d_ref_fast.so" if fast else "libo3d_ref.so")
+        set_accel(4) on it to route the reference's own routines into the CUDA arm.
+        core != 0: the build whose src/CoreFunc.h has another core function #defined (oracle/Makefile core_build)."""
+        name = "libo3d_ref_fast.so" if fast else self.CORE_BUILDS[core]
+        if dropin:   # dropin="exp": the drop-in build of a reference with the exponential core #defined
+            name = "libo3d_dropin_exp.so" if dropin == "exp" else "libo3d_dropin.so"
+        path = os.path.join(OUT, name)
         if not os.path.exists(path):
             build(want_ref=True)
         if not os.path.exists(path):

@@ -128,6 +128,54 @@ def vtk(ref):
     np.savez_compressed(os.path.join(OUT, "vtk.npz"), **g)
 
 
+def cores():
+    """tests/golden/cores.npz: particles -> points from the three builds of the reference whose src/CoreFunc.h has
+    another core function #defined (oracle/Makefile: libo3d_ref_{rm,exp,v2}.so) - the four kernel variants each,
+    per-particle radii, coincident pairs, += on non-zero outputs - plus a uniform-radius self-influence cloud."""
+    rng = np.random.Generator(np.random.MT19937(9090))
+    ns, nt = 601, 257
+    sx, ss, sr = cloud(ns, 1001, 0.02, 0.08)
+    ss = (ss * f32(ns)).astype(f32)
+    tx, _, tr = cloud(nt, 2002, 0.01, 0.06)
+    tx[:, :40] = sx[:, :40]  # coincident pairs
+    # a ladder of close pairs (separation / radius from 0.02 to 3): walks the exponential core through all three
+    # of its branches (reld3 < 0.001, in between, > 16: src/CoreFunc.h:114-128)
+    for k in range(40, 100):
+        tx[:, k] = sx[:, k] + f32(0.02 + 0.05 * (k - 40)) * sr[k] * np.array([0.6, -0.48, 0.64], f32)
+    u0 = (rng.random((3, nt), dtype=f32) - f32(0.5)).astype(f32)
+    g0 = (rng.random((9, nt), dtype=f32) - f32(0.5)).astype(f32)
+    g = {"sx": sx, "ss": ss, "sr": sr, "tx": tx, "tr": tr, "u0": u0, "g0": g0}
+    x, s, r = W.random_cloud(1000, seed=12345, radius=0.05)
+    g.update(cx=x, cs=s, cr=r)
+    for core, tag in ((1, "rm"), (2, "exp"), (3, "v2")):
+        ref = oracle_py.Reference(core=core)
+        for name, blob, grad in (("0bg", True, True), ("0b", True, False), ("0pg", False, True), ("0p", False, False)):
+            tu, tug = u0.copy(), (g0.copy() if grad else None)
+            ref.pts_on_pts(sx, sr, ss, tx, tr if blob else None, tu, tug)
+            g[f"{tag}_u_{name}"] = tu
+            if grad:
+                g[f"{tag}_g_{name}"] = tug
+        tu, tug = np.zeros((3, 1000), f32), np.zeros((9, 1000), f32)
+        ref.pts_on_pts(x, r, s, x, r, tu, tug)
+        g[f"{tag}_cloud_u"], g[f"{tag}_cloud_g"] = tu, tug
+        # panels -> points (with gradients) on the inputs of panels_80.npz: the panel leaves evaluate the core at zero
+        # radius, where the four cores coincide up to rounding
+        pg = np.load(os.path.join(OUT, "panels_80.npz"))
+        tu, tug = pg["u0"].copy(), pg["g0"].copy()
+        ref.pan_on_pts(pg["nodes_i"], pg["idx"], pg["val"], pg["tx"], None, tu, tug, targ_kind=ref.TARG_FIELD)
+        g[f"{tag}_pan_u"], g[f"{tag}_pan_g"] = tu, tug
+        # two Convection::advect steps of each order through that build's own Points methods (o3d_ref_advect)
+        for order in (1, 2, 3):
+            ax, as_, ar = W.random_cloud(300, seed=11, radius=0.08)
+            as_ = (as_ * f32(30.0)).astype(f32)
+            ae = np.ones(300, f32)
+            if core == 1 and order == 1:
+                g["adv_x0"], g["adv_s0"], g["adv_r"] = ax.copy(), as_.copy(), ar
+            ref.advect(order, 2, 0.02, (0.1, 0.0, 0.0), ax, as_, ar, ae)
+            g[f"{tag}_adv{order}_x"], g[f"{tag}_adv{order}_s"], g[f"{tag}_adv{order}_elong"] = ax, as_, ae
+    np.savez_compressed(os.path.join(OUT, "cores.npz"), **g)
+
+
 def main():
     oracle_py.build(want_ref=True)
     ref = oracle_py.Reference()
@@ -237,4 +285,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["cores"]:
+        cores()
+    else:
+        main()
+        cores()

@@ -129,3 +129,39 @@ def test_reflect_and_clear_inner_through_reference_functions(dropin):
     x = g["x0"].copy()
     n = dropin.clear_inner(1, g["nodes_i"], g["idx"], x, np.full(x.shape[1], 0.03, f32), float(g["clear_cm"]), float(g["clear_ips"]))
     assert n == int(g["clear_moved"]) and np.array_equal(x, g["clear_x"])
+
+
+def test_cuda_arm_follows_the_reference_core_define():
+    """oracle/_ref/libo3d_dropin_exp.so: the patched reference with "#define USE_EXPONENTIAL_KERNEL" active in its
+    src/CoreFunc.h. Its gpu_cuda arm must give what ITS cpu_x86 arm gives - and not what the shipped (WL) core gives.
+    Run in a process of its own: both drop-in builds define the same inline context holder."""
+    import subprocess
+    import sys
+    from oracle import oracle_py
+    if not os.path.exists(os.path.join(oracle_py.OUT, "libo3d_dropin_exp.so")):
+        pytest.skip("oracle/_ref/libo3d_dropin_exp.so not built (needs /root/reference at build time)")
+    code = """
+import numpy as np, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from conftest import rel_err
+from oracle import oracle_py
+from omega3d_b200 import workloads as W
+lib = oracle_py.Reference(dropin="exp")
+assert lib.built_with_cuda()
+x, s, r = W.random_cloud(3000, seed=61)
+out = []
+for accel in (1, 4):
+    lib.set_accel(accel)
+    tu, tug = np.full((3, 3000), 0.25, np.float32), np.full((9, 3000), -0.5, np.float32)
+    lib.pts_on_pts(x, r, s, x, r, tu, tug)
+    out.append((tu - 0.25, tug + 0.5))
+wl = oracle_py.Restatement()
+wu, wg = np.zeros((3, 3000), np.float32), np.zeros((9, 3000), np.float32)
+wl.pts_on_pts(x, r, s, x, r, wu, wg)
+print("ERR", rel_err(out[1][0], out[0][0]), rel_err(out[1][1], out[0][1]), rel_err(out[1][1], wg))
+""" % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    eu, eg, e_wl = [float(v) for v in r.stdout.split("ERR")[1].split()]
+    assert eu <= VEL_TOL and eg <= GRAD_TOL
+    assert e_wl > 100 * GRAD_TOL      # the two cores really differ on this cloud

@@ -100,3 +100,51 @@ def test_reference_reproduces_golden(reference_lib):
     assert np.array_equal(tu, p["u_vel"])
     with pytest.raises(RuntimeError):  # inert lagrangian tracers + velandgrad: the reference asserts (src/Influence.h:368)
         reference_lib.pts_on_pts(g["sx"], g["sr"], g["ss"], g["tx"], None, tu, tug, targ_kind=reference_lib.TARG_TRACER)
+
+
+# ---- the alternate core functions of src/CoreFunc.h -----------------------------------------------------------------
+@pytest.mark.parametrize("core,tag", [(1, "rm"), (2, "exp"), (3, "v2")])
+def test_restatement_matches_reference_core_builds_bit_for_bit(restate, core, tag):
+    """tests/golden/cores.npz holds outputs of the reference built with USE_RM_KERNEL / USE_EXPONENTIAL_KERNEL /
+    USE_V2_KERNEL active in src/CoreFunc.h; the restatement's core argument reproduces each bit for bit."""
+    g = golden("cores.npz")
+    for variant, blob, grad in (("0bg", True, True), ("0b", True, False), ("0pg", False, True), ("0p", False, False)):
+        tu = g["u0"].copy()
+        tug = g["g0"].copy() if grad else None
+        restate.pts_on_pts(g["sx"], g["sr"], g["ss"], g["tx"], g["tr"] if blob else None, tu, tug, core=core)
+        assert np.array_equal(tu, g[f"{tag}_u_{variant}"])
+        if grad:
+            assert np.array_equal(tug, g[f"{tag}_g_{variant}"])
+    u, ug = np.zeros((3, 1000), np.float32), np.zeros((9, 1000), np.float32)
+    restate.pts_on_pts(g["cx"], g["cr"], g["cs"], g["cx"], g["cr"], u, ug, core=core)
+    assert np.array_equal(u, g[f"{tag}_cloud_u"]) and np.array_equal(ug, g[f"{tag}_cloud_g"])
+
+
+def test_exponential_core_golden_walks_all_three_branches():
+    """The close-pair ladder of cores.npz puts pairs in each arm of exp_cond (src/CoreFunc.h:114-128)."""
+    g = golden("cores.npz")
+    d = (g["tx"][:, 40:100] - g["sx"][:, 40:100]).astype(np.float64)
+    dist = np.sqrt((d * d).sum(0))
+    reld3 = dist ** 3 / (g["sr"][40:100].astype(np.float64) ** 3 + g["tr"][40:100].astype(np.float64) ** 3)
+    assert (reld3 < 0.001).any() and (reld3 > 16).any() and ((reld3 > 0.001) & (reld3 < 16)).any()
+
+
+def test_core_zero_is_the_shipped_restatement(restate):
+    from oracle.oracle_py import _p
+    g = golden("pts_on_pts.npz")
+    a, ag = g["u0"].copy(), g["g0"].copy()
+    sx, ss, tx = [np.ascontiguousarray(g[k]) for k in ("sx", "ss", "tx")]
+    sr, tr = np.ascontiguousarray(g["sr"]), np.ascontiguousarray(g["tr"])
+    restate.lib.o3d_oracle_pts_on_pts_core(0, sx.shape[1], _p(sx[0]), _p(sx[1]), _p(sx[2]), _p(sr), _p(ss[0]), _p(ss[1]), _p(ss[2]),
+                                           tx.shape[1], _p(tx[0]), _p(tx[1]), _p(tx[2]), _p(tr), _p(a), _p(ag))
+    assert np.array_equal(a, g["u_0bg"]) and np.array_equal(ag, g["g_0bg"])
+
+
+@pytest.mark.parametrize("core,tag", [(1, "rm"), (2, "exp"), (3, "v2")])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_restatement_advect_matches_reference_core_builds(restate, core, tag, order):
+    g = golden("cores.npz")
+    x, s, e = g["adv_x0"].copy(), g["adv_s0"].copy(), np.ones(300, np.float32)
+    restate.advect(order, 2, 0.02, (0.1, 0.0, 0.0), x, s, g["adv_r"], e, core=core)
+    assert np.array_equal(x, g[f"{tag}_adv{order}_x"]) and np.array_equal(s, g[f"{tag}_adv{order}_s"])
+    assert np.array_equal(e, g[f"{tag}_adv{order}_elong"])
