@@ -38,60 +38,92 @@ __host__ __device__ __forceinline__ float core_radius_term(const int core, const
   return core == kCoreEXP ? r2 * r : core == kCoreV2 ? r2 * r2 : r2;
 }
 
-// Exponential core, one lane (src/CoreFunc.h:114-128 exp_cond, :158-172 exp_bbb, :213-238). Branch-free selects: at
-// |d| = 0 the unselected operands are inf / NaN exactly as in the reference's scalar code, where they are never read
-// (reld3 = 0 takes the "< 0.001" arm: r3 = corefac, bbb = -1.5 * 0 * r3 * r3 = 0).
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Exponential core, two lanes (src/CoreFunc.h:114-128 exp_cond, :158-172 exp_bbb, :213-238):
+//   dist = sqrt(|d|^2), d3 = |d|^2 dist, corefac = 1/(sr^3 + tr^3), reld3 = d3 corefac, ood3 = 1/d3
+//   r3  = reld3 > 16 ? ood3 : reld3 < 0.001 ? corefac : ood3 (1 - exp(-reld3))
+//   bbb = reld3 > 16 ? -3 r3/|d|^2 : reld3 < 0.001 ? -1.5 dist r3 r3 : 3 (corefac exp(-reld3) - r3)/|d|^2
+// All three arms are evaluated with packed arithmetic in the reference's operation order and the reference's comparisons
+// pick one per lane (FSEL). At |d| = 0 the unselected arms hold inf / NaN exactly as the reference's scalar code would
+// have produced had it evaluated them; selects do not propagate them (reld3 = 0 takes the "< 0.001" arm: r3 = corefac,
+// bbb = -1.5 * 0 * r3 * r3 = -0). Four MUFU per lane: SQRT, two RCP, EX2 (exp(-x) = 2^(-x log2 e)).
 template <bool GRAD>
-__device__ __forceinline__ void exp_core_lane(const float dsq, const float st, float& r3, float& bbb) {
-  const float dist = sqrt_approx(dsq);
-  const float d3 = dsq * dist;
-  const float cf = rcp_approx(st);
-  const float reld3 = d3 * cf;
-  const float ood3 = rcp_approx(d3);
-  const float e = expf(-reld3);
-  const bool far = reld3 > 16.0f, near = reld3 < 0.001f;
-  r3 = far ? ood3 : near ? cf : ood3 * (1.0f - e);
+__device__ __forceinline__ void exp_core2(const float2 dsq, const float2 st, float2& r3, float2& bbb) {
+  const float2 dist = f2(sqrt_approx(dsq.x), sqrt_approx(dsq.y));
+  const float2 d3 = __fmul2_rn(dsq, dist);
+  const float2 cf = f2(rcp_approx(st.x), rcp_approx(st.y));
+  const float2 reld3 = __fmul2_rn(d3, cf);
+  const float2 ood3 = f2(rcp_approx(d3.x), rcp_approx(d3.y));
+  const float2 xe = __fmul2_rn(reld3, f2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 e = f2(ex2_approx(xe.x), ex2_approx(xe.y));
+  const float2 mid = __fmul2_rn(ood3, __fadd2_rn(f2(1.0f, 1.0f), neg2(e)));
+  const bool far0 = reld3.x > 16.0f, near0 = reld3.x < 0.001f;
+  const bool far1 = reld3.y > 16.0f, near1 = reld3.y < 0.001f;
+  r3.x = far0 ? ood3.x : near0 ? cf.x : mid.x;
+  r3.y = far1 ? ood3.y : near1 ? cf.y : mid.y;
   if constexpr (GRAD) {
-    const float oodsq = ood3 * dist;                      // 1 / |d|^2
-    const float b_far = -3.0f * r3 * oodsq;
-    const float b_near = -1.5f * dist * r3 * r3;
-    const float b_mid = 3.0f * (cf * e - r3) * oodsq;
-    bbb = far ? b_far : near ? b_near : b_mid;
+    const float2 oodsq = __fmul2_rn(ood3, dist);                                          // 1 / |d|^2
+    const float2 bfar = __fmul2_rn(__fmul2_rn(f2(-3.0f, -3.0f), r3), oodsq);
+    const float2 bnear = __fmul2_rn(__fmul2_rn(f2(-1.5f, -1.5f), dist), __fmul2_rn(r3, r3));
+    const float2 bmid = __fmul2_rn(__fmul2_rn(f2(3.0f, 3.0f), __ffma2_rn(cf, e, neg2(r3))), oodsq);
+    bbb.x = far0 ? bfar.x : near0 ? bnear.x : bmid.x;
+    bbb.y = far1 ? bfar.y : near1 ? bnear.y : bmid.y;
   }
 }
 
-// Two sources (one packed record pair) on one target. st = source lane + target term (see the table above).
+// Two sources (one packed record pair) on one target; tt = the target's term of the table above. The Rosenhead-Moore and
+// Vatistas bodies live in their own files: like pp_interact2's, their statement ORDER decides how many packed instructions
+// pay a third register-file cycle, and tools/tune_order.py (O3D_TUNE_VARIANT=rm|rmvel|v2|v2vel) searches it.
+//   Rosenhead-Moore:  st = tt + lane; d2 = |d|^2 + st; rs = rsqrt(d2); r3 = rs^3; bbb = (-3 rs^2) r3
+//   Vatistas n=2:     st = tt + lane; den = |d|^4 + st; rq = rsqrt(den); r3 = rq sqrt(rq); bbb = (-3 rq) r3
+// followed by c = (dz wy - dy wz, dx wz - dz wx, dy wx - dx wy), A += r3 w, u += r3 c, G += d (x) (bbb c) without the
+// wz slot (trace-free: recovered as -(ux + vy) per tile, d . (d x w) = 0 whatever the core).
+#ifndef O3D_PPC_BODY_RM_GRAD
+#define O3D_PPC_BODY_RM_GRAD "ppc_body_rm_velgrad.inc"
+#endif
+#ifndef O3D_PPC_BODY_RM_VEL
+#define O3D_PPC_BODY_RM_VEL "ppc_body_rm_vel.inc"
+#endif
+#ifndef O3D_PPC_BODY_V2_GRAD
+#define O3D_PPC_BODY_V2_GRAD "ppc_body_v2_velgrad.inc"
+#endif
+#ifndef O3D_PPC_BODY_V2_VEL
+#define O3D_PPC_BODY_V2_VEL "ppc_body_v2_vel.inc"
+#endif
 template <int CORE, bool GRAD>
 __device__ __forceinline__ void ppc_interact2(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
                                               const float2 tx, const float2 ty, const float2 tz, const float2 tt,
                                               float2 (&acc)[PPAcc<GRAD>::N]) {
+  if constexpr (CORE == kCoreRM && GRAD) {
+#include O3D_PPC_BODY_RM_GRAD
+    return;
+  }
+  if constexpr (CORE == kCoreRM && !GRAD) {
+#include O3D_PPC_BODY_RM_VEL
+    return;
+  }
+  if constexpr (CORE == kCoreV2 && GRAD) {
+#include O3D_PPC_BODY_V2_GRAD
+    return;
+  }
+  if constexpr (CORE == kCoreV2 && !GRAD) {
+#include O3D_PPC_BODY_V2_VEL
+    return;
+  }
+  // exponential core: all three arms packed, one select per lane and factor
   const float2 dx = __fadd2_rn(tx, f2(q0.x, q0.y));
   const float2 dy = __fadd2_rn(ty, f2(q0.z, q0.w));
   const float2 dz = __fadd2_rn(tz, f2(q1.x, q1.y));
   const float2 st = __fadd2_rn(tt, f2(q1.z, q1.w));
   const float2 wx = f2(q2.x, q2.y), wy = f2(q2.z, q2.w), wz = f2(q3.x, q3.y);
   float2 r3, bbb = f2(0.f, 0.f);
-  if constexpr (CORE == kCoreRM) {
-    // r3 = r2^-1.5, bbb = -3 r3 / r2 with r2 = |d|^2 + sr^2 + tr^2
-    const float2 r2 = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __ffma2_rn(dz, dz, st)));
-    const float2 rs = f2(rsqrt_approx(r2.x), rsqrt_approx(r2.y));
-    const float2 rs2 = __fmul2_rn(rs, rs);
-    r3 = __fmul2_rn(rs2, rs);
-    if constexpr (GRAD) bbb = __fmul2_rn(__fmul2_rn(f2(-3.0f, -3.0f), rs2), r3);
-  } else if constexpr (CORE == kCoreV2) {
-    // r3 = denom^-0.75, bbb = -3 r3 / sqrt(denom) with denom = |d|^4 + sr^4 + tr^4
-    const float2 dsq = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
-    const float2 denom = __ffma2_rn(dsq, dsq, st);
-    const float2 rq = f2(rsqrt_approx(denom.x), rsqrt_approx(denom.y));     // denom^-1/2
-    const float2 sq = f2(sqrt_approx(rq.x), sqrt_approx(rq.y));             // denom^-1/4
-    r3 = __fmul2_rn(rq, sq);
-    if constexpr (GRAD) bbb = __fmul2_rn(__fmul2_rn(f2(-3.0f, -3.0f), rq), r3);
-  } else {
-    const float2 dsq = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
-    exp_core_lane<GRAD>(dsq.x, st.x, r3.x, bbb.x);
-    exp_core_lane<GRAD>(dsq.y, st.y, r3.y, bbb.y);
-  }
-  // c = (dz wy - dy wz, dx wz - dz wx, dy wx - dx wy)
+  const float2 dsq = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
+  exp_core2<GRAD>(dsq, st, r3, bbb);
   const float2 t1 = __fmul2_rn(dy, wz);
   const float2 t2 = __fmul2_rn(dx, wz);
   const float2 t3 = __fmul2_rn(dx, wy);
@@ -118,7 +150,6 @@ __device__ __forceinline__ void ppc_interact2(const float4 q0, const float4 q1, 
     acc[6]  = __ffma2_rn(dy, cx, acc[6]);
     acc[9]  = __ffma2_rn(dz, cx, acc[9]);
     acc[10] = __ffma2_rn(dz, cy, acc[10]);
-    // acc[11] (wz slot): trace-free, recovered as -(ux + vy) per tile - d . (d x w) = 0 whatever the core
   }
 }
 
@@ -173,7 +204,7 @@ __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) ppc_kernel(const PPArgs p)
     const int buf = k & 1;
     mbar_wait(&full[buf], (k >> 1) & 1);
     const float4* __restrict__ s = tile[buf];
-#pragma unroll(CORE == kCoreEXP ? 1 : 2)
+#pragma unroll(CORE == kCoreEXP ? 2 : GRAD ? kPPUnrollGrad : kPPUnrollVel)
     for (int j = 0; j < kTile / 2; ++j) {
       const float4 q0 = s[4 * j], q1 = s[4 * j + 1], q2 = s[4 * j + 2], q3 = s[4 * j + 3];
 #pragma unroll

@@ -177,6 +177,7 @@ static_assert(kPPTgrad == 2 && kPPTvel == 4 && kPPBlock == 128, "kernel names be
 struct TunedKernels {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t grad = nullptr, vel = nullptr;
+  cudaKernel_t core[4][2] = {};   // ppc_kernel<core, .., grad?>: [O3D_CORE_RM .. O3D_CORE_V2][0 = velocity only, 1 = with gradients]
   cudaError_t status = cudaSuccess;
   const char* where = "";
 };
@@ -193,6 +194,13 @@ const TunedKernels& tuned_kernels() {
       k.status = cudaLibraryGetKernel(&k.vel, k.lib, "_ZN3o3d10pp2_kernelILi4ELb0ELi128EEEvNS_6PPArgsE");
       k.where = "cudaLibraryGetKernel(pp2_kernel<4,false,128>)";
     }
+    for (int core = O3D_CORE_RM; core <= O3D_CORE_V2 && k.status == cudaSuccess; ++core)
+      for (int g = 0; g < 2 && k.status == cudaSuccess; ++g) {
+        char name[96];
+        snprintf(name, sizeof name, "_ZN3o3d10ppc_kernelILi%dELi%dELb%dELi128EEEvNS_6PPArgsE", core, g ? kPPTgrad : kPPTvel, g);
+        k.status = cudaLibraryGetKernel(&k.core[core][g], k.lib, name);
+        k.where = "cudaLibraryGetKernel(ppc_kernel<core,T,grad,128>)";
+      }
     if (k.status != cudaSuccess) cudaGetLastError();
     return k;
   }();
@@ -286,6 +294,10 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   if (d.core != O3D_CORE_WL) {
     // the alternate core functions of src/CoreFunc.h (csrc/biot_pp_cores.cuh); the stream was packed for d.core
     a.radius_range = nullptr;
+    if (d.tuned) {   // the post-processed copy (same instructions and results; tools/sass_patch.py)
+      void* params[] = {&a};
+      O3D_TRY(d, cudaLaunchKernel((const void*)tuned_kernels().core[d.core][grad ? 1 : 0], s.grid, dim3(kPPBlock), params, 0, st));
+    } else {
 #define O3D_PPC_LAUNCH(CORE)                                                                          \
   if (grad) ppc_kernel<CORE, kPPTgrad, true, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a);               \
   else      ppc_kernel<CORE, kPPTvel, false, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a)
@@ -293,6 +305,7 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
     else if (d.core == O3D_CORE_EXP) { O3D_PPC_LAUNCH(kCoreEXP); }
     else { O3D_PPC_LAUNCH(kCoreV2); }
 #undef O3D_PPC_LAUNCH
+    }
   } else if (d.tuned) {
     const TunedKernels& tk = tuned_kernels();
     void* params[] = {&a};

@@ -216,6 +216,33 @@ def test_panel_kernels_under_other_cores(ctx, core, tag):
     assert flops < wl_flops and (wl_flops - flops) % dl == 0
 
 
+@pytest.mark.parametrize("core,tag", CORES)
+@pytest.mark.parametrize("grad", [True, False])
+def test_cores_tuned_kernels_bit_identical(ctx, core, tag, grad):
+    """The alternate-core kernels also run from the SASS-post-processed cubin (operand-reuse bits and yield hints only):
+    every output bit equals the copy linked into the library."""
+    ns, nt = 4099, 2050
+    sx, ss, _ = W.random_cloud(ns, seed=900 + ns)
+    tx, _, _ = W.random_cloud(nt, seed=950 + nt)
+    sr, tr = W.varied_radii(ns, 901, 0.03, 0.12), W.varied_radii(nt, 902, 0.03, 0.12)
+    out = []
+    ctx.set_core_func(core)
+    try:
+        for on in (True, False):
+            ctx.set_tuned_kernels(on)
+            u = np.full((3, nt), 0.25, f32)
+            g = np.full((9, nt), -0.5, f32) if grad else None
+            ctx.pts_on_pts(sx, sr, ss, tx, tr, u, g)
+            out.append((u, g))
+    finally:
+        ctx.set_tuned_kernels(True)
+        ctx.set_core_func("wl")
+    assert np.array_equal(out[0][0].view(np.uint32), out[1][0].view(np.uint32))
+    if grad:
+        assert np.array_equal(out[0][1].view(np.uint32), out[1][1].view(np.uint32))
+    assert np.all(np.isfinite(out[0][0]))
+
+
 def test_switching_back_restores_the_default_kernel(ctx, restate):
     g = golden("self_cloud_1000.npz")
     ctx.set_core_func("v2")

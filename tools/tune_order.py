@@ -69,9 +69,37 @@ elif VARIANT == "vel":
     STMTS = _GEOM + _D2 + _CORE_UNI + _CROSS + _VEL
 elif VARIANT == "velgen":
     STMTS = _GEOM + [_CORE_GEN[0]] + _D2 + _CORE_GEN[1:] + _CROSS + _VEL
-KERNEL = "pp2_kernel<2, true, 128>" if VARIANT in ("uni", "gen") else "pp2_kernel<4, false, 128>"
-BODY_MACRO = {"uni": "O3D_PP_BODY_FILE", "gen": "O3D_PP_BODY_FILE_GEN", "vel": "O3D_PP_BODY_FILE_VEL", "velgen": "O3D_PP_BODY_FILE_VELGEN"}[VARIANT]
-PER_BODY = len([st for st in STMTS if st[1] != "rsq"])        # packed instructions per (target, source pair): picks the loop
+# the alternate core functions of src/CoreFunc.h (csrc/biot_pp_cores.cuh: ppc_kernel<CORE, T, GRAD, 128>):
+#   rm / rmvel   Rosenhead-Moore, velocity+gradient (34 statements) / velocity only (18)
+#   v2 / v2vel   Vatistas n=2 (34 / 18; two MUFU per lane: rsqrt and sqrt)
+_ST = [("st", "add", "tt", "sl", None)]
+_D2_RM = [("a1", "fma", "dz", "dz", "st"), ("a2", "fma", "dy", "dy", "a1"), ("d2", "fma", "dx", "dx", "a2"), ("rs", "rsq", "d2", None, None)]
+_CORE_RM = [("rs2", "mul", "rs", "rs", None), ("r3", "mul", "rs2", "rs", None)]
+_BBB_RM = [("w", "mul", "m3", "rs2", None), ("bbb", "mul", "w", "r3", None)]
+_D2_V2 = [("b1", "mul", "dz", "dz", None), ("b2", "fma", "dy", "dy", "b1"), ("dsq", "fma", "dx", "dx", "b2"), ("den", "fma", "dsq", "dsq", "st"),
+          ("rq", "rsq", "den", None, None), ("sq", "sqrt", "rq", None, None)]
+_CORE_V2 = [("r3", "mul", "rq", "sq", None)]
+_BBB_V2 = [("w", "mul", "m3", "rq", None), ("bbb", "mul", "w", "r3", None)]
+if VARIANT == "rm":
+    STMTS = _GEOM + _ST + _D2_RM + _CORE_RM + _CROSS + _ANTI + _VEL + _BBB_RM + _GRAD
+elif VARIANT == "rmvel":
+    STMTS = _GEOM + _ST + _D2_RM + _CORE_RM + _CROSS + _VEL
+elif VARIANT == "v2":
+    STMTS = _GEOM + _ST + _D2_V2 + _CORE_V2 + _CROSS + _ANTI + _VEL + _BBB_V2 + _GRAD
+elif VARIANT == "v2vel":
+    STMTS = _GEOM + _ST + _D2_V2 + _CORE_V2 + _CROSS + _VEL
+PPC = VARIANT in ("rm", "rmvel", "v2", "v2vel")
+HEADER = "biot_pp_cores.cuh" if PPC else "biot_pp.cuh"
+SASS_NAME = "ppc_kernel" if PPC else "pp2_kernel"
+MUFU_PER_BODY = 4.0 if VARIANT in ("v2", "v2vel") else 2.0     # MUFU instructions per (target, source pair): two lanes x (rsqrt [+ sqrt])
+if PPC:
+    KERNEL = {"rm": "ppc_kernel<1, 2, true, 128>", "rmvel": "ppc_kernel<1, 4, false, 128>",
+              "v2": "ppc_kernel<3, 2, true, 128>", "v2vel": "ppc_kernel<3, 4, false, 128>"}[VARIANT]
+    BODY_MACRO = {"rm": "O3D_PPC_BODY_RM_GRAD", "rmvel": "O3D_PPC_BODY_RM_VEL", "v2": "O3D_PPC_BODY_V2_GRAD", "v2vel": "O3D_PPC_BODY_V2_VEL"}[VARIANT]
+else:
+    KERNEL = "pp2_kernel<2, true, 128>" if VARIANT in ("uni", "gen") else "pp2_kernel<4, false, 128>"
+    BODY_MACRO = {"uni": "O3D_PP_BODY_FILE", "gen": "O3D_PP_BODY_FILE_GEN", "vel": "O3D_PP_BODY_FILE_VEL", "velgen": "O3D_PP_BODY_FILE_VELGEN"}[VARIANT]
+PER_BODY = len([st for st in STMTS if st[1] not in ("rsq", "sqrt")])        # packed instructions per (target, source pair): picks the loop
 
 # O3D_TUNE_JOINT=1: search ONE order over the statements of both register-blocked targets (T = 2) - the source operands
 # (wx wy wz sx sy sz and the constants) are shared between the two, so operand-reuse chains can span the targets.
@@ -108,6 +136,8 @@ PRELUDE = """    const float2 sx = f2(q0.x, q0.y), sy = f2(q0.z, q0.w), sz = f2(
 if VARIANT in ("gen", "velgen"):
     PRELUDE = PRELUDE.replace("const float2 r2 = tr2, m3 = f2(-3.0f, -3.0f);",
                               "const float2 sr2 = f2(q1.z, q1.w), c15 = f2(1.5f, 1.5f), m5 = f2(-5.0f, -5.0f), p2 = f2(2.0f, 2.0f);")
+if PPC:
+    PRELUDE = PRELUDE.replace("const float2 r2 = tr2, m3 = f2(-3.0f, -3.0f);", "const float2 sl = f2(q1.z, q1.w), m3 = f2(-3.0f, -3.0f);")
 if JOINT:
     PRELUDE = PRELUDE.replace("r2 = tr2,", "r2 = tr2[0],")
 
@@ -129,6 +159,8 @@ def emit(order, swaps):
             out.append(f"    {decl}{res} = __ffma2_rn({v(a)}, {v(b)}, {v(c)});\n")
         elif op == "rsq":
             out.append(f"    {decl}{res} = f2(rsqrt_approx({a}.x), rsqrt_approx({a}.y));\n")
+        elif op == "sqrt":
+            out.append(f"    {decl}{res} = f2(sqrt_approx({a}.x), sqrt_approx({a}.y));\n")
     return "".join(out)
 
 
@@ -171,7 +203,7 @@ def score(args):
         f.write(emit(order, swaps))
     cu = os.path.join(WORK, f"one_{k}.cu")
     with open(cu, "w") as f:
-        f.write('#include "biot_pp.cuh"\nusing namespace o3d;\ntemplate __global__ void o3d::' + KERNEL + '(const PPArgs);\n')
+        f.write('#include "' + HEADER + '"\nusing namespace o3d;\ntemplate __global__ void o3d::' + KERNEL + '(const PPArgs);\n')
     cubin = os.path.join(WORK, f"one_{k}.cubin")
     cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-I" + os.path.join(ROOT, "omega3d_b200", "csrc"),
            "-DO3D_PP_POW=2", f'-D{BODY_MACRO}="{body}"', "-Xptxas", "-v", "-cubin", cu, "-o", cubin] + extra + EXTRA
@@ -183,24 +215,24 @@ def score(args):
         return None
     if PATCHED:                                   # score what tools/sass_patch.py makes of it
         pc = os.path.join(WORK, f"one_{k}_p.cubin")
-        if subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_patch.py"), cubin, pc, "pp2_kernel"],
+        if subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_patch.py"), cubin, pc, SASS_NAME],
                           capture_output=True, text=True).returncode != 0:
             return None
         cubin = pc
     regs = int(re.search(r"Used (\d+) registers", r.stderr).group(1))
     spill = "0 bytes spill stores" not in r.stderr
-    ins = M.kernel_sass(cubin, "pp2_kernel")
+    ins = M.kernel_sass(cubin, SASS_NAME)
     best = None
     for j, i in M.hot_loops(ins):                # the kernel holds a uniform-radius and a per-particle-radius loop
         bodyins = [t for _, t in ins[j:i + 1]]
         n, three, tot, other = M.model(bodyins)
         nm = sum(1 for t in bodyins if t.startswith("MUFU"))
-        if nm and abs(n / (nm / 2.0) - PER_BODY) < 0.5:
+        if nm and abs(n / (nm / MUFU_PER_BODY) - PER_BODY) < 0.5:
             best = (n, three, tot, other, nm)
     if best is None:
         return None
     n, three, tot, other, nm = best
-    per_pair = (tot + other) / (nm / 2.0)        # modelled cycles per (target, source pair)
+    per_pair = (tot + other) / (nm / MUFU_PER_BODY)        # modelled cycles per (target, source pair)
     return per_pair, n, three, tot + other, regs, spill
 
 
@@ -283,7 +315,7 @@ def parse_body(path):
     order, swaps = [], set()
     for line in open(path):
         m = re.match(r"\s+(?:const float2 )?([\w\[\]]+) = (__f\w+2_rn|f2)\((.*)\);", line)
-        if not m or line.lstrip().startswith(("const float2 sx =", "const float2 wx =", "const float2 r2 = tr2", "const float2 sr2 = f2(q1")):
+        if not m or line.lstrip().startswith(("const float2 sx =", "const float2 wx =", "const float2 r2 = tr2", "const float2 sr2 = f2(q1", "const float2 sl = f2(q1")):
             continue
         res = m.group(1)
         idx = next(k for k, st in enumerate(STMTS) if st[0] == res)
@@ -332,6 +364,10 @@ def anneal(minutes, seed, jobs, start_file=None):
 
 
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "emit":      # write the formula-order body of the variant to a file
+        with open(sys.argv[2], "w") as f:
+            f.write(emit(list(range(len(STMTS))), frozenset()))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "anneal":
         return anneal(float(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 8,
                       sys.argv[5] if len(sys.argv) > 5 else None)
