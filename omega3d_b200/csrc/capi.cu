@@ -237,9 +237,11 @@ PPShape pp_shape(const Device& d, int64_t ntiles, int64_t nt, bool grad) {
   const int64_t gx = (nt + per_cta - 1) / per_cta;
   const int64_t slots = (int64_t)d.sm_count * (grad ? kPPResidentGrad : kPPResidentVel);
   // Pick the source split that wastes the least of the last wave: efficiency = CTAs / (waves * slots).
-  // Large target counts (>= 16 waves) never split; tiny ones split until the GPU is covered twice.
+  // Large target counts (>= 64 waves: at most 0.8 % to gain) never split; tiny ones split until the GPU is covered twice.
+  // (The bound was 16 waves until the 2 M point of the size sweep showed 18.45 waves = 97.1 %: 2 M targets per GPU is also
+  // the 16 M / 8 GPU configuration. A split costs nsplit x 96 B per target of FP64 slab traffic: microseconds.)
   int64_t best = 1;
-  if (gx < 16 * slots) {
+  if (gx < 64 * slots) {
     double best_eff = 0.0;
     const int64_t max_split = std::min<int64_t>(ntiles, 64);
     for (int64_t sp = 1; sp <= max_split; ++sp) {
