@@ -7,4 +7,4 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O
 echo "== pytest cores + dropin"
 timeout 300 python -m pytest tests/test_gpu_cores.py tests/test_gpu_dropin.py -q -m gpu -x 2>&1 | tail -15 | tee $OUT/pytest_cores.txt
 echo "== bench cores 256K"
-timeout 120 python scripts/bench_cores.py 262144 2>&1 | tail -10 | tee $OUT/bench_cores_256k.jsonl
+timeout 120 python tests/perf/bench_cores.py 262144 2>&1 | tail -10 | tee $OUT/bench_cores_256k.jsonl

@@ -15,6 +15,6 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --cs
     python bench.py --steps 2 --warmup 1 --e2e-steps 1 --no-cpu > $OUT/bench_under_ncu.log 2>&1
 echo "== ncu full capture of ppc_kernel (Rosenhead-Moore, vel+grad, N = 256K)"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:ppc_kernel -c 1 -f -o $OUT/ppc_rm_full_256k \
-    python scripts/bench_cores.py 262144 > $OUT/ncu_ppc.log 2>&1
+    python tests/perf/bench_cores.py 262144 > $OUT/ncu_ppc.log 2>&1
 ncu -i $OUT/ppc_rm_full_256k.ncu-rep --page raw --csv > $OUT/ppc_rm_full_256k_raw.csv 2>/dev/null
 ls -la $OUT | tail -14

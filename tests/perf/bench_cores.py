@@ -2,14 +2,14 @@
 """Secondary measurement (not the headline bench): particles -> points under each core function of the reference's
 src/CoreFunc.h (o3d_cuda_set_core_func) through the host C ABI; one JSON line per (core, result type) with the
 kernel time, interactions/s, FLOP/s by the reference's own per-core flop count and the error of a strided target
-sample against the oracle. Usage: python scripts/bench_cores.py [particles=262144]"""
+sample against the oracle. Usage: python tests/perf/bench_cores.py [particles=262144]"""
 import json
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from omega3d_b200 import influence as I  # noqa: E402
 from omega3d_b200 import workloads as W  # noqa: E402

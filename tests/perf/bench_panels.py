@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Secondary measurement (not the headline bench): the panel kernels on the flow_over_sphere geometry
 (BASELINE configs[3]) through the host C ABI, next to the reference's CPU routines on a bounded sample.
-Prints one JSON line per routine. Usage: python scripts/bench_panels.py [levels=2] [particles=1000000]"""
+Prints one JSON line per routine. Usage: python tests/perf/bench_panels.py [levels=2] [particles=1000000]"""
 import json
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from omega3d_b200 import influence as I  # noqa: E402
 from omega3d_b200 import workloads as W  # noqa: E402

@@ -2,7 +2,7 @@
 default order) for the example cases and their grown versions, CUDA-graph replay vs launch-by-launch, next to the
 reference's own CPU step (oracle/_ref, the reference's Points methods + influence templates) where it is small enough.
 
-  python scripts/bench_step.py [--sizes small|all] [--steps K]      -> one JSON line per case
+  python tests/perf/bench_step.py [--sizes small|all] [--steps K]      -> one JSON line per case
 """
 import argparse
 import json
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from omega3d_b200 import convection as C  # noqa: E402
 from omega3d_b200 import influence as I  # noqa: E402

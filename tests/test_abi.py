@@ -61,6 +61,19 @@ def test_product_never_imports_the_oracle():
                 assert "oracle_py" not in text and "biot_oracle" not in text and "libo3d_ref" not in text, f
 
 
+def test_only_tests_smoke_and_bench_touch_the_oracle():
+    """oracle/ is the checker: besides tests/ only bench.py (CPU-baseline legs) and __graft_entry__.py (smoke, and build(),
+    which compiles it) may name it - not the package, not integration/, not scripts/ or tools/."""
+    for sub in ("omega3d_b200", "integration", "include", "scripts", "tools"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, sub)):
+            if os.sep + "lib" in dirpath or "__pycache__" in dirpath:
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".sh", ".inc")):
+                    text = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert "oracle_py" not in text and "from oracle" not in text and "libo3d_oracle" not in text, os.path.join(dirpath, f)
+
+
 def test_execenv_and_resultstype_mirror_reference():
     e = I.ExecEnv()
     assert e.is_internal() and e.get_instrs() == I.accel_t.gpu_cuda and int(I.accel_t.gpu_cuda) == 4
