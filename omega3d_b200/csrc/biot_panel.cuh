@@ -41,14 +41,45 @@ struct Tri {
   float x0, y0, z0, x1, y1, z1, x2, y2, z2;
 };
 
+// s / 3 correctly rounded (== __fdiv_rn(s, 3.0f), the reference's IEEE division) in three FP32 instructions instead of the
+// ~9 of the generic division (FCHK, MUFU-seeded FFMA chain, convergence barrier around a slow-path call): with
+// y = RN(1/3), q = RN(s y) is a faithful quotient (|s y - s/3| <= 2^-25 |s/3|: at most a quarter ulp off before rounding),
+// r = s - 3 q is exact in one FMA, and q + r y rounds to RN(s/3) (Markstein's theorem). Zeros, infinities and the subnormal
+// range aside - an exhaustive sweep of all 2^32 inputs on the device (csrc/microbench/div3_check.cu,
+// profiles/r01_div3_check.txt) finds no other difference; -0 gives +0, which a centroid coordinate cannot tell apart.
+__device__ __forceinline__ float div3_rn(float s) {
+  const float y = 0.3333333432674407958984375f;   // 0x3EAAAAAB
+  const float q = __fmul_rn(s, y);
+  const float r = __fmaf_rn(-3.0f, q, s);
+  return __fmaf_rn(r, y, q);
+}
 // reference operand order: (a + b + c) / 3  (src/Kernels.h:1052-1054)
 __device__ __forceinline__ float third_sum(float a, float b, float c) {
-  return __fdiv_rn(__fadd_rn(__fadd_rn(a, b), c), 3.0f);
+  return div3_rn(__fadd_rn(__fadd_rn(a, b), c));
 }
 __device__ __forceinline__ float mid(float a, float b) { return __fmul_rn(0.5f, __fadd_rn(a, b)); }
 // my_dist (src/Kernels.h:979-982): sqrt(dx*dx + dy*dy + dz*dz), unfused, left to right
 __device__ __forceinline__ float sumsq_rn(float dx, float dy, float dz) {
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// The stop predicate without the square root. The reference tests  my_dist = sqrt(dx^2+dy^2+dz^2) > 4 sqrt(area)  with a
+// correctly rounded sqrt (src/Kernels.h:979-1002); that function is monotonic, so for every threshold thr there is one float
+// T = max { x : sqrt_rn(x) <= thr }  with  sqrt_rn(x) > thr  <=>  x > T  for all x >= 0: the SAME decision, bit for bit, from
+// the squared distance the leaf needs anyway, without an IEEE square root (MUFU + fix-up, ~8 instructions) per visited node.
+// T is found once per panel (pan_pack_kernel) by stepping from fl(thr*thr) through neighbouring floats; a level down, the
+// threshold halves and T quarters, both exactly (sqrt_rn(4^-l x) = 2^-l sqrt_rn(x)). Checked by brute force over the
+// neighbourhood of T for thousands of thresholds (tests/test_abi.py::test_squared_threshold_identity), and on the device by
+// the leaf-for-leaf flop counts of the golden panels (tests/test_gpu_parity.py::test_panels_golden).
+__device__ __forceinline__ float sq_threshold(float thr) {
+  float x = __fmul_rn(thr, thr);
+  for (int it = 0; it < 8 && x > 0.0f && __fsqrt_rn(x) > thr; ++it) x = __uint_as_float(__float_as_uint(x) - 1u);
+  for (int it = 0; it < 8; ++it) {
+    const float nx = __uint_as_float(__float_as_uint(x) + 1u);
+    if (!(__fsqrt_rn(nx) <= thr)) break;
+    x = nx;
+  }
+  return x;
 }
 
 struct Mids {
@@ -111,15 +142,14 @@ __device__ __forceinline__ void pan_leaf(float dx, float dy, float dz, float dis
 }
 
 // Node test + leaf for a triangle whose centroid is (cx,cy,cz): returns true when the node was
-// consumed as a leaf (well separated, or deepest level).
+// consumed as a leaf (well separated, or deepest level). thrsq = sq_threshold(4 sqrt(area of the node)).
 template <bool GRAD>
-__device__ __forceinline__ bool pan_node(float cx, float cy, float cz, float thr, bool deepest, float tx, float ty,
+__device__ __forceinline__ bool pan_node(float cx, float cy, float cz, float thrsq, bool deepest, float tx, float ty,
                                          float tz, float wx, float wy, float wz, float q,
                                          float (&acc)[PanAcc<GRAD>::N]) {
   const float dx = __fsub_rn(tx, cx), dy = __fsub_rn(ty, cy), dz = __fsub_rn(tz, cz);
   const float distsq = sumsq_rn(dx, dy, dz);
-  const float dist = __fsqrt_rn(distsq);
-  if (dist > thr || deepest) {
+  if (distsq > thrsq || deepest) {      // == sqrt_rn(distsq) > thr, see sq_threshold
     pan_leaf<GRAD>(dx, dy, dz, distsq, wx, wy, wz, q, acc);
     return true;
   }
@@ -127,13 +157,13 @@ __device__ __forceinline__ bool pan_node(float cx, float cy, float cz, float thr
 }
 
 // Levels 1..3 of a (panel, point) pair whose level-0 node was NOT well separated. (wx,wy,wz,q) = total panel
-// strengths; thr0 = 4 sqrt(area). counts[0] += leaves, counts[1] += splits (the level-0 split included).
+// strengths; thr0 = sq_threshold(4 sqrt(area)), the level-0 squared threshold. counts[0] += leaves, counts[1] += splits (the level-0 split included).
 template <bool GRAD>
 __device__ __forceinline__ void pan_subdivide(const Tri& p0, float thr0, float wx, float wy, float wz, float q, float tx,
                                               float ty, float tz, float (&acc)[PanAcc<GRAD>::N], unsigned (&counts)[2]) {
   counts[1] += 1;
   const Mids m0 = tri_mids(p0);
-  const float w1x = wx * 0.25f, w1y = wy * 0.25f, w1z = wz * 0.25f, q1 = q * 0.25f, thr1 = thr0 * 0.5f;
+  const float w1x = wx * 0.25f, w1y = wy * 0.25f, w1z = wz * 0.25f, q1 = q * 0.25f, thr1 = thr0 * 0.25f;
 #pragma unroll 1
   for (int k1 = 0; k1 < 4; ++k1) {
     const Tri p1 = tri_child(p0, m0, k1);
@@ -144,7 +174,7 @@ __device__ __forceinline__ void pan_subdivide(const Tri& p0, float thr0, float w
     }
     counts[1] += 1;
     const Mids m1 = tri_mids(p1);
-    const float w2x = w1x * 0.25f, w2y = w1y * 0.25f, w2z = w1z * 0.25f, q2 = q1 * 0.25f, thr2 = thr1 * 0.5f;
+    const float w2x = w1x * 0.25f, w2y = w1y * 0.25f, w2z = w1z * 0.25f, q2 = q1 * 0.25f, thr2 = thr1 * 0.25f;
 #pragma unroll 1
     for (int k2 = 0; k2 < 4; ++k2) {
       const Tri p2 = tri_child(p1, m1, k2);
@@ -168,6 +198,7 @@ __device__ __forceinline__ void pan_subdivide(const Tri& p0, float thr0, float w
 }
 
 // Whole (panel, point) pair: level-0 node, then the subdivision if it was not well separated.
+// (thr0 is the SQUARED level-0 threshold, sq_threshold(4 sqrt(area)).)
 template <bool GRAD>
 __device__ __forceinline__ void pan_on_point(const Tri& p0, float c0x, float c0y, float c0z, float thr0, float wx,
                                              float wy, float wz, float q, float tx, float ty, float tz,
@@ -201,7 +232,7 @@ __device__ __forceinline__ void pan_promote(float (&acc)[PanAcc<GRAD>::N], doubl
 
 // ---- packed panel records ---------------------------------------------------------------------------
 //   r[0] = { x0 y0 z0 x1 }  r[1] = { y1 z1 x2 y2 }  r[2] = { z2 wx wy wz }  r[3] = { q cx cy cz }
-//   r[4] = { thr0 = 4 sqrt(area), area, 0, 0 }
+//   r[4] = { thr0 = 4 sqrt(area), area, sq_threshold(thr0), 0 }
 // Padding records (j >= np) sit far away with zero strength and thr0 = 0: always one zero-valued leaf.
 __global__ void pan_pack_kernel(int64_t np, int64_t np_pad, const float* nx, const float* ny, const float* nz,
                                 const uint32_t* idx, const float* tsx, const float* tsy, const float* tsz,
@@ -218,7 +249,8 @@ __global__ void pan_pack_kernel(int64_t np, int64_t np_pad, const float* nx, con
     r1 = make_float4(y1, z1, x2, y2);
     r2 = make_float4(z2, tsx ? tsx[j] : 0.f, tsy ? tsy[j] : 0.f, tsz ? tsz[j] : 0.f);
     r3 = make_float4(sss ? __fmul_rn(sss[j], sa) : 0.f, third_sum(x0, x1, x2), third_sum(y0, y1, y2), third_sum(z0, z1, z2));
-    r4 = make_float4(__fmul_rn(__fsqrt_rn(sa), 4.0f), sa, 0.f, 0.f);
+    const float thr0 = __fmul_rn(__fsqrt_rn(sa), 4.0f);
+    r4 = make_float4(thr0, sa, sq_threshold(thr0), 0.f);
   }
   float4* o = out + (size_t)j * kPanRec;
   o[0] = r0; o[1] = r1; o[2] = r2; o[3] = r3; o[4] = r4;
@@ -292,7 +324,7 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_kernel(const PanPtsArgs p) {
 #pragma unroll 1
     for (int j = 0; j < kPanTile; ++j) {
       const float4 r2 = tile[j * kPanRec + 2], r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
-      if (pan_node<GRAD>(r3.y, r3.z, r3.w, r4.x, false, tx, ty, tz, r2.y, r2.z, r2.w, r3.x, acc)) counts[0] += 1;
+      if (pan_node<GRAD>(r3.y, r3.z, r3.w, r4.z, false, tx, ty, tz, r2.y, r2.z, r2.w, r3.x, acc)) counts[0] += 1;
       else near |= 1ull << j;
     }
     while (near) {
@@ -301,7 +333,7 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_kernel(const PanPtsArgs p) {
       const float4 r0 = tile[j * kPanRec], r1 = tile[j * kPanRec + 1], r2 = tile[j * kPanRec + 2],
                    r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
       const Tri t{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
-      pan_subdivide<GRAD>(t, r4.x, r2.y, r2.z, r2.w, r3.x, tx, ty, tz, acc, counts);
+      pan_subdivide<GRAD>(t, r4.z, r2.y, r2.z, r2.w, r3.x, tx, ty, tz, acc, counts);
     }
     pan_promote<GRAD>(acc, sum);
   }
@@ -357,7 +389,7 @@ __global__ void __launch_bounds__(BLOCK) pts_pan_kernel(const PtsPanArgs p) {
   const float4* r = p.pan + (size_t)ic * kPanRec;
   const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4];
   const Tri t{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
-  const float cx = r3.y, cy = r3.z, cz = r3.w, thr0 = r4.x;
+  const float cx = r3.y, cy = r3.z, cz = r3.w, thr0 = r4.z;   // the squared level-0 threshold (sq_threshold)
 
   float acc[3] = {0.f, 0.f, 0.f};
   double sum[3] = {0.0, 0.0, 0.0};
@@ -445,13 +477,17 @@ __device__ __forceinline__ void coef_leaf(float dx, float dy, float dz, float di
   R.v[8] = fmaf(k, dz, R.v[8]);
 }
 
+// SQ: thr is the squared threshold of sq_threshold (levels 1..3); !SQ: thr is 4 (sqrt(sa) + sqrt(ta)) itself and the
+// distance takes the reference's correctly rounded square root (level 0: most pairs end there, and finding the squared
+// threshold costs more than the one square root it would save).
+template <bool SQ>
 __device__ __forceinline__ bool coef_node(const Tri& s, const Tri& t, float thr, bool deepest, float str,
                                           const float (&b1)[3], const float (&b2)[3], Coef9& R) {
   const float sx = third_sum(s.x0, s.x1, s.x2), sy = third_sum(s.y0, s.y1, s.y2), sz = third_sum(s.z0, s.z1, s.z2);
   const float tx = third_sum(t.x0, t.x1, t.x2), ty = third_sum(t.y0, t.y1, t.y2), tz = third_sum(t.z0, t.z1, t.z2);
   const float dx = __fsub_rn(tx, sx), dy = __fsub_rn(ty, sy), dz = __fsub_rn(tz, sz);
   const float distsq = sumsq_rn(dx, dy, dz);
-  if (__fsqrt_rn(distsq) > thr || deepest) {
+  if ((SQ ? distsq : __fsqrt_rn(distsq)) > thr || deepest) {
     coef_leaf(dx, dy, dz, distsq, str, b1, b2, R);
     return true;
   }
@@ -479,30 +515,30 @@ __device__ __forceinline__ void coef_block(const PanCoefArgs& p, const int64_t i
 #pragma unroll
   for (int k = 0; k < 9; ++k) R.v[k] = 0.0f;
 
-  if (coef_node(s0, t0, thr0, false, sa, b1, b2, R)) {
+  if (coef_node<false>(s0, t0, thr0, false, sa, b1, b2, R)) {
     counts[0] += 1;
   } else {
     counts[1] += 1;
     const Mids sm0 = tri_mids(s0), tm0 = tri_mids(t0);
-    const float str1 = sa * 0.0625f, thr1 = thr0 * 0.5f;
+    const float str1 = sa * 0.0625f, thr1 = sq_threshold(thr0) * 0.25f;   // squared thresholds from here down
 #pragma unroll 1
     for (int e1 = 0; e1 < 16; ++e1) {
       const Tri s1 = tri_child(s0, sm0, e1 >> 2), t1 = tri_child(t0, tm0, e1 & 3);
-      if (coef_node(s1, t1, thr1, false, str1, b1, b2, R)) { counts[0] += 1; continue; }
+      if (coef_node<true>(s1, t1, thr1, false, str1, b1, b2, R)) { counts[0] += 1; continue; }
       counts[1] += 1;
       const Mids sm1 = tri_mids(s1), tm1 = tri_mids(t1);
-      const float str2 = str1 * 0.0625f, thr2 = thr1 * 0.5f;
+      const float str2 = str1 * 0.0625f, thr2 = thr1 * 0.25f;
 #pragma unroll 1
       for (int e2 = 0; e2 < 16; ++e2) {
         const Tri s2 = tri_child(s1, sm1, e2 >> 2), t2 = tri_child(t1, tm1, e2 & 3);
-        if (coef_node(s2, t2, thr2, false, str2, b1, b2, R)) { counts[0] += 1; continue; }
+        if (coef_node<true>(s2, t2, thr2, false, str2, b1, b2, R)) { counts[0] += 1; continue; }
         counts[1] += 1;
         const Mids sm2 = tri_mids(s2), tm2 = tri_mids(t2);
         const float str3 = str2 * 0.0625f;
 #pragma unroll 1
         for (int e3 = 0; e3 < 16; ++e3) {
           const Tri s3 = tri_child(s2, sm2, e3 >> 2), t3 = tri_child(t2, tm2, e3 & 3);
-          coef_node(s3, t3, 0.0f, true, str3, b1, b2, R);
+          coef_node<true>(s3, t3, 0.0f, true, str3, b1, b2, R);
           counts[0] += 1;
         }
       }

@@ -1549,7 +1549,7 @@ int closest_point_pass(o3d_ctx* c, const char* who, int mode, float cutoff, int6
     O3D_TRY(d, cudaSetDevice(d.id));
     cudaStream_t st = d.stream;
     O3D_TRY(d, d.geom.ensure(((size_t)3 * nn + (size_t)6 * np) * 4));
-    O3D_TRY(d, d.panels.ensure((size_t)npad * 3 * sizeof(float4)));
+    O3D_TRY(d, d.panels.ensure((size_t)npad * kRefRec * sizeof(float4)));
     O3D_TRY(d, d.targ.ensure((size_t)3 * n * 4));
     float* g = d.geom.as<float>();
     uint32_t* gidx = reinterpret_cast<uint32_t*>(g + 3 * nn);

@@ -14,14 +14,17 @@
 // integer-like work: the kernel keeps the reference's panel order per particle and spells every float operation
 // unfused, in the reference's operation order (its `1.0 / x` is a double division rounded to float), and returns the
 // same bits - positions and counts (tests/test_gpu_reflect.py). One thread owns one particle; panels stream through
-// shared memory as 48-byte records (3 nodes + normal), every LDS a warp-wide broadcast. Bound: FP32/issue (~150 flops
-// per pair, the reference's own count), parallel over particles only.
+// shared memory as 144-byte records, every LDS a warp-wide broadcast. Everything panel_point_distance computes from the
+// PANEL ALONE - the three edge vectors, 1 / |edge|^2 (the double divisions) and the three normal x edge vectors of the
+// prism test, 48 of its ~150 flops - is formed once per panel by ref_pack_kernel, with the same unfused operations in the
+// same order, and read from the record: the same bits reach every comparison. Bound: FP32/issue, parallel over particles.
 #pragma once
 #include "o3d_common.cuh"
 
 namespace o3d {
 
-constexpr int kRefTile = 256;   // panels per shared-memory tile (12 KB)
+constexpr int kRefTile = 256;   // panels per shared-memory tile (36 KB)
+constexpr int kRefRec = 9;      // float4 per packed panel: 3 nodes + normal | 3 x (edge, 1/|edge|^2) | 3 x (normal x edge)
 
 struct Closest {
   float distsq, cpx, cpy, cpz;
@@ -38,10 +41,9 @@ __device__ __forceinline__ void cross3_rn(float a0, float a1, float a2, float b0
 // "const S r = 1.0 / x" : a double division stored into a float
 __device__ __forceinline__ float recip_via_double(float x) { return __double2float_rn(__ddiv_rn(1.0, (double)x)); }
 
-// one edge of panel_point_distance (src/Reflect.h:107-159): a -> b, dt = t - a
-__device__ __forceinline__ void closest_edge(float ax, float ay, float az, float ex, float ey, float ez, float dx, float dy, float dz,
-                                             Closest& r) {
-  const float inv = recip_via_double(dot3_rn(ex, ey, ez, ex, ey, ez));
+// one edge of panel_point_distance (src/Reflect.h:107-159): a -> b, dt = t - a; inv = 1 / |e|^2 from the record
+__device__ __forceinline__ void closest_edge(float ax, float ay, float az, float ex, float ey, float ez, float inv, float dx, float dy,
+                                             float dz, Closest& r) {
   float rx, ry, rz;
   cross3_rn(ex, ey, ez, dx, dy, dz, rx, ry, rz);
   const float d = __fmul_rn(dot3_rn(rx, ry, rz, rx, ry, rz), inv);
@@ -56,8 +58,9 @@ __device__ __forceinline__ void closest_edge(float ax, float ay, float az, float
   }
 }
 
-// src/Reflect.h:55-188
-__device__ __forceinline__ Closest panel_point_distance(const float4 p0, const float4 p1, const float4 p2, float tx, float ty, float tz) {
+// src/Reflect.h:55-188; rec = the panel's kRefRec float4 (ref_pack_kernel)
+__device__ __forceinline__ Closest panel_point_distance(const float4* __restrict__ rec, float tx, float ty, float tz) {
+  const float4 p0 = rec[0], p1 = rec[1], p2 = rec[2];
   const float x0 = p0.x, y0 = p0.y, z0 = p0.z, x1 = p0.w, y1 = p1.x, z1 = p1.y, x2 = p1.z, y2 = p1.w, z2 = p2.x;
   const float nx = p2.y, ny = p2.z, nz = p2.w;
   Closest r;
@@ -74,20 +77,15 @@ __device__ __forceinline__ Closest panel_point_distance(const float4 p0, const f
   const float d2 = dot3_rn(d2x, d2y, d2z, d2x, d2y, d2z);
   if (d2 < r.distsq) { r.distsq = d2; r.cpx = x2; r.cpy = y2; r.cpz = z2; }
   // the three edges (:107-159)
-  const float e01x = __fsub_rn(x1, x0), e01y = __fsub_rn(y1, y0), e01z = __fsub_rn(z1, z0);
-  closest_edge(x0, y0, z0, e01x, e01y, e01z, d0x, d0y, d0z, r);
-  const float e12x = __fsub_rn(x2, x1), e12y = __fsub_rn(y2, y1), e12z = __fsub_rn(z2, z1);
-  closest_edge(x1, y1, z1, e12x, e12y, e12z, d1x, d1y, d1z, r);
-  const float e20x = __fsub_rn(x0, x2), e20y = __fsub_rn(y0, y2), e20z = __fsub_rn(z0, z2);
-  closest_edge(x2, y2, z2, e20x, e20y, e20z, d2x, d2y, d2z, r);
-  // inside the panel's prism (:163-184)
-  float ix, iy, iz;
-  cross3_rn(nx, ny, nz, e01x, e01y, e01z, ix, iy, iz);
-  const float in01 = dot3_rn(d0x, d0y, d0z, ix, iy, iz);
-  cross3_rn(nx, ny, nz, e12x, e12y, e12z, ix, iy, iz);
-  const float in12 = dot3_rn(d1x, d1y, d1z, ix, iy, iz);
-  cross3_rn(nx, ny, nz, e20x, e20y, e20z, ix, iy, iz);
-  const float in20 = dot3_rn(d2x, d2y, d2z, ix, iy, iz);
+  const float4 e01 = rec[3], e12 = rec[4], e20 = rec[5];
+  closest_edge(x0, y0, z0, e01.x, e01.y, e01.z, e01.w, d0x, d0y, d0z, r);
+  closest_edge(x1, y1, z1, e12.x, e12.y, e12.z, e12.w, d1x, d1y, d1z, r);
+  closest_edge(x2, y2, z2, e20.x, e20.y, e20.z, e20.w, d2x, d2y, d2z, r);
+  // inside the panel's prism (:163-184); normal x edge from the record
+  const float4 i01 = rec[6], i12 = rec[7], i20 = rec[8];
+  const float in01 = dot3_rn(d0x, d0y, d0z, i01.x, i01.y, i01.z);
+  const float in12 = dot3_rn(d1x, d1y, d1z, i12.x, i12.y, i12.z);
+  const float in20 = dot3_rn(d2x, d2y, d2z, i20.x, i20.y, i20.z);
   if (in01 > 0.0f && in12 > 0.0f && in20 > 0.0f) {
     const float td = dot3_rn(d0x, d0y, d0z, nx, ny, nz);
     r.distsq = __fmul_rn(td, td);
@@ -98,8 +96,9 @@ __device__ __forceinline__ Closest panel_point_distance(const float4 p0, const f
   return r;
 }
 
-// nodes SoA + connectivity + normals SoA (3 x np, stride np) -> 3 float4 per panel, padded to whole tiles with
-// panels a long way off (they never come within eps of any real minimum)
+// nodes SoA + connectivity + normals SoA (3 x np, stride np) -> kRefRec float4 per panel, padded to whole tiles (padding
+// records are never read: the kernel stops at the last real panel). The derived fields are the reference's own
+// per-pair expressions (src/Reflect.h:107-113 edge and 1.0/dot(edge,edge), :163-170 cross(normal, edge)), evaluated once.
 __global__ void ref_pack_kernel(int64_t np, int64_t np_pad, const float* nx, const float* ny, const float* nz, const uint32_t* idx,
                                 const float* nrm, float4* out) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -111,7 +110,19 @@ __global__ void ref_pack_kernel(int64_t np, int64_t np_pad, const float* nx, con
     b = make_float4(ny[i1], nz[i1], nx[i2], ny[i2]);
     c = make_float4(nz[i2], nrm[j], nrm[np + j], nrm[2 * np + j]);
   }
-  out[3 * j] = a; out[3 * j + 1] = b; out[3 * j + 2] = c;
+  float4* o = out + (size_t)j * kRefRec;
+  o[0] = a; o[1] = b; o[2] = c;
+  const float x0 = a.x, y0 = a.y, z0 = a.z, x1 = a.w, y1 = b.x, z1 = b.y, x2 = b.z, y2 = b.w, z2 = c.x;
+  const float e[3][3] = {{__fsub_rn(x1, x0), __fsub_rn(y1, y0), __fsub_rn(z1, z0)},
+                         {__fsub_rn(x2, x1), __fsub_rn(y2, y1), __fsub_rn(z2, z1)},
+                         {__fsub_rn(x0, x2), __fsub_rn(y0, y2), __fsub_rn(z0, z2)}};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    o[3 + k] = make_float4(e[k][0], e[k][1], e[k][2], recip_via_double(dot3_rn(e[k][0], e[k][1], e[k][2], e[k][0], e[k][1], e[k][2])));
+    float ix, iy, iz;
+    cross3_rn(c.y, c.z, c.w, e[k][0], e[k][1], e[k][2], ix, iy, iz);
+    o[6 + k] = make_float4(ix, iy, iz, 0.f);
+  }
 }
 
 struct ReflectArgs {
@@ -127,7 +138,7 @@ struct ReflectArgs {
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) reflect_kernel(const ReflectArgs p) {
-  __shared__ float4 tile[kRefTile * 3];
+  __shared__ float4 tile[kRefTile * kRefRec];
   const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   const int64_t ic = min(i, p.nt - 1);
   const float tx = p.tx[ic], ty = p.ty[ic], tz = p.tz[ic];
@@ -138,12 +149,12 @@ __global__ void __launch_bounds__(BLOCK) reflect_kernel(const ReflectArgs p) {
 
   for (int k = 0; k < p.ntiles; ++k) {
     __syncthreads();
-    for (int q = threadIdx.x; q < kRefTile * 3; q += BLOCK) tile[q] = p.pan[(size_t)k * kRefTile * 3 + q];
+    for (int q = threadIdx.x; q < kRefTile * kRefRec; q += BLOCK) tile[q] = p.pan[(size_t)k * kRefTile * kRefRec + q];
     __syncthreads();
     const int nj = (int)min((int64_t)kRefTile, p.np - (int64_t)k * kRefTile);
     for (int j = 0; j < nj; ++j) {
-      const float4 p0 = tile[3 * j], p1 = tile[3 * j + 1], p2 = tile[3 * j + 2];
-      const Closest r = panel_point_distance(p0, p1, p2, tx, ty, tz);
+      const float4 p2 = tile[kRefRec * j + 2];
+      const Closest r = panel_point_distance(tile + kRefRec * j, tx, ty, tz);
       // the reference's hit list (src/Reflect.h:226-243), reduced on the fly to what is read from it afterwards:
       // the sums of normals and contact points in hit order, the count, and the first hit's distance
       if (r.distsq < __fsub_rn(mindist, eps)) {

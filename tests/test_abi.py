@@ -114,3 +114,33 @@ def test_workloads_are_seeded():
     assert abs(float(a[2][0]) - 1.5 * 1000 ** (-1 / 3)) < 1e-6
     n, i = W.icosphere(2)
     assert i.shape == (320, 3)  # the flow_over_sphere body of SURVEY.md 8 (C4)
+
+
+def test_squared_threshold_identity():
+    """csrc/biot_panel.cuh: sq_threshold. For a correctly rounded float sqrt, T = max{x : sqrt(x) <= thr} satisfies
+    sqrt(x) > thr <=> x > T for every float x >= 0, and a subdivision level down (thr/2, T/4) it still does - so the panel
+    kernels take the reference's stop decision (src/Kernels.h:979-1002) from the squared distance, bit for bit, without
+    the square root. Brute force over the float neighbourhood of T, same stepping algorithm as the device function."""
+    def t_of(thr):
+        xi = np.array([f32(thr) * f32(thr)], f32).view(np.uint32)
+        for _ in range(8):
+            if xi.view(f32)[0] > 0 and np.sqrt(xi.view(f32)[0]) > thr:
+                xi -= 1
+            else:
+                break
+        for _ in range(8):
+            if not (np.sqrt((xi + 1).view(f32)[0]) <= thr):
+                break
+            xi += 1
+        return xi.view(f32)[0]
+
+    rng = np.random.default_rng(0)
+    thrs = np.concatenate([rng.random(600).astype(f32) * f32(2), rng.random(600).astype(f32) * f32(1e-3),
+                           np.array([0, 1, 0.5, 4 * np.sqrt(f32(0.0098))], f32)])
+    for thr in thrs:
+        t = t_of(thr)
+        for lev in range(4):
+            thr_l, t_l = f32(thr) * f32(0.5) ** lev, t * f32(0.25) ** lev
+            ti = int(np.array([t_l], f32).view(np.uint32)[0])
+            xs = np.arange(max(ti - 40, 0), ti + 40, dtype=np.uint32).view(f32)
+            assert np.array_equal(np.sqrt(xs) > thr_l, xs > t_l), (thr, lev)
