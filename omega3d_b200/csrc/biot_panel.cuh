@@ -186,7 +186,7 @@ __device__ __forceinline__ void pan_subdivide(const Tri& p0, float thr0, float w
       counts[1] += 1;
       const Mids m2 = tri_mids(p2);
       const float w3x = w2x * 0.25f, w3y = w2y * 0.25f, w3z = w2z * 0.25f, q3 = q2 * 0.25f;
-#pragma unroll 1
+#pragma unroll   // deepest level, most of the visited nodes: unrolled so that each child is a static choice of registers, not selects
       for (int k3 = 0; k3 < 4; ++k3) {
         const Tri p3 = tri_child(p2, m2, k3);
         pan_node<GRAD>(third_sum(p3.x0, p3.x1, p3.x2), third_sum(p3.y0, p3.y1, p3.y2), third_sum(p3.z0, p3.z1, p3.z2),
@@ -408,14 +408,18 @@ __global__ void __launch_bounds__(BLOCK) pts_pan_kernel(const PtsPanArgs p) {
     for (int c0 = 0; c0 < cnt; c0 += 64) {
       const int cn = min(64, cnt - c0);
       unsigned long long near = 0ull;
+      // c0 is even and a record pair holds particles 2 pr, 2 pr + 1: one set of four LDS.128 serves both (the stream is
+      // padded to whole tiles, so the second half of the last pair is readable; it is skipped when jj + 1 == cn)
 #pragma unroll 1
-      for (int jj = 0; jj < cn; ++jj) {
-        const int j = c0 + jj, pr = j >> 1, h = j & 1;
+      for (int jj = 0; jj < cn; jj += 2) {
+        const int pr = (c0 + jj) >> 1;
         const float4 q0 = tile[4 * pr], q1 = tile[4 * pr + 1], q2 = tile[4 * pr + 2], q3 = tile[4 * pr + 3];
-        const float px = -(h ? q0.y : q0.x), py = -(h ? q0.w : q0.z), pz = -(h ? q1.y : q1.x);
-        const float wx = h ? q2.y : q2.x, wy = h ? q2.w : q2.z, wz = h ? q3.y : q3.x;
-        if (pan_node<false>(cx, cy, cz, thr0, false, px, py, pz, wx, wy, wz, 0.0f, acc)) counts[0] += 1;
+        if (pan_node<false>(cx, cy, cz, thr0, false, -q0.x, -q0.z, -q1.x, q2.x, q2.z, q3.x, 0.0f, acc)) counts[0] += 1;
         else near |= 1ull << jj;
+        if (jj + 1 < cn) {
+          if (pan_node<false>(cx, cy, cz, thr0, false, -q0.y, -q0.w, -q1.y, q2.y, q2.w, q3.y, 0.0f, acc)) counts[0] += 1;
+          else near |= 1ull << (jj + 1);
+        }
       }
       while (near) {
         const int jj = __ffsll((long long)near) - 1;
