@@ -175,7 +175,7 @@ __device__ __forceinline__ void pan_subdivide(const Tri& p0, float thr0, float w
     counts[1] += 1;
     const Mids m1 = tri_mids(p1);
     const float w2x = w1x * 0.25f, w2y = w1y * 0.25f, w2z = w1z * 0.25f, q2 = q1 * 0.25f, thr2 = thr1 * 0.25f;
-#pragma unroll 1
+#pragma unroll
     for (int k2 = 0; k2 < 4; ++k2) {
       const Tri p2 = tri_child(p1, m1, k2);
       if (pan_node<GRAD>(third_sum(p2.x0, p2.x1, p2.x2), third_sum(p2.y0, p2.y1, p2.y2),
@@ -539,7 +539,7 @@ __device__ __forceinline__ void coef_block(const PanCoefArgs& p, const int64_t i
         counts[1] += 1;
         const Mids sm2 = tri_mids(s2), tm2 = tri_mids(t2);
         const float str3 = str2 * 0.0625f;
-#pragma unroll 1
+#pragma unroll 4   // the target child (e3 & 3) becomes a static choice of registers
         for (int e3 = 0; e3 < 16; ++e3) {
           const Tri s3 = tri_child(s2, sm2, e3 >> 2), t3 = tri_child(t2, tm2, e3 & 3);
           coef_node<true>(s3, t3, 0.0f, true, str3, b1, b2, R);
