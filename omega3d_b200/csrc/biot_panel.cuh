@@ -164,7 +164,7 @@ __device__ __forceinline__ void pan_subdivide(const Tri& p0, float thr0, float w
   counts[1] += 1;
   const Mids m0 = tri_mids(p0);
   const float w1x = wx * 0.25f, w1y = wy * 0.25f, w1z = wz * 0.25f, q1 = q * 0.25f, thr1 = thr0 * 0.25f;
-#pragma unroll 1
+#pragma unroll 1   // (unrolling this level too costs registers: 255 + spills in pts_pan_kernel)
   for (int k1 = 0; k1 < 4; ++k1) {
     const Tri p1 = tri_child(p0, m0, k1);
     if (pan_node<GRAD>(third_sum(p1.x0, p1.x1, p1.x2), third_sum(p1.y0, p1.y1, p1.y2), third_sum(p1.z0, p1.z1, p1.z2),
@@ -539,7 +539,7 @@ __device__ __forceinline__ void coef_block(const PanCoefArgs& p, const int64_t i
         counts[1] += 1;
         const Mids sm2 = tri_mids(s2), tm2 = tri_mids(t2);
         const float str3 = str2 * 0.0625f;
-#pragma unroll 4   // the target child (e3 & 3) becomes a static choice of registers
+#pragma unroll     // both children (e3 >> 2, e3 & 3) become static choices of registers
         for (int e3 = 0; e3 < 16; ++e3) {
           const Tri s3 = tri_child(s2, sm2, e3 >> 2), t3 = tri_child(t2, tm2, e3 & 3);
           coef_node<true>(s3, t3, 0.0f, true, str3, b1, b2, R);
