@@ -8,7 +8,7 @@ SEL="golden or kat or empty or bad_arguments or edge_cases or bit_exact or test_
 for tool in memcheck initcheck; do
   echo "== compute-sanitizer --tool $tool"
   timeout 540 compute-sanitizer --tool $tool --error-exitcode 66 --print-limit 20 \
-      python -m pytest tests/test_gpu_parity.py tests/test_gpu_reflect.py tests/test_gpu_convection.py tests/test_gpu_bem.py \
+      python -m pytest tests/test_gpu_parity.py tests/test_gpu_reflect.py tests/test_gpu_convection.py tests/test_gpu_bem.py tests/test_gpu_cores.py \
       -q -m gpu -x -k "$SEL" -p no:cacheprovider > $OUT/sanitize_$tool.txt 2>&1
   echo "exit $?" | tee -a $OUT/sanitize_$tool.txt
   grep -E "ERROR SUMMARY|passed|failed|Invalid|Uninitialized" $OUT/sanitize_$tool.txt | tail -8
