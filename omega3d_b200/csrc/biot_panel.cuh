@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_kernel(const PanPtsArgs p) {
     // mask (kPanTile = 64); (B) each lane walks its own mask in ascending panel order. Per target this only reorders
     // the FP32 terms inside one tile (far leaves first); leaf and split counts are unchanged.
     unsigned long long near = 0ull;
-#pragma unroll 1
+#pragma unroll 2
     for (int j = 0; j < kPanTile; ++j) {
       const float4 r2 = tile[j * kPanRec + 2], r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
       if (pan_node<GRAD>(r3.y, r3.z, r3.w, r4.z, false, tx, ty, tz, r2.y, r2.z, r2.w, r3.x, acc)) counts[0] += 1;

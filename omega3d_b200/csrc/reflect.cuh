@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(BLOCK) reflect_kernel(const ReflectArgs p) {
     for (int q = threadIdx.x; q < kRefTile * kRefRec; q += BLOCK) tile[q] = p.pan[(size_t)k * kRefTile * kRefRec + q];
     __syncthreads();
     const int nj = (int)min((int64_t)kRefTile, p.np - (int64_t)k * kRefTile);
+#pragma unroll 2
     for (int j = 0; j < nj; ++j) {
       const float4 p2 = tile[kRefRec * j + 2];
       const Closest r = panel_point_distance(tile + kRefRec * j, tx, ty, tz);
