@@ -532,7 +532,7 @@ __device__ __forceinline__ void coef_block(const PanCoefArgs& p, const int64_t i
       counts[1] += 1;
       const Mids sm1 = tri_mids(s1), tm1 = tri_mids(t1);
       const float str2 = str1 * 0.0625f, thr2 = thr1 * 0.25f;
-#pragma unroll 1
+#pragma unroll 1   // (unroll 4 here: 254 registers, coefficient block 5.2 -> 7.7 ms at 5120 panels: measured, not adopted)
       for (int e2 = 0; e2 < 16; ++e2) {
         const Tri s2 = tri_child(s1, sm1, e2 >> 2), t2 = tri_child(t1, tm1, e2 & 3);
         if (coef_node<true>(s2, t2, thr2, false, str2, b1, b2, R)) { counts[0] += 1; continue; }
