@@ -114,6 +114,15 @@ int o3d_cuda_pan_on_pan_coeff(o3d_ctx* ctx, int64_t snn, const float* snx, const
 
 /* Number of 32-byte records the packed source stream holds for ns sources (padded to whole tiles). */
 int64_t o3d_cuda_packed_records(int64_t ns);
+
+/* The launch shape the library picks for particles -> points on a device with sm_count SMs - host arithmetic only, no
+ * device needed (capi.cu: pp_shape): CTAs along the targets (128 threads x 2 targets with gradients, x 4 without),
+ * source slices (gridDim.y; > 1 when the targets alone would leave much of the last wave of resident CTAs empty - the
+ * slices meet in FP64 slabs of workspace_bytes, summed in slice order), and the fraction of the launch's waves that is
+ * occupied. Any output pointer may be NULL. The reference's counterpart is the static OpenMP schedule over targets
+ * (src/Influence.h:281,405,445). */
+int o3d_cuda_plan_pts_on_pts(int sm_count, int64_t ns, int64_t nt, int want_grad, int64_t* grid_x, int* nsplit,
+                             double* wave_efficiency, int64_t* workspace_bytes);
 /* SoA sources -> packed record stream `packed` (device memory, nrec * 32 bytes). nrec = 0 means
  * o3d_cuda_packed_records(ns); a larger whole number of tiles is filled up with zero-strength records
  * (ranks of a sharded job all contribute equally sized streams to one all-gather). */

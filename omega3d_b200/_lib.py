@@ -57,6 +57,7 @@ SYMBOLS = {
     "o3d_cuda_particles_graph_active": (c_int, [c_void_p]),
     "o3d_cuda_set_tuned_kernels": (c_int, [c_void_p, c_int]),
     "o3d_cuda_tuned_kernels": (c_int, [c_void_p]),
+    "o3d_cuda_plan_pts_on_pts": (c_int, [c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "o3d_cuda_set_core_func": (c_int, [c_void_p, c_int]),
     "o3d_cuda_core_func": (c_int, [c_void_p]),
     "o3d_cuda_set_profiling": (c_int, [c_void_p, c_int]),

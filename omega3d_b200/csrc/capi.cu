@@ -232,10 +232,10 @@ double pp_pair_flops(int core, bool grad, bool blob) { return (grad ? 54.0 : 23.
 // ... and of the panel leaves: flops_0vs_0pg = 79 + tp_grads, flops_0vs_0p = 29 + tp_nograds (src/Kernels.h:115,294); WL: 93 / 37
 double leaf_flops(int core, bool grad) { return (grad ? 79.0 : 29.0) + core_flops(core, grad, false); }
 
-PPShape pp_shape(const Device& d, int64_t ntiles, int64_t nt, bool grad) {
+PPShape pp_shape(int sm_count, int64_t ntiles, int64_t nt, bool grad) {
   const int per_cta = kPPBlock * (grad ? kPPTgrad : kPPTvel);
   const int64_t gx = (nt + per_cta - 1) / per_cta;
-  const int64_t slots = (int64_t)d.sm_count * (grad ? kPPResidentGrad : kPPResidentVel);
+  const int64_t slots = (int64_t)sm_count * (grad ? kPPResidentGrad : kPPResidentVel);
   // Pick the source split that wastes the least of the last wave: efficiency = CTAs / (waves * slots).
   // Large target counts (>= 64 waves: at most 0.8 % to gain) never split; tiny ones split until the GPU is covered twice.
   // (The bound was 16 waves until the 2 M point of the size sweep showed 18.45 waves = 97.1 %: 2 M targets per GPU is also
@@ -264,7 +264,7 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
                int64_t tug_stride, double* workspace) {
   const bool grad = tug != nullptr;
   const int64_t ntiles = nrec / kTile;
-  const PPShape s = pp_shape(d, ntiles, nt, grad);
+  const PPShape s = pp_shape(d.sm_count, ntiles, nt, grad);
   PPArgs a{};
   a.src = packed;
   a.ntiles = (int)ntiles;
@@ -1104,6 +1104,20 @@ int o3d_cuda_pan_on_pan_coeff(o3d_ctx* c, int64_t snn, const float* snx, const f
 
 // ---------------------------------------------------------------------------------------------------
 int64_t o3d_cuda_packed_records(int64_t ns) { return ns < 0 ? 0 : padded_sources(ns); }
+
+int o3d_cuda_plan_pts_on_pts(int sm_count, int64_t ns, int64_t nt, int want_grad, int64_t* grid_x, int* nsplit,
+                             double* wave_efficiency, int64_t* workspace_bytes) {
+  if (sm_count < 1 || ns < 1 || nt < 1) return O3D_ERR_INVALID;
+  const bool grad = want_grad != 0;
+  const PPShape s = pp_shape(sm_count, padded_sources(ns) / kTile, nt, grad);
+  const int64_t slots = (int64_t)sm_count * (grad ? kPPResidentGrad : kPPResidentVel);
+  const int64_t ctas = (int64_t)s.grid.x * s.grid.y, waves = (ctas + slots - 1) / slots;
+  if (grid_x) *grid_x = s.grid.x;
+  if (nsplit) *nsplit = s.nsplit;
+  if (wave_efficiency) *wave_efficiency = (double)ctas / (double)(waves * slots);
+  if (workspace_bytes) *workspace_bytes = (int64_t)s.work_bytes;
+  return O3D_OK;
+}
 
 int o3d_cuda_pack_sources_dev(o3d_ctx* c, void* stream, int64_t ns, const float* sx, const float* sy, const float* sz,
                               const float* sr, const float* ssx, const float* ssy, const float* ssz, int64_t nrec,

@@ -144,3 +144,26 @@ def test_squared_threshold_identity():
             ti = int(np.array([t_l], f32).view(np.uint32)[0])
             xs = np.arange(max(ti - 40, 0), ti + 40, dtype=np.uint32).view(f32)
             assert np.array_equal(np.sqrt(xs) > thr_l, xs > t_l), (thr, lev)
+
+
+def test_launch_plan_fills_the_gpu_at_the_benchmark_sizes():
+    """Host logic of the launch shape (capi.cu: pp_shape through o3d_cuda_plan_pts_on_pts, no device needed): at every
+    size of the BASELINE sweep, whole or sharded over 2/4/8 GPUs, the chosen source split leaves at most 1.5 % of the
+    launch's waves of resident CTAs empty on a 148-SM B200, and the FP64 slab workspace stays small."""
+    lib = _lib.load()
+    from ctypes import byref, c_double, c_int, c_int64
+    for n in (1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 24):
+        for gpus in (1, 2, 4, 8):
+            nt = n // gpus
+            gx, sp, eff, ws = c_int64(), c_int(), c_double(), c_int64()
+            assert lib.o3d_cuda_plan_pts_on_pts(148, n, nt, 1, byref(gx), byref(sp), byref(eff), byref(ws)) == 0
+            assert gx.value == (nt + 255) // 256 and 1 <= sp.value <= 64
+            assert eff.value >= 0.985, (n, gpus, sp.value, eff.value)
+            assert ws.value == (sp.value * 12 * nt * 8 if sp.value > 1 else 0) and ws.value <= 2 << 30
+    # tiny target counts: split until the GPU is covered, never more slices than tiles
+    gx, sp, eff, ws = c_int64(), c_int(), c_double(), c_int64()
+    assert lib.o3d_cuda_plan_pts_on_pts(148, 100000, 320, 0, byref(gx), byref(sp), byref(eff), byref(ws)) == 0
+    assert gx.value == 1 and 32 <= sp.value <= 64
+    assert lib.o3d_cuda_plan_pts_on_pts(148, 700, 5, 1, byref(gx), byref(sp), byref(eff), byref(ws)) == 0
+    assert sp.value <= 2            # 700 sources are two 512-record tiles
+    assert lib.o3d_cuda_plan_pts_on_pts(0, 10, 10, 1, None, None, None, None) == 1   # O3D_ERR_INVALID
