@@ -148,3 +148,22 @@ def test_restatement_advect_matches_reference_core_builds(restate, core, tag, or
     restate.advect(order, 2, 0.02, (0.1, 0.0, 0.0), x, s, g["adv_r"], e, core=core)
     assert np.array_equal(x, g[f"{tag}_adv{order}_x"]) and np.array_equal(s, g[f"{tag}_adv{order}_s"])
     assert np.array_equal(e, g[f"{tag}_adv{order}_elong"])
+
+
+@pytest.mark.parametrize("core,tag", [(1, "rm"), (2, "exp"), (3, "v2")])
+def test_reference_core_builds_reproduce_cores_golden(core, tag):
+    """Where the core builds of the reference are present (oracle/_ref/libo3d_ref_{rm,exp,v2}.so: built in the container
+    that has /root/reference, shipped prebuilt to the GPU box), they reproduce tests/golden/cores.npz bit for bit - the
+    fixtures are reproducible outputs of the reference's own code, not of the restatement."""
+    import os
+    from oracle import oracle_py
+    if not (os.path.exists(os.path.join(oracle_py.OUT, oracle_py.Reference.CORE_BUILDS[core])) or oracle_py.have_reference()):
+        pytest.skip("core builds of the reference not present")
+    ref = oracle_py.Reference(core=core)
+    g = golden("cores.npz")
+    tu, tug = g["u0"].copy(), g["g0"].copy()
+    ref.pts_on_pts(g["sx"], g["sr"], g["ss"], g["tx"], g["tr"], tu, tug)
+    assert np.array_equal(tu, g[f"{tag}_u_0bg"]) and np.array_equal(tug, g[f"{tag}_g_0bg"])
+    x, s, e = g["adv_x0"].copy(), g["adv_s0"].copy(), np.ones(300, np.float32)
+    ref.advect(2, 2, 0.02, (0.1, 0.0, 0.0), x, s, g["adv_r"], e)
+    assert np.array_equal(x, g[f"{tag}_adv2_x"]) and np.array_equal(s, g[f"{tag}_adv2_s"])
