@@ -167,3 +167,33 @@ def test_reference_core_builds_reproduce_cores_golden(core, tag):
     x, s, e = g["adv_x0"].copy(), g["adv_s0"].copy(), np.ones(300, np.float32)
     ref.advect(2, 2, 0.02, (0.1, 0.0, 0.0), x, s, g["adv_r"], e)
     assert np.array_equal(x, g[f"{tag}_adv2_x"]) and np.array_equal(s, g[f"{tag}_adv2_s"])
+
+
+@pytest.mark.parametrize("core", [0, 1, 2, 3])
+def test_restatement_properties_hold_for_every_core(restate, core):
+    """Size-independent properties the GPU tests lean on, checked on the checker itself: the vortex-only velocity gradient
+    is trace free (d . (d x w) = 0), the sums are exactly linear under power-of-two scaling of the strengths, a particle
+    induces no velocity on itself, and a rigid translation by a power of two leaves velocities unchanged to rounding."""
+    from omega3d_b200 import workloads as W
+    n = 400
+    x, s, r = W.random_cloud(n, seed=31, radius=0.07)
+    s = (s * np.float32(n)).astype(np.float32)
+    u, g = np.zeros((3, n), np.float32), np.zeros((9, n), np.float32)
+    restate.pts_on_pts(x, r, s, x, r, u, g, core=core)
+    assert np.isfinite(u).all() and np.isfinite(g).all()
+    trace = g[0].astype(np.float64) + g[4] + g[8]
+    assert np.max(np.abs(trace)) <= 2e-6 * np.max(np.abs(g))
+    u2, g2 = np.zeros((3, n), np.float32), np.zeros((9, n), np.float32)
+    restate.pts_on_pts(x, r, (s * np.float32(0.25)).astype(np.float32), x, r, u2, g2, core=core)
+    assert np.array_equal(u2, u * np.float32(0.25)) and np.array_equal(g2, g * np.float32(0.25))
+    # one particle on itself: zero velocity; the gradient keeps only the antisymmetric +-w r3 terms (src/Kernels.h:185-191)
+    x1, s1, r1 = x[:, :1].copy(), s[:, :1].copy(), r[:1].copy()
+    a, b = np.zeros((3, 1), np.float32), np.zeros((9, 1), np.float32)
+    restate.pts_on_pts(x1, r1, s1, x1, r1, a, b, core=core)
+    assert not a.any() and b[0, 0] == 0 and b[4, 0] == 0 and b[8, 0] == 0
+    assert b[1, 0] == -b[3, 0] and b[2, 0] == -b[6, 0] and b[5, 0] == -b[7, 0] and b[1, 0] != 0
+    # translation
+    xt = (x + np.float32(2.0)).astype(np.float32)
+    ut = np.zeros((3, n), np.float32)
+    restate.pts_on_pts(xt, r, s, xt, r, ut, None, core=core)
+    assert np.max(np.abs(ut - u)) <= 2e-5 * np.max(np.abs(u))
