@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define O3D_CUDA_ABI_VERSION 2
+#define O3D_CUDA_ABI_VERSION 3
 
 enum {
   O3D_OK = 0,
@@ -110,19 +110,26 @@ int o3d_cuda_pan_on_pan_coeff(o3d_ctx* ctx, int64_t snn, const float* snx, const
 
 /* ---- device-pointer entry points (arrays already resident in HBM on the context's device 0) ------- */
 /* `stream` is a cudaStream_t passed as an opaque pointer (NULL = the legacy default stream). All calls
- * are asynchronous with respect to the host. */
+ * are asynchronous with respect to the host. ONE stream per context at a time: the launches share the context's
+ * scratch (radius-range block, stream-K workspace), so calls on different streams must be ordered by the caller, or use
+ * one context per stream. The stream must belong to the context's first device, which must be the CURRENT device of the
+ * calling thread (O3D_ERR_INVALID otherwise - the library does not switch devices under a caller that owns them). */
 
 /* Number of 32-byte records the packed source stream holds for ns sources (padded to whole tiles). */
 int64_t o3d_cuda_packed_records(int64_t ns);
 
 /* The launch shape the library picks for particles -> points on a device with sm_count SMs - host arithmetic only, no
- * device needed (capi.cu: pp_shape): CTAs along the targets (128 threads x 2 targets with gradients, x 4 without),
- * source slices (gridDim.y; > 1 when the targets alone would leave much of the last wave of resident CTAs empty - the
- * slices meet in FP64 slabs of workspace_bytes, summed in slice order), and the fraction of the launch's waves that is
- * occupied. Any output pointer may be NULL. The reference's counterpart is the static OpenMP schedule over targets
- * (src/Influence.h:281,405,445). */
-int o3d_cuda_plan_pts_on_pts(int sm_count, int64_t ns, int64_t nt, int want_grad, int64_t* grid_x, int* nsplit,
-                             double* wave_efficiency, int64_t* workspace_bytes);
+ * device needed (capi.cu: pp_shape). The kernels run as PERSISTENT CTAs (128 threads x 2 targets with gradients, x 4
+ * without) over a static stream-K partition: the (target block, source tile) units, block-major, are dealt out in equal
+ * contiguous shares to `grid` = min(units, 3 x sm_count) CTAs. `split_blocks` target blocks are shared by more than one
+ * CTA; their FP64 partial sums meet in a fixed workspace of `workspace_bytes` and are added in unit order. `balance` =
+ * mean / max tiles per CTA (1 = perfectly even). Any output pointer may be NULL. The reference's counterpart is the
+ * static OpenMP schedule over targets (src/Influence.h:281,405,445). */
+int o3d_cuda_plan_pts_on_pts(int sm_count, int64_t ns, int64_t nt, int want_grad, int64_t* grid, int* split_blocks,
+                             double* balance, int64_t* workspace_bytes);
+/* Host replay of that launch's bookkeeping (every CTA's segments, every workspace slot, every fix-up) - 0 when each unit
+ * is consumed exactly once and each target block is finished exactly once; otherwise the number of the failed check. */
+int o3d_cuda_plan_check(int sm_count, int64_t ns, int64_t nt, int want_grad);
 /* SoA sources -> packed record stream `packed` (device memory, nrec * 32 bytes). nrec = 0 means
  * o3d_cuda_packed_records(ns); a larger whole number of tiles is filled up with zero-strength records
  * (ranks of a sharded job all contribute equally sized streams to one all-gather). */
@@ -193,6 +200,29 @@ int o3d_cuda_set_graphs(o3d_ctx* ctx, int on);
 int o3d_cuda_particles_graph_active(const o3d_particles* p);
 /* sqrt(max |s|^2) (ElementBase::get_max_str, src/ElementBase.h:339-351) and max elongation (src/Points.h:523-532). */
 int o3d_cuda_particles_stats(o3d_ctx* ctx, o3d_particles* p, float* max_str, float* max_elong);
+
+
+/* ---- status-file quantities and writer (src/StatusFile.cpp, src/Simulation.cpp:851-924) ------------ */
+/* Total circulation sum_i s_i (ElementBase::get_total_circ, src/ElementBase.h:354-378) and linear impulse
+ * sum_i (s1 x2 - s2 x1, s2 x0 - s0 x2, s0 x1 - s1 x0) (Points::get_total_impulse, src/Points.h:547-563) of a resident
+ * collection, reduced on the device(s): per-particle terms in float as the reference forms them, sums in FP64 over a
+ * fixed-shape tree (deterministic). circ, impulse: 3 doubles each, either may be NULL. */
+int o3d_cuda_particles_totals(o3d_ctx* ctx, o3d_particles* p, double* circ, double* impulse);
+
+/* The line-per-step status file: StatusFile's behaviour byte for byte (header of value names per data set, "# " and
+ * spaces for .dat, commas for csv != 0, values printed as by operator<<, an empty line between data sets, append mode).
+ * Host I/O only - these five need no device. append_*: name NULL = StatusFile's anonymous "float" / "int". */
+typedef struct o3d_status o3d_status;
+int o3d_cuda_status_open(const char* path, int csv, o3d_status** out);
+void o3d_cuda_status_close(o3d_status* st);
+int o3d_cuda_status_reset_sim(o3d_status* st);                                   /* StatusFile::reset_sim */
+int o3d_cuda_status_append_float(o3d_status* st, const char* name, float value);  /* StatusFile::append_value */
+int o3d_cuda_status_append_int(o3d_status* st, const char* name, int value);
+int o3d_cuda_status_write_line(o3d_status* st);                                   /* StatusFile::write_line */
+/* Simulation::dump_stats_to_status for a system that is one resident particle collection: appends time, Nv, gx gy gz
+ * (o3d_cuda_particles_totals) and fx fy fz (calculate_simple_forces: the one-sided time difference of the total impulse,
+ * whose previous sample the status object keeps; time < 0.1 dt restarts it) and writes the line. */
+int o3d_cuda_particles_write_status(o3d_ctx* ctx, o3d_particles* p, o3d_status* st, double time, double dt);
 
 
 /* ---- matrix-free BEM operator ----------------------------------------------------------- */

@@ -44,6 +44,14 @@ SYMBOLS = {
     "o3d_cuda_particles_find_vels": (c_int, [c_void_p, c_void_p, POINTER(c_double), c_int, POINTER(c_double)]),
     "o3d_cuda_particles_advect": (c_int, [c_void_p, c_void_p, c_int, c_double, c_double, POINTER(c_double), c_int, POINTER(c_double)]),
     "o3d_cuda_particles_stats": (c_int, [c_void_p, c_void_p, POINTER(ctypes.c_float), POINTER(ctypes.c_float)]),
+    "o3d_cuda_particles_totals": (c_int, [c_void_p, c_void_p, POINTER(c_double), POINTER(c_double)]),
+    "o3d_cuda_status_open": (c_int, [c_char_p, c_int, POINTER(c_void_p)]),
+    "o3d_cuda_status_close": (None, [c_void_p]),
+    "o3d_cuda_status_reset_sim": (c_int, [c_void_p]),
+    "o3d_cuda_status_append_float": (c_int, [c_void_p, c_char_p, ctypes.c_float]),
+    "o3d_cuda_status_append_int": (c_int, [c_void_p, c_char_p, c_int]),
+    "o3d_cuda_status_write_line": (c_int, [c_void_p]),
+    "o3d_cuda_particles_write_status": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double]),
     "o3d_cuda_bem_op_create": (c_int, [c_void_p, c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P,
                                        c_int64, _P, _P, _P, c_int64, _P, _P, _P, _P, _P, c_int, POINTER(c_void_p)]),
     "o3d_cuda_bem_op_apply": (c_int, [c_void_p, c_void_p, _P, _P, POINTER(c_double)]),
@@ -58,6 +66,7 @@ SYMBOLS = {
     "o3d_cuda_set_tuned_kernels": (c_int, [c_void_p, c_int]),
     "o3d_cuda_tuned_kernels": (c_int, [c_void_p]),
     "o3d_cuda_plan_pts_on_pts": (c_int, [c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "o3d_cuda_plan_check": (c_int, [c_int, c_int64, c_int64, c_int]),
     "o3d_cuda_set_core_func": (c_int, [c_void_p, c_int]),
     "o3d_cuda_core_func": (c_int, [c_void_p]),
     "o3d_cuda_set_profiling": (c_int, [c_void_p, c_int]),

@@ -13,12 +13,20 @@
 //
 // Design:
 //   * each thread owns T targets in registers; every source record is read once from shared memory
-//     (one broadcast LDS.128 pair per warp) and applied to all T targets: 40 FP32-pipe instructions
-//     + 1 MUFU.RSQ per interaction for velocity+gradient, 21 + 1 for velocity only;
+//     (one broadcast LDS.128 per warp) and applied to all T targets, two sources per packed FP32
+//     instruction: 35 FFMA2/FMUL2/FADD2 + 1 MUFU.RSQ per interaction for velocity+gradient;
 //   * the antisymmetric +/- w_k r3 part of the gradient is accumulated once as A = sum w r3 (3 FMA)
 //     and applied in the epilogue instead of 6 FMA per interaction;
 //   * source tiles (512 records = 16 KB, contiguous) arrive by cp.async.bulk (TMA, SASS UBLKCP)
 //     into a 2-deep mbarrier ring - no thread spends registers or issue slots on the copy;
+//   * PERSISTENT CTAs over a static stream-K partition (PPPlan below): the work is the nblocks x ntiles
+//     grid of (target block, source tile) units in block-major order and CTA c of the P resident CTAs
+//     owns units [W c / P, W (c+1) / P). Every CTA streams the same number of tiles (+-1) whatever the
+//     target count - no last-wave quantisation, no source split - and the TMA ring runs straight
+//     through target-block boundaries. A target block that lies wholly inside one CTA's range is
+//     finished in place; the (at most P-1) blocks cut by a range boundary leave FP64 partial sums in a
+//     fixed-size workspace (2 slots per CTA) which pp_fixup_kernel adds in unit order: deterministic,
+//     no atomics, a few MB of traffic whatever the problem size;
 //   * sums are FP32 FMA chains inside one tile, promoted to FP64 once per tile (B200 keeps a full FP64
 //     pipe; 12 DADD per 512 interactions), mirroring the reference's float-kernel/double-accumulator
 //     scheme (src/Simulation.h:41-47) to ~1e-7 relative;
@@ -57,6 +65,10 @@
 #ifndef O3D_PP_UNROLL_GRAD
 #define O3D_PP_UNROLL_GRAD 4   // source pairs per trip of the packed inner loop, velocity+gradient kernel
 #endif
+#ifndef O3D_PP_STAGE
+#define O3D_PP_STAGE 0    // how a source tile reaches shared memory. 0 (product): one cp.async.bulk (TMA) per tile by one elected
+#endif                    // thread + mbarrier; 1: cp.async 16 B x 8 per thread; 2: LDG.128 -> STS.128 through registers. 1 and 2 exist
+                          // for microbench/kbench only (make kbench_stage): DESIGN.md section 7 "staging" rows
 #ifndef O3D_PP_UNROLL_VEL
 #define O3D_PP_UNROLL_VEL 2    // ... velocity-only kernel
 #endif
@@ -81,44 +93,6 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 
 template <bool GRAD> struct PPAcc { static constexpr int N = GRAD ? 15 : 3; };
 
-// One source record (a = x y z sr^2, b = wx wy wz -) on one target. acc layout:
-//   [0..2] u v w | [3..11] G[3j+i] = sum d_j * bbb*c_i | [12..14] A = sum w * r3
-template <bool GRAD>
-__device__ __forceinline__ void pp_interact(const float4 a, const float4 b, const float tx, const float ty,
-                                            const float tz, const float tr2, float (&acc)[PPAcc<GRAD>::N]) {
-  const float dx = tx - a.x, dy = ty - a.y, dz = tz - a.z;
-  const float r2 = a.w + tr2;
-  const float d2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, r2)));
-  const float top = fmaf(1.5f, r2, d2);
-  const float rs = rsqrt_approx(d2);
-  const float rs2 = rs * rs;
-  const float rs4 = rs2 * rs2;
-  const float dn5 = rs4 * rs;
-  const float r3 = top * dn5;
-  float cx = fmaf(dz, b.y, -(dy * b.z));
-  float cy = fmaf(dx, b.z, -(dz * b.x));
-  float cz = fmaf(dy, b.x, -(dx * b.y));
-  acc[0] = fmaf(r3, cx, acc[0]);
-  acc[1] = fmaf(r3, cy, acc[1]);
-  acc[2] = fmaf(r3, cz, acc[2]);
-  if constexpr (GRAD) {
-    const float bbb = dn5 * fmaf(-5.0f, top * rs2, 2.0f);
-    cx *= bbb; cy *= bbb; cz *= bbb;
-    acc[3]  = fmaf(dx, cx, acc[3]);
-    acc[4]  = fmaf(dx, cy, acc[4]);
-    acc[5]  = fmaf(dx, cz, acc[5]);
-    acc[6]  = fmaf(dy, cx, acc[6]);
-    acc[7]  = fmaf(dy, cy, acc[7]);
-    acc[8]  = fmaf(dy, cz, acc[8]);
-    acc[9]  = fmaf(dz, cx, acc[9]);
-    acc[10] = fmaf(dz, cy, acc[10]);
-    acc[11] = fmaf(dz, cz, acc[11]);
-    acc[12] = fmaf(b.x, r3, acc[12]);
-    acc[13] = fmaf(b.y, r3, acc[13]);
-    acc[14] = fmaf(b.z, r3, acc[14]);
-  }
-}
-
 // Fold the per-tile FP32 partials into the 3 (or 12) FP64 running sums and clear them.
 template <bool GRAD>
 __device__ __forceinline__ void pp_promote(float (&acc)[PPAcc<GRAD>::N], double (&sum)[GRAD ? 12 : 3]) {
@@ -139,117 +113,192 @@ __device__ __forceinline__ void pp_promote(float (&acc)[PPAcc<GRAD>::N], double 
   for (int k = 0; k < PPAcc<GRAD>::N; ++k) acc[k] = 0.0f;
 }
 
+
+// ---- the static stream-K partition -----------------------------------------------------------------------------
+// Units are (target block b, source tile k), numbered u = b * ntiles + k. CTA c owns [begin(c), begin(c+1)).
+// Host and device use the same arithmetic (capi.cu: launch shape, o3d_cuda_plan_pts_on_pts; the kernels; pp_fixup_kernel).
+struct PPPlan {
+  int64_t W;      // units = nblocks * ntiles
+  int P;          // CTAs (<= W: no CTA is empty)
+  int ntiles;
+  __host__ __device__ int64_t begin(int c) const { return W * (int64_t)c / P; }
+};
+// A CTA's range is cut into segments at target-block boundaries. Only its FIRST and its LAST segment can cover a block
+// partially; a partial first segment leaves its sums in slot 0 of the CTA's workspace pair, a partial last segment that is
+// not also the first in slot 1.
+constexpr int kPPSlots = 2;
+
 struct PPArgs {
   const float4* src;      // packed source stream, 2 float4 per source, padded to whole tiles
-  int tile_begin;         // first tile of this launch's source range (per blockIdx.y slice: see split)
   int ntiles;             // tiles in the whole stream
-  int nsplit;             // source slices = gridDim.y
+  int nblocks;            // target blocks of BLOCK * T targets
   int64_t nt;             // targets
   const float* tx; const float* ty; const float* tz;
   const float* tr;        // nullptr => singular targets (tr = 0)
   float* tu; float* tv; float* tw;   // velocity, read-modify-write
   float* tug;             // 9 rows of stride tug_stride, or nullptr
   int64_t tug_stride;
-  double* partial;        // nsplit > 1: [nsplit][12 or 3][nt] FP64 workspace, one slab per source slice
-  float sign;             // +1, or -1 for the points->panels convention
+  double* partial;        // [gridDim.x][kPPSlots][12 or 3][BLOCK * T] FP64: sums of the target blocks this CTA shares
+  float sign;             // +1
   const uint32_t* radius_range;  // pp_scan_kernel output, or nullptr: no uniform-radius fast path
 };
 
-// Scalar-FFMA kernel: T register-blocked targets per thread.
-template <int T, bool GRAD, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) pp_kernel(const PPArgs p) {
-  constexpr int NA = PPAcc<GRAD>::N;
-  constexpr int NS = GRAD ? 12 : 3;
-  __shared__ alignas(128) float4 tile[2][kTile * 2];
-  __shared__ alignas(8) uint64_t full[2];
+// The walk of one persistent CTA through its share. Everything here is a function of blockIdx and the kernel parameters
+// only, so ptxas keeps it in UNIFORM registers: the inner loops address shared memory as [UR + imm] and branch on uniform
+// predicates exactly as a one-block-per-CTA kernel would (values re-read from shared memory would count as divergent and move
+// the loop counters and LDS addresses into the vector register file, whose read bandwidth is what bounds the hot loop).
+struct PPWalk {
+  int nk;           // tiles in the CTA's share
+  int b0, kt0;      // target block and source tile of its first unit
+  int kring;        // tiles consumed so far; tile kring lives in ring buffer kring & 1
+  int tnext;        // source tile the next refill fetches (wraps from the last tile of a block to tile 0 of the next)
+};
+__device__ __forceinline__ int pp_wrap(int t, int ntiles) { return t + 1 == ntiles ? 0 : t + 1; }
 
-  // this CTA's slice of the source stream
-  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
-  const int k0 = blockIdx.y * per;
-  const int k1 = min(p.ntiles, k0 + per);
-  const int nk = k1 - k0;
+#if O3D_PP_STAGE != 0
+// microbench-only staging variants: every thread moves its 128-byte share of the tile (8 x 16 B, coalesced per 16-byte column)
+template <int BLOCK>
+__device__ __forceinline__ void pp_stage_copy(float4* dst, const float4* __restrict__ src) {
+#if O3D_PP_STAGE == 1
+#pragma unroll
+  for (int q = 0; q < kTile * 2 / BLOCK; ++q)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + q * BLOCK + threadIdx.x)), "l"(src + q * BLOCK + threadIdx.x) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#else
+  float4 v[kTile * 2 / BLOCK];
+#pragma unroll
+  for (int q = 0; q < kTile * 2 / BLOCK; ++q) v[q] = __ldg(src + q * BLOCK + threadIdx.x);
+#pragma unroll
+  for (int q = 0; q < kTile * 2 / BLOCK; ++q) dst[q * BLOCK + threadIdx.x] = v[q];
+#endif
+}
+#endif
 
+// fetch source tile w.tnext into ring buffer `buf` (barrier `bar`) and advance
+template <int BLOCK>
+__device__ __forceinline__ void pp_ring_fetch(const PPArgs& p, PPWalk& w, float4* buf, uint64_t* bar) {
+#if O3D_PP_STAGE == 0
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, kTileBytes);
+    bulk_g2s(buf, p.src + (size_t)w.tnext * (kTile * 2), kTileBytes, bar);
+  }
+#else
+  pp_stage_copy<BLOCK>(buf, p.src + (size_t)w.tnext * (kTile * 2));
+#endif
+  w.tnext = pp_wrap(w.tnext, p.ntiles);
+}
+
+template <int BLOCK>
+__device__ __forceinline__ PPWalk pp_ring_start(const PPArgs& p, float4 (&tile)[2][kTile * 2], uint64_t (&full)[2]) {
+  const PPPlan plan{(int64_t)p.nblocks * p.ntiles, (int)gridDim.x, p.ntiles};
+  const int64_t u0 = plan.begin(blockIdx.x), u1 = plan.begin(blockIdx.x + 1);
+  // (the 64-bit divisions run as a subroutine on the vector datapath, after which ptxas no longer knows the quotients to be
+  // warp-uniform; a warp reduction - REDUX writes a uniform register - hands them back as provably uniform values)
+  const int b0 = (int)(u0 / p.ntiles);
+  PPWalk w;
+  w.nk = __reduce_max_sync(0xffffffffu, (int)(u1 - u0));
+  w.b0 = __reduce_max_sync(0xffffffffu, b0);
+  w.kt0 = __reduce_max_sync(0xffffffffu, (int)(u0 - (int64_t)b0 * p.ntiles));
+  w.kring = 0;
+  w.tnext = w.kt0;
+#if O3D_PP_STAGE == 0
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+#endif
 #pragma unroll
-    for (int s = 0; s < 2; ++s)
-      if (s < nk) {
-        mbar_expect_tx(&full[s], kTileBytes);
-        bulk_g2s(tile[s], p.src + (size_t)(k0 + s) * (kTile * 2), kTileBytes, &full[s]);
-      }
+  for (int s = 0; s < 2; ++s) {
+    if (s < w.nk) pp_ring_fetch<BLOCK>(p, w, tile[s], &full[s]);
+#if O3D_PP_STAGE == 1
+    else asm volatile("cp.async.commit_group;" ::: "memory");   // keep the group count in step with the tile count
+#endif
   }
-
-  float tx[T], ty[T], tz[T], tr2[T];
-  const int64_t base = (int64_t)blockIdx.x * (BLOCK * T) + threadIdx.x;
+  return w;
+}
+// tile w.kring of the CTA's share has landed in its ring buffer
+__device__ __forceinline__ void pp_ring_wait(uint64_t (&full)[2], const int kring) {
+#if O3D_PP_STAGE == 0
+  mbar_wait(&full[kring & 1], (kring >> 1) & 1);
+#else
+#if O3D_PP_STAGE == 1
+  asm volatile("cp.async.wait_group 1;" ::: "memory");   // all but the newest group
+#endif
+  __syncthreads();
+#endif
+}
+// every warp is done with the buffer of tile w.kring: refill it with the tile two ahead, step to the next tile
+template <int BLOCK>
+__device__ __forceinline__ void pp_ring_refill(const PPArgs& p, PPWalk& w, float4* buf, uint64_t* bar) {
+  __syncthreads();
+  if (w.kring + 2 < w.nk) pp_ring_fetch<BLOCK>(p, w, buf, bar);
+#if O3D_PP_STAGE == 1
+  else asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+  ++w.kring;
+}
+// Epilogue of one segment for one thread's T targets: a whole block is finished in place, a partial one parks its sums.
+template <int T, bool GRAD, int BLOCK>
+__device__ __forceinline__ void pp_store(const PPArgs& p, const int b, const bool whole, const int slot,
+                                         const double (&sum)[T][GRAD ? 12 : 3]) {
+  constexpr int NS = GRAD ? 12 : 3;
+  constexpr int PER = BLOCK * T;
+  if (!whole) {
+    double* w = p.partial + ((size_t)blockIdx.x * kPPSlots + slot) * (NS * PER) + threadIdx.x;
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
-    tx[t] = p.tx[i]; ty[t] = p.ty[i]; tz[t] = p.tz[i];
-    const float r = p.tr ? p.tr[i] : 0.0f;
-    tr2[t] = r * r;
-  }
-
-  float acc[T][NA];
-  double sum[T][NS];
+    for (int t = 0; t < T; ++t) {
 #pragma unroll
-  for (int t = 0; t < T; ++t) {
-#pragma unroll
-    for (int k = 0; k < NA; ++k) acc[t][k] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
-  }
-
-  for (int k = 0; k < nk; ++k) {
-    const int buf = k & 1;
-    mbar_wait(&full[buf], (k >> 1) & 1);
-    const float4* __restrict__ s = tile[buf];
-#pragma unroll 4
-    for (int j = 0; j < kTile; ++j) {
-      const float4 a = s[2 * j], b = s[2 * j + 1];
-#pragma unroll
-      for (int t = 0; t < T; ++t) pp_interact<GRAD>(a, b, tx[t], ty[t], tz[t], tr2[t], acc[t]);
+      for (int k = 0; k < NS; ++k) w[k * PER + t * BLOCK] = sum[t][k];
     }
-#pragma unroll
-    for (int t = 0; t < T; ++t) pp_promote<GRAD>(acc[t], sum[t]);
-    __syncthreads();  // every warp is done with tile[buf]; safe to refill
-    if (threadIdx.x == 0 && k + 2 < nk) {
-      mbar_expect_tx(&full[buf], kTileBytes);
-      bulk_g2s(tile[buf], p.src + (size_t)(k0 + k + 2) * (kTile * 2), kTileBytes, &full[buf]);
-    }
+    return;
   }
-
+  const int64_t base = (int64_t)b * PER + threadIdx.x;
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int64_t i = base + (int64_t)t * BLOCK;
     if (i >= p.nt) continue;
-    if (p.nsplit > 1) {
-      // slice blockIdx.y owns its own [NS][nt] slab: plain stores, summed in slice order by
-      // pp_finish_kernel, so the result does not depend on CTA scheduling
-      double* slab = p.partial + (size_t)blockIdx.y * NS * p.nt;
+    const double sg = (double)p.sign;
+    p.tu[i] = (float)((double)p.tu[i] + sg * sum[t][0]);
+    p.tv[i] = (float)((double)p.tv[i] + sg * sum[t][1]);
+    p.tw[i] = (float)((double)p.tw[i] + sg * sum[t][2]);
+    if constexpr (GRAD) {
 #pragma unroll
-      for (int k = 0; k < NS; ++k) slab[(size_t)k * p.nt + i] = sum[t][k];
-    } else {
-      const double sg = (double)p.sign;
-      p.tu[i] = (float)((double)p.tu[i] + sg * sum[t][0]);
-      p.tv[i] = (float)((double)p.tv[i] + sg * sum[t][1]);
-      p.tw[i] = (float)((double)p.tw[i] + sg * sum[t][2]);
-      if constexpr (GRAD) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          float* g = p.tug + (size_t)k * p.tug_stride + i;
-          *g = (float)((double)*g + sum[t][3 + k]);
-        }
+      for (int k = 0; k < 9; ++k) {
+        float* g = p.tug + (size_t)k * p.tug_stride + i;
+        *g = (float)((double)*g + sg * sum[t][3 + k]);
       }
     }
   }
 }
 
-// nsplit > 1 epilogue: out[i] = float(double(out[i]) + sign * sum over slices (in slice order) of partial).
+// One CTA per range boundary j = blockIdx.x + 1 of the launch that just ran with P CTAs: if that boundary is the first one
+// inside its target block, add the block's pieces in unit order - the last segment of CTA j-1, then the first segments of
+// CTAs j, j+1, ... that start inside the block - and finish the block: out = float(double(out) + sign * sum).
+// blockDim.x = targets per block (BLOCK * T of the main kernel).
+__global__ void pp_fixup_kernel(const int nrows, const PPPlan plan, const int64_t nt, const double* __restrict__ partial,
+                                float* tu, float* tv, float* tw, float* tug, const int64_t tug_stride, const float sign) {
+  const int j = blockIdx.x + 1;
+  const int64_t cut = plan.begin(j);
+  const int64_t b = cut / plan.ntiles, start = b * plan.ntiles, end = start + plan.ntiles;
+  if (cut == start) return;                 // the boundary coincides with a block edge: nothing is shared here
+  const int64_t prev = plan.begin(j - 1);
+  if (prev > start) return;                 // an earlier boundary inside this block owns it
+  const int per = blockDim.x;
+  const int64_t i = b * per + threadIdx.x;
+  if (i >= nt) return;
+  const size_t slot_elems = (size_t)nrows * per;
+  for (int k = 0; k < nrows; ++k) {
+    double acc = partial[((size_t)(j - 1) * kPPSlots + (prev == start ? 0 : 1)) * slot_elems + (size_t)k * per + threadIdx.x];
+    for (int c = j; c < plan.P && plan.begin(c) < end; ++c)
+      acc += partial[((size_t)c * kPPSlots) * slot_elems + (size_t)k * per + threadIdx.x];
+    float* o = k == 0 ? tu + i : k == 1 ? tv + i : k == 2 ? tw + i : tug + (size_t)(k - 3) * tug_stride + i;
+    *o = (float)((double)*o + (double)sign * acc);
+  }
+}
+
+// nsplit-slab epilogue of the PANEL kernels (csrc/biot_panel.cuh): out[i] = float(double(out[i]) + sign * sum over slices (in slice order) of partial).
 __global__ void pp_finish_kernel(int nrows, int nsplit, int64_t nt, const double* partial, float* tu, float* tv, float* tw,
                                  float* tug, int64_t tug_stride, float sign) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -260,21 +309,6 @@ __global__ void pp_finish_kernel(int nrows, int nsplit, int64_t nt, const double
     float* o = k == 0 ? tu + i : k == 1 ? tv + i : k == 2 ? tw + i : tug + (size_t)(k - 3) * tug_stride + i;
     *o = (float)((double)*o + (double)sign * acc);
   }
-}
-
-// SoA (the reference's Points layout) -> packed record stream, with zero-strength padding records.
-__global__ void pp_pack_kernel(int64_t ns, int64_t ns_pad, const float* sx, const float* sy, const float* sz,
-                               const float* sr, const float* wx, const float* wy, const float* wz, float4* out) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= ns_pad) return;
-  float4 a = make_float4(0.f, 0.f, 0.f, 1.0f), b = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (j < ns) {
-    const float r = sr ? sr[j] : 0.0f;
-    a = make_float4(sx[j], sy[j], sz[j], r * r);
-    b = make_float4(wx[j], wy[j], wz[j], 0.f);
-  }
-  out[2 * j] = a;
-  out[2 * j + 1] = b;
 }
 
 // =============================================================================================
@@ -405,24 +439,41 @@ __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, c
   }
 }
 
-// One CTA's pass over its source tiles; the UNI flag is warp-uniform, so the two instantiations are two
-// straight-line copies of the loop selected once per kernel.
+// The whole share of one persistent CTA: ONE loop over its tiles (the nest is two deep - tiles, source pairs - like a
+// one-block-per-CTA kernel's, which is the shape ptxas keeps the inner loop's counter and LDS addresses in uniform registers
+// for); the target block changes inside that loop, at the tiles where a segment starts / ends. The UNI flag is warp-uniform,
+// so the two instantiations are two straight-line copies of the loop selected once per kernel.
 template <int T, bool GRAD, bool UNI, int BLOCK>
-__device__ __forceinline__ void pp2_tiles(const PPArgs& p, const int k0, const int nk, float4 (&tile)[2][kTile * 2],
-                                          uint64_t (&full)[2], const float2 (&tx)[T], const float2 (&ty)[T],
-                                          const float2 (&tz)[T], const float2 (&tr2)[T],
-                                          double (&sum)[T][GRAD ? 12 : 3]) {
+__device__ __forceinline__ void pp2_walk(const PPArgs& p, PPWalk& w, float4 (&tile)[2][kTile * 2], uint64_t (&full)[2], const float r2u) {
   constexpr int NA = PPAcc<GRAD>::N;
+  constexpr int NS = GRAD ? 12 : 3;
   constexpr int U = GRAD ? kPPUnrollGrad : kPPUnrollVel;
+  float2 tx[T], ty[T], tz[T], tr2[T];
+  double sum[T][NS];
   float2 acc[T][NA];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
 #pragma unroll
     for (int k = 0; k < NA; ++k) acc[t][k] = f2(0.f, 0.f);
   }
-  for (int k = 0; k < nk; ++k) {
-    const int buf = k & 1;
-    mbar_wait(&full[buf], (k >> 1) & 1);
+  int b = w.b0, kt = w.kt0;                // target block and source tile of the current unit
+  bool seg_first = true;                   // the current segment is the CTA's first
+  bool fresh = true;                       // the current tile starts a segment
+  for (; w.kring < w.nk;) {
+    if (fresh) {
+      const int64_t base = (int64_t)b * (BLOCK * T) + threadIdx.x;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
+        tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
+        const float r = p.tr ? p.tr[i] : 0.0f;
+        tr2[t] = UNI ? f2(r2u, r2u) : f2(r * r, r * r);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
+      }
+    }
+    const int buf = w.kring & 1;
+    pp_ring_wait(full, w.kring);
     const float4* __restrict__ s = tile[buf];
 #pragma unroll(U)
     for (int j = 0; j < kTile / 2; ++j) {
@@ -449,39 +500,26 @@ __device__ __forceinline__ void pp2_tiles(const PPArgs& p, const int k0, const i
 #endif
       pp_promote<GRAD>(h, sum[t]);
     }
-    __syncthreads();  // every warp is done with tile[buf]; safe to refill
-    if (threadIdx.x == 0 && k + 2 < nk) {
-      mbar_expect_tx(&full[buf], kTileBytes);
-      bulk_g2s(tile[buf], p.src + (size_t)(k0 + k + 2) * (kTile * 2), kTileBytes, &full[buf]);
+    pp_ring_refill<BLOCK>(p, w, tile[buf], &full[buf]);       // ++w.kring
+    ++kt;
+    fresh = kt == p.ntiles || w.kring == w.nk;                // the segment ends with this tile
+    if (fresh) {
+      // whole block <=> the segment ran from tile 0 to the last tile: then kt == ntiles and (not the first segment or kt0 == 0)
+      const bool whole = kt == p.ntiles && (!seg_first || w.kt0 == 0);
+      pp_store<T, GRAD, BLOCK>(p, b, whole, seg_first ? 0 : 1, sum);
+      seg_first = false;
+      kt = 0;
+      ++b;
     }
   }
 }
 
 template <int T, bool GRAD, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) pp2_kernel(const PPArgs p) {
-  constexpr int NS = GRAD ? 12 : 3;
   __shared__ alignas(128) float4 tile[2][kTile * 2];
   __shared__ alignas(8) uint64_t full[2];
 
-  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
-  const int k0 = blockIdx.y * per;
-  const int k1 = min(p.ntiles, k0 + per);
-  const int nk = k1 - k0;
-
-  if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-      if (s < nk) {
-        mbar_expect_tx(&full[s], kTileBytes);
-        bulk_g2s(tile[s], p.src + (size_t)(k0 + s) * (kTile * 2), kTileBytes, &full[s]);
-      }
-  }
+  PPWalk w = pp_ring_start<BLOCK>(p, tile, full);
 
   // radius scan (pp_scan_kernel): [0] ~min, [1] max of sr^2 bit patterns over sources that carry strength,
   // [2] ~min, [3] max of tr bit patterns. Uniform <=> both ranges collapse and the constant r2 is positive.
@@ -493,51 +531,8 @@ __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) pp2_kernel(const PPArgs p)
     r2u = __fadd_rn(__uint_as_float(s0), __fmul_rn(tr, tr));   // sr*sr + tr*tr, the reference's r2 (src/CoreFunc.h:267)
     uni = s0 == s1 && (!p.tr || t0 == t1) && r2u > 0.0f && s0 != 0xffffffffu;
   }
-
-  float2 tx[T], ty[T], tz[T], tr2[T];
-  const int64_t base = (int64_t)blockIdx.x * (BLOCK * T) + threadIdx.x;
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
-    tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
-    const float r = p.tr ? p.tr[i] : 0.0f;
-    tr2[t] = uni ? f2(r2u, r2u) : f2(r * r, r * r);
-  }
-
-  double sum[T][NS];
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-#pragma unroll
-    for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
-  }
-
-  if (uni) pp2_tiles<T, GRAD, true, BLOCK>(p, k0, nk, tile, full, tx, ty, tz, tr2, sum);
-  else     pp2_tiles<T, GRAD, false, BLOCK>(p, k0, nk, tile, full, tx, ty, tz, tr2, sum);
-
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int64_t i = base + (int64_t)t * BLOCK;
-    if (i >= p.nt) continue;
-    if (p.nsplit > 1) {
-      // slice blockIdx.y owns its own [NS][nt] slab: plain stores, summed in slice order by
-      // pp_finish_kernel, so the result does not depend on CTA scheduling
-      double* slab = p.partial + (size_t)blockIdx.y * NS * p.nt;
-#pragma unroll
-      for (int k = 0; k < NS; ++k) slab[(size_t)k * p.nt + i] = sum[t][k];
-    } else {
-      const double sg = (double)p.sign;
-      p.tu[i] = (float)((double)p.tu[i] + sg * sum[t][0]);
-      p.tv[i] = (float)((double)p.tv[i] + sg * sum[t][1]);
-      p.tw[i] = (float)((double)p.tw[i] + sg * sum[t][2]);
-      if constexpr (GRAD) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          float* g = p.tug + (size_t)k * p.tug_stride + i;
-          *g = (float)((double)*g + sum[t][3 + k]);
-        }
-      }
-    }
-  }
+  if (uni) pp2_walk<T, GRAD, true, BLOCK>(p, w, tile, full, r2u);
+  else     pp2_walk<T, GRAD, false, BLOCK>(p, w, tile, full, r2u);
 }
 
 // Radius ranges for the uniform-radius fast path of pp2_kernel. range[0..1]: min/max of the sr^2 bit patterns

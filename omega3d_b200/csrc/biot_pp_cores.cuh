@@ -160,49 +160,34 @@ __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) ppc_kernel(const PPArgs p)
   __shared__ alignas(128) float4 tile[2][kTile * 2];
   __shared__ alignas(8) uint64_t full[2];
 
-  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
-  const int k0 = blockIdx.y * per;
-  const int k1 = min(p.ntiles, k0 + per);
-  const int nk = k1 - k0;
-
-  if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-      if (s < nk) {
-        mbar_expect_tx(&full[s], kTileBytes);
-        bulk_g2s(tile[s], p.src + (size_t)(k0 + s) * (kTile * 2), kTileBytes, &full[s]);
-      }
-  }
+  // persistent CTA: one loop over the tiles of its share, the target block changing at segment boundaries (pp2_walk, biot_pp.cuh)
+  PPWalk w = pp_ring_start<BLOCK>(p, tile, full);
 
   float2 tx[T], ty[T], tz[T], tt[T];
-  const int64_t base = (int64_t)blockIdx.x * (BLOCK * T) + threadIdx.x;
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
-    tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
-    const float term = core_radius_term(CORE, p.tr ? p.tr[i] : 0.0f);
-    tt[t] = f2(term, term);
-  }
-
   double sum[T][NS];
   float2 acc[T][NA];
 #pragma unroll
   for (int t = 0; t < T; ++t) {
 #pragma unroll
-    for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
-#pragma unroll
     for (int k = 0; k < NA; ++k) acc[t][k] = f2(0.f, 0.f);
   }
-
-  for (int k = 0; k < nk; ++k) {
-    const int buf = k & 1;
-    mbar_wait(&full[buf], (k >> 1) & 1);
+  int b = w.b0, kt = w.kt0;
+  bool seg_first = true, fresh = true;
+  for (; w.kring < w.nk;) {
+    if (fresh) {
+      const int64_t base = (int64_t)b * (BLOCK * T) + threadIdx.x;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
+        tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
+        const float term = core_radius_term(CORE, p.tr ? p.tr[i] : 0.0f);
+        tt[t] = f2(term, term);
+#pragma unroll
+        for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
+      }
+    }
+    const int buf = w.kring & 1;
+    pp_ring_wait(full, w.kring);
     const float4* __restrict__ s = tile[buf];
 #pragma unroll(CORE == kCoreEXP ? 2 : GRAD ? kPPUnrollGrad : kPPUnrollVel)
     for (int j = 0; j < kTile / 2; ++j) {
@@ -218,33 +203,15 @@ __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) ppc_kernel(const PPArgs p)
       if constexpr (GRAD) h[11] = -(h[3] + h[7]);
       pp_promote<GRAD>(h, sum[t]);
     }
-    __syncthreads();  // every warp is done with tile[buf]; safe to refill
-    if (threadIdx.x == 0 && k + 2 < nk) {
-      mbar_expect_tx(&full[buf], kTileBytes);
-      bulk_g2s(tile[buf], p.src + (size_t)(k0 + k + 2) * (kTile * 2), kTileBytes, &full[buf]);
-    }
-  }
-
-#pragma unroll
-  for (int t = 0; t < T; ++t) {
-    const int64_t i = base + (int64_t)t * BLOCK;
-    if (i >= p.nt) continue;
-    if (p.nsplit > 1) {
-      double* slab = p.partial + (size_t)blockIdx.y * NS * p.nt;   // summed in slice order by pp_finish_kernel
-#pragma unroll
-      for (int k = 0; k < NS; ++k) slab[(size_t)k * p.nt + i] = sum[t][k];
-    } else {
-      const double sg = (double)p.sign;
-      p.tu[i] = (float)((double)p.tu[i] + sg * sum[t][0]);
-      p.tv[i] = (float)((double)p.tv[i] + sg * sum[t][1]);
-      p.tw[i] = (float)((double)p.tw[i] + sg * sum[t][2]);
-      if constexpr (GRAD) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          float* g = p.tug + (size_t)k * p.tug_stride + i;
-          *g = (float)((double)*g + sum[t][3 + k]);
-        }
-      }
+    pp_ring_refill<BLOCK>(p, w, tile[buf], &full[buf]);       // ++w.kring
+    ++kt;
+    fresh = kt == p.ntiles || w.kring == w.nk;
+    if (fresh) {
+      const bool whole = kt == p.ntiles && (!seg_first || w.kt0 == 0);
+      pp_store<T, GRAD, BLOCK>(p, b, whole, seg_first ? 0 : 1, sum);
+      seg_first = false;
+      kt = 0;
+      ++b;
     }
   }
 }

@@ -20,6 +20,7 @@
 #include "convect.cuh"
 #include "reflect.cuh"
 #include "vtu_writer.h"
+#include "status_writer.h"
 #include "pp2_tuned_cubin.h"   // generated (csrc/Makefile): pp_tuned.cu -> cubin -> tools/sass_patch.py -> byte array
 
 using namespace o3d;
@@ -84,7 +85,7 @@ struct Device {
   bool profile = false;
   bool tuned = true;                                         // launch pp2_kernel from the post-processed cubin (TunedKernels)
   int core = O3D_CORE_WL;                                    // core function of the particle kernels (o3d_cuda_set_core_func)
-  DevBuf src, packed, targ, out, work, geom, panels, tpanels, cnt, rng;
+  DevBuf src, packed, targ, out, work, ppwork, geom, panels, tpanels, cnt, rng;
   unsigned long long counts[2] = {0, 0};  // leaves, splits of the last panel call on this device
   // result of the last call on this device
   float kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
@@ -207,18 +208,23 @@ const TunedKernels& tuned_kernels() {
   return t;
 }
 
-// ---- launch-shape selection for particles -> points ------------------------------------------------
-// Product configuration (profiles/r01_*: packed FFMA2 kernel, 128-thread CTAs): vel+grad keeps 2 targets
-// per thread, velocity-only 4. When the target count cannot fill the GPU the source range is split over
-// gridDim.y and the per-slice FP64 partial sums meet in a workspace.
+// ---- launch shape for particles -> points ---------------------------------------------------------
+// Product configuration: packed FFMA2 kernels, 128-thread CTAs, 2 targets per thread with gradients, 4 without, as
+// PERSISTENT CTAs over a static stream-K partition of the (target block, source tile) units (csrc/biot_pp.cuh: PPPlan):
+// one CTA per resident slot of the GPU, every CTA the same number of tiles (+-1) whatever the target count.
 struct PPShape {
-  int nsplit;
-  dim3 grid;
-  size_t work_bytes;
+  int nblocks;        // target blocks of 128 * T targets
+  int grid;           // CTAs = min(units, resident slots)
+  int64_t units;      // nblocks * ntiles
+  int split_blocks;   // target blocks shared by more than one CTA (finished by pp_fixup_kernel)
 };
-// CTAs resident per SM (register-limited: 162 / 158 registers x 128 threads, lib/ptxas.log) for the two product kernels
-constexpr int kPPResidentGrad = 3;
-constexpr int kPPResidentVel = 3;
+// CTAs resident per SM (register-limited: <= 168 registers x 128 threads, lib/ptxas.log) for every product kernel
+constexpr int kPPResident = 3;
+// workspace of one launch: 2 slots per CTA x (12 rows x 256 targets | 3 rows x 512 targets) FP64 - a constant of the device
+constexpr size_t pp_workspace_bytes(int sm_count) {
+  return (size_t)sm_count * kPPResident * kPPSlots * 12 * (kPPBlock * kPPTgrad) * sizeof(double);
+}
+static_assert(12 * kPPTgrad >= 3 * kPPTvel, "the gradient kernel's slots are the larger ones");
 
 // pair-term flops of the reference's core functions, src/CoreFunc.h: flops_tv_grads / flops_tp_grads /
 // flops_tv_nograds / flops_tp_nograds for WL (:251-288), Rosenhead-Moore (:50-82), exponential (:202-237), Vatistas (:304-340)
@@ -234,55 +240,38 @@ double leaf_flops(int core, bool grad) { return (grad ? 79.0 : 29.0) + core_flop
 
 PPShape pp_shape(int sm_count, int64_t ntiles, int64_t nt, bool grad) {
   const int per_cta = kPPBlock * (grad ? kPPTgrad : kPPTvel);
-  const int64_t gx = (nt + per_cta - 1) / per_cta;
-  const int64_t slots = (int64_t)sm_count * (grad ? kPPResidentGrad : kPPResidentVel);
-  // Pick the source split that wastes the least of the last wave: efficiency = CTAs / (waves * slots).
-  // Large target counts (>= 64 waves: at most 0.8 % to gain) never split; tiny ones split until the GPU is covered twice.
-  // (The bound was 16 waves until the 2 M point of the size sweep showed 18.45 waves = 97.1 %: 2 M targets per GPU is also
-  // the 16 M / 8 GPU configuration. A split costs nsplit x 96 B per target of FP64 slab traffic: microseconds.)
-  int64_t best = 1;
-  if (gx < 64 * slots) {
-    double best_eff = 0.0;
-    const int64_t max_split = std::min<int64_t>(ntiles, 64);
-    for (int64_t sp = 1; sp <= max_split; ++sp) {
-      const int64_t ctas = gx * sp;
-      const int64_t waves = (ctas + slots - 1) / slots;
-      double eff = (double)ctas / (double)(waves * slots);
-      if (ctas >= 2 * slots) eff += 1e-3 * (1.0 / sp);  // among equals prefer fewer slices
-      if (eff > best_eff + 0.02) best_eff = eff, best = sp;
-    }
-  }
   PPShape s;
-  s.nsplit = (int)best;
-  s.grid = dim3((unsigned)gx, (unsigned)best, 1);
-  s.work_bytes = best > 1 ? (size_t)best * (grad ? 12 : 3) * nt * sizeof(double) : 0;
+  s.nblocks = (int)((nt + per_cta - 1) / per_cta);
+  s.units = (int64_t)s.nblocks * ntiles;
+  s.grid = (int)std::min<int64_t>(s.units, (int64_t)sm_count * kPPResident);
+  const PPPlan plan{s.units, s.grid, (int)ntiles};
+  s.split_blocks = 0;
+  for (int j = 1; j < s.grid; ++j) {      // pp_fixup_kernel's own test: a boundary inside a block, the first one there
+    const int64_t cut = plan.begin(j), start = cut / ntiles * ntiles;
+    if (cut != start && plan.begin(j - 1) <= start) ++s.split_blocks;
+  }
   return s;
 }
 
 bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, int64_t nt, const float* tx,
                const float* ty, const float* tz, const float* tr, float* tu, float* tv, float* tw, float* tug,
-               int64_t tug_stride, double* workspace) {
+               int64_t tug_stride) {
   const bool grad = tug != nullptr;
   const int64_t ntiles = nrec / kTile;
   const PPShape s = pp_shape(d.sm_count, ntiles, nt, grad);
   PPArgs a{};
   a.src = packed;
   a.ntiles = (int)ntiles;
-  a.nsplit = s.nsplit;
+  a.nblocks = s.nblocks;
   a.nt = nt;
   a.tx = tx; a.ty = ty; a.tz = tz; a.tr = tr;
   a.tu = tu; a.tv = tv; a.tw = tw;
   a.tug = tug;
   a.tug_stride = tug_stride;
   a.sign = 1.0f;
-  a.partial = nullptr;
-  if (s.nsplit > 1) {
-    if (!workspace) {
-      O3D_TRY(d, d.work.ensure(s.work_bytes));
-      workspace = d.work.as<double>();
-    }
-    a.partial = workspace;
-  }
+  // fixed-size, allocated once per device and never moved: captured CUDA graphs may hold its address
+  O3D_TRY(d, d.ppwork.ensure(pp_workspace_bytes(d.sm_count)));
+  a.partial = d.ppwork.as<double>();
   if (d.core == O3D_CORE_WL) {
     // radius ranges for the uniform-radius fast path (one pass over the records' r^2 lane and the target radii)
     O3D_TRY(d, d.rng.ensure(4 * sizeof(uint32_t)));
@@ -292,17 +281,18 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
     d.launches += 1;
     a.radius_range = d.rng.as<uint32_t>();
   }
+  const dim3 grid((unsigned)s.grid);
   if (d.profile) O3D_TRY(d, cudaEventRecord(d.evk[0], st));
   if (d.core != O3D_CORE_WL) {
     // the alternate core functions of src/CoreFunc.h (csrc/biot_pp_cores.cuh); the stream was packed for d.core
     a.radius_range = nullptr;
     if (d.tuned) {   // the post-processed copy (same instructions and results; tools/sass_patch.py)
       void* params[] = {&a};
-      O3D_TRY(d, cudaLaunchKernel((const void*)tuned_kernels().core[d.core][grad ? 1 : 0], s.grid, dim3(kPPBlock), params, 0, st));
+      O3D_TRY(d, cudaLaunchKernel((const void*)tuned_kernels().core[d.core][grad ? 1 : 0], grid, dim3(kPPBlock), params, 0, st));
     } else {
-#define O3D_PPC_LAUNCH(CORE)                                                                          \
-  if (grad) ppc_kernel<CORE, kPPTgrad, true, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a);               \
-  else      ppc_kernel<CORE, kPPTvel, false, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a)
+#define O3D_PPC_LAUNCH(CORE)                                                                        \
+  if (grad) ppc_kernel<CORE, kPPTgrad, true, kPPBlock><<<grid, kPPBlock, 0, st>>>(a);               \
+  else      ppc_kernel<CORE, kPPTvel, false, kPPBlock><<<grid, kPPBlock, 0, st>>>(a)
     if (d.core == O3D_CORE_RM) { O3D_PPC_LAUNCH(kCoreRM); }
     else if (d.core == O3D_CORE_EXP) { O3D_PPC_LAUNCH(kCoreEXP); }
     else { O3D_PPC_LAUNCH(kCoreV2); }
@@ -311,18 +301,20 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   } else if (d.tuned) {
     const TunedKernels& tk = tuned_kernels();
     void* params[] = {&a};
-    O3D_TRY(d, cudaLaunchKernel((const void*)(grad ? tk.grad : tk.vel), s.grid, dim3(kPPBlock), params, 0, st));
+    O3D_TRY(d, cudaLaunchKernel((const void*)(grad ? tk.grad : tk.vel), grid, dim3(kPPBlock), params, 0, st));
   } else if (grad) {
-    pp2_kernel<kPPTgrad, true, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a);
+    pp2_kernel<kPPTgrad, true, kPPBlock><<<grid, kPPBlock, 0, st>>>(a);
   } else {
-    pp2_kernel<kPPTvel, false, kPPBlock><<<s.grid, kPPBlock, 0, st>>>(a);
+    pp2_kernel<kPPTvel, false, kPPBlock><<<grid, kPPBlock, 0, st>>>(a);
   }
   O3D_TRY(d, cudaGetLastError());
   if (d.profile) O3D_TRY(d, cudaEventRecord(d.evk[1], st));
   d.launches += 1;
-  if (s.nsplit > 1) {
-    pp_finish_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(grad ? 12 : 3, s.nsplit, nt, workspace, tu, tv, tw,
-                                                                  tug, tug_stride, 1.0f);
+  if (s.grid > 1) {
+    // the target blocks cut by a CTA-range boundary: add their pieces in unit order (one CTA per boundary)
+    const PPPlan plan{s.units, s.grid, (int)ntiles};
+    pp_fixup_kernel<<<(unsigned)(s.grid - 1), kPPBlock * (grad ? kPPTgrad : kPPTvel), 0, st>>>(grad ? 12 : 3, plan, nt, a.partial, tu, tv, tw,
+                                                                                              tug, tug_stride, 1.0f);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
   }
@@ -390,7 +382,7 @@ enum { kRowX = 0, kRowS = 3, kRowR = 6, kRowE = 7, kRowU = 8, kRowG = 11, kRowsM
 enum { kIntX = 0, kIntS = 3, kIntU = 6, kIntG = 9, kRowsInterim = 18 };
 
 struct PartDev {
-  DevBuf main, interim[2], packed, stats;
+  DevBuf main, interim[2], packed, stats, totals;
   cudaEvent_t packed_ready = nullptr;   // this device's slice of the packed stream is written
   cudaEvent_t pulled = nullptr;         // this device has copied every peer's slice
   cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -528,7 +520,7 @@ bool part_find_vels(o3d_ctx* c, o3d_particles* p, int sel, const double* fs, boo
     PartView v = sel == 0 ? view_main(q) : view_interim(q, sel - 1);
     if (d.profile && !in_capture) O3D_TRY(d, cudaEventRecord(q.ev[0], st));
     if (!launch_pp(d, st, p->nrec, q.packed.as<float4>(), q.n, v.x[0], v.x[1], v.x[2], v.r, v.u[0], v.u[1], v.u[2],
-                   grad ? v.ug : nullptr, v.stride, nullptr))
+                   grad ? v.ug : nullptr, v.stride))
       return false;
     pts_finalize_kernel<<<(unsigned)((q.n + 255) / 256), 256, 0, st>>>(q.n, v.u[0], v.u[1], v.u[2], grad ? v.ug : nullptr, v.stride,
                                                                       fs[0], fs[1], fs[2]);
@@ -658,6 +650,12 @@ void part_release_graph(PartDev& q) {
   q.graph_n = -1;
 }
 
+// *_dev entry points launch on a caller stream: the context's first device must be the caller's current device
+bool on_current_device(const o3d_ctx* c) {
+  int cur = -1;
+  return c && !c->dev.empty() && cudaGetDevice(&cur) == cudaSuccess && cur == c->dev[0].id;
+}
+
 bool check_counts(o3d_ctx* c, int64_t a, int64_t b) {
   return c && a >= 0 && b >= 0 && a < (int64_t(1) << 31) && b < (int64_t(1) << 31);
 }
@@ -719,7 +717,7 @@ void o3d_cuda_destroy(o3d_ctx* c) {
   if (!c) return;
   for (Device& d : c->dev) {
     cudaSetDevice(d.id);
-    for (DevBuf* b : {&d.src, &d.packed, &d.targ, &d.out, &d.work, &d.geom, &d.panels, &d.tpanels, &d.cnt, &d.rng}) b->release();
+    for (DevBuf* b : {&d.src, &d.packed, &d.targ, &d.out, &d.work, &d.ppwork, &d.geom, &d.panels, &d.tpanels, &d.cnt, &d.rng}) b->release();
     for (cudaEvent_t e : d.ev)
       if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : d.evk)
@@ -802,7 +800,7 @@ int o3d_cuda_pts_on_pts(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
     if (!launch_pack(d, st, ns, ds, ds + ns, ds + 2 * ns, ds + 3 * ns, ds + 4 * ns, ds + 5 * ns, ds + 6 * ns, d.packed.as<float4>()))
       return false;
     if (!launch_pp(d, st, nrec, d.packed.as<float4>(), n, dt, dt + n, dt + 2 * n, tr ? dt + 3 * n : nullptr, dout, dout + n,
-                   dout + 2 * n, grad ? dout + 3 * n : nullptr, n, nullptr))
+                   dout + 2 * n, grad ? dout + 3 * n : nullptr, n))
       return false;
     O3D_TRY(d, cudaEventRecord(d.ev[2], st));
     for (int a = 0; a < nout; ++a) O3D_TRY(d, cudaMemcpyAsync(ho[a] + t0, dout + (size_t)a * n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -1105,18 +1103,93 @@ int o3d_cuda_pan_on_pan_coeff(o3d_ctx* c, int64_t snn, const float* snx, const f
 // ---------------------------------------------------------------------------------------------------
 int64_t o3d_cuda_packed_records(int64_t ns) { return ns < 0 ? 0 : padded_sources(ns); }
 
-int o3d_cuda_plan_pts_on_pts(int sm_count, int64_t ns, int64_t nt, int want_grad, int64_t* grid_x, int* nsplit,
-                             double* wave_efficiency, int64_t* workspace_bytes) {
+int o3d_cuda_plan_pts_on_pts(int sm_count, int64_t ns, int64_t nt, int want_grad, int64_t* grid, int* split_blocks,
+                             double* balance, int64_t* workspace_bytes) {
   if (sm_count < 1 || ns < 1 || nt < 1) return O3D_ERR_INVALID;
   const bool grad = want_grad != 0;
-  const PPShape s = pp_shape(sm_count, padded_sources(ns) / kTile, nt, grad);
-  const int64_t slots = (int64_t)sm_count * (grad ? kPPResidentGrad : kPPResidentVel);
-  const int64_t ctas = (int64_t)s.grid.x * s.grid.y, waves = (ctas + slots - 1) / slots;
-  if (grid_x) *grid_x = s.grid.x;
-  if (nsplit) *nsplit = s.nsplit;
-  if (wave_efficiency) *wave_efficiency = (double)ctas / (double)(waves * slots);
-  if (workspace_bytes) *workspace_bytes = (int64_t)s.work_bytes;
+  const int64_t ntiles = padded_sources(ns) / kTile;
+  const PPShape s = pp_shape(sm_count, ntiles, nt, grad);
+  if (grid) *grid = s.grid;
+  if (split_blocks) *split_blocks = s.split_blocks;
+  if (balance) {   // mean / max tiles per CTA: what fraction of the launch's duration the average CTA is busy
+    const PPPlan plan{s.units, s.grid, (int)ntiles};
+    int64_t most = 0;
+    for (int c = 0; c < s.grid; ++c) most = std::max(most, plan.begin(c + 1) - plan.begin(c));
+    *balance = (double)s.units / ((double)most * s.grid);
+  }
+  if (workspace_bytes) *workspace_bytes = (int64_t)pp_workspace_bytes(sm_count);
   return O3D_OK;
+}
+
+// Host replay of one launch's bookkeeping, for tests without a device: walks every CTA's tiles exactly as the kernels do
+// (pp_ring_start, pp2_walk) and every boundary exactly as pp_fixup_kernel does, and checks that each (target block,
+// source tile) unit is consumed once, that every partial segment has its own workspace slot, and that every shared block is
+// finished by exactly one fix-up CTA from exactly the slots that were written. Returns 0, or the number of the failed check.
+int o3d_cuda_plan_check(int sm_count, int64_t ns, int64_t nt, int want_grad) {
+  if (sm_count < 1 || ns < 1 || nt < 1) return -1;
+  const bool grad = want_grad != 0;
+  const int ntiles = (int)(padded_sources(ns) / kTile);
+  const PPShape s = pp_shape(sm_count, ntiles, nt, grad);
+  const PPPlan plan{s.units, s.grid, ntiles};
+  if (s.grid < 1 || s.grid > sm_count * kPPResident || plan.begin(0) != 0 || plan.begin(s.grid) != s.units) return 1;
+  std::vector<int> tiles_done(s.nblocks, 0), whole(s.nblocks, 0), fixed(s.nblocks, 0);
+  std::vector<int> slot_block((size_t)s.grid * kPPSlots, -1), slot_tiles((size_t)s.grid * kPPSlots, 0), slot_read((size_t)s.grid * kPPSlots, 0);
+  for (int c = 0; c < s.grid; ++c) {
+    const int64_t u0 = plan.begin(c), u1 = plan.begin(c + 1);
+    const int nk = (int)(u1 - u0), b0 = (int)(u0 / ntiles), kt0 = (int)(u0 % ntiles);      // pp_ring_start
+    if (nk < 1) return 2;
+    int b = b0, kt = kt0, kring = 0, seg_tiles = 0;                                          // pp2_walk / ppc_kernel
+    bool seg_first = true;
+    while (kring < nk) {
+      if (b >= s.nblocks) return 3;
+      if ((int64_t)b * ntiles + kt != u0 + kring) return 4;
+      ++kring; ++kt; ++seg_tiles;
+      if (kt == ntiles || kring == nk) {
+        const bool is_whole = kt == ntiles && (!seg_first || kt0 == 0);
+        if (is_whole != (seg_tiles == ntiles)) return 5;
+        tiles_done[b] += seg_tiles;
+        if (is_whole) whole[b] += 1;
+        else {
+          const size_t slot = (size_t)c * kPPSlots + (seg_first ? 0 : 1);
+          if (slot_block[slot] != -1) return 6;                             // a slot is written once per launch
+          slot_block[slot] = b;
+          slot_tiles[slot] = seg_tiles;
+        }
+        seg_first = false;
+        kt = 0;
+        seg_tiles = 0;
+        ++b;
+      }
+    }
+  }
+  for (int j = 1; j < s.grid; ++j) {                                      // pp_fixup_kernel
+    const int64_t cut = plan.begin(j);
+    const int64_t b = cut / ntiles, start = b * ntiles, end = start + ntiles;
+    if (cut == start) continue;
+    const int64_t prev = plan.begin(j - 1);
+    if (prev > start) continue;
+    int got = 0;
+    auto take = [&](size_t slot) {
+      if (slot_block[slot] != (int)b) return false;
+      got += slot_tiles[slot];
+      slot_read[slot] += 1;
+      return true;
+    };
+    if (!take((size_t)(j - 1) * kPPSlots + (prev == start ? 0 : 1))) return 7;
+    for (int c = j; c < plan.P && plan.begin(c) < end; ++c)
+      if (!take((size_t)c * kPPSlots)) return 8;
+    if (got != ntiles) return 9;
+    fixed[b] += 1;
+  }
+  int nsplit = 0;
+  for (int b = 0; b < s.nblocks; ++b) {
+    if (tiles_done[b] != ntiles) return 10;
+    if (whole[b] + fixed[b] != 1) return 11;
+    nsplit += fixed[b];
+  }
+  for (size_t k = 0; k < slot_block.size(); ++k)
+    if ((slot_block[k] != -1) != (slot_read[k] == 1)) return 12;
+  return nsplit == s.split_blocks ? 0 : 13;
 }
 
 int o3d_cuda_pack_sources_dev(o3d_ctx* c, void* stream, int64_t ns, const float* sx, const float* sy, const float* sz,
@@ -1126,6 +1199,7 @@ int o3d_cuda_pack_sources_dev(o3d_ctx* c, void* stream, int64_t ns, const float*
   if (nrec != 0 && (nrec < padded_sources(ns) || nrec % kTile != 0)) return fail(c, O3D_ERR_INVALID, "pack_sources_dev: bad nrec");
   if (ns == 0 && nrec == 0) return O3D_OK;
   if (!packed || (ns > 0 && (!sx || !sy || !sz || !ssx || !ssy || !ssz))) return fail(c, O3D_ERR_INVALID, "pack_sources_dev: NULL array");
+  if (!on_current_device(c)) return fail(c, O3D_ERR_INVALID, "pack_sources_dev: the context's device is not the current device");
   Device& d = c->dev[0];
   d.launches = 0;
   launch_pack(d, (cudaStream_t)stream, ns, sx, sy, sz, sr, ssx, ssy, ssz, (float4*)packed, nrec);
@@ -1139,9 +1213,10 @@ int o3d_cuda_pts_on_pts_dev(o3d_ctx* c, void* stream, int64_t nrec, const void* 
   if (nrec == 0 || nt == 0) return O3D_OK;
   if (!packed || !tx || !ty || !tz || !tu || !tv || !tw || (tug && tug_stride < nt))
     return fail(c, O3D_ERR_INVALID, "pts_on_pts_dev: NULL array");
+  if (!on_current_device(c)) return fail(c, O3D_ERR_INVALID, "pts_on_pts_dev: the context's device is not the current device");
   Device& d = c->dev[0];
   d.launches = 0;
-  launch_pp(d, (cudaStream_t)stream, nrec, (const float4*)packed, nt, tx, ty, tz, tr, tu, tv, tw, tug, tug_stride, nullptr);
+  launch_pp(d, (cudaStream_t)stream, nrec, (const float4*)packed, nt, tx, ty, tz, tr, tu, tv, tw, tug, tug_stride);
   return collect(c);
 }
 
@@ -1153,6 +1228,7 @@ int o3d_cuda_pts_finalize_dev(o3d_ctx* c, void* stream, int64_t n, float* u, flo
   if (!c || n < 0 || n >= (int64_t(1) << 31)) return fail(c, O3D_ERR_INVALID, "pts_finalize_dev: bad context or count");
   if (n == 0) return O3D_OK;
   if (!u || !v || !w || !fs || (ug && ug_stride < n)) return fail(c, O3D_ERR_INVALID, "pts_finalize_dev: NULL array");
+  if (!on_current_device(c)) return fail(c, O3D_ERR_INVALID, "pts_finalize_dev: the context's device is not the current device");
   Device& d = c->dev[0];
   d.launches = 0;
   pts_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, u, v, w, ug, ug_stride, fs[0], fs[1], fs[2]);
@@ -1192,6 +1268,7 @@ int o3d_cuda_pts_move_dev(o3d_ctx* c, void* stream, int64_t n, int order, double
     a.uout[d] = order > 1 ? uout[d] : nullptr;
   }
   a.ein = ein; a.eout = eout;
+  if (!on_current_device(c)) return fail(c, O3D_ERR_INVALID, "pts_move_dev: the context's device is not the current device");
   Device& d = c->dev[0];
   d.launches = 0;
   launch_move(d, (cudaStream_t)stream, a, order);
@@ -1212,7 +1289,7 @@ void o3d_cuda_particles_destroy(o3d_ctx* c, o3d_particles* p) {
     if (c && k < c->dev.size()) cudaSetDevice(c->dev[k].id);
     PartDev& q = p->dev[k];
     part_release_graph(q);
-    for (DevBuf* b : {&q.main, &q.interim[0], &q.interim[1], &q.packed, &q.stats}) b->release();
+    for (DevBuf* b : {&q.main, &q.interim[0], &q.interim[1], &q.packed, &q.stats, &q.totals}) b->release();
     for (cudaEvent_t e : {q.packed_ready, q.pulled, q.ev[0], q.ev[1]})
       if (e) cudaEventDestroy(e);
   }
@@ -1407,6 +1484,102 @@ int o3d_cuda_particles_stats(o3d_ctx* c, o3d_particles* p, float* max_str, float
   if (max_str) *max_str = std::sqrt(ms);   // ElementBase::get_max_str returns sqrt of the largest |s|^2
   if (max_elong) *max_elong = me;
   return collect(c);
+}
+
+// Status-file quantities of a resident collection: total circulation and linear impulse
+int o3d_cuda_particles_totals(o3d_ctx* c, o3d_particles* p, double* circ, double* impulse) {
+  if (!c || !p || p->dev.size() != c->dev.size()) return fail(c, O3D_ERR_INVALID, "particles_totals: bad argument");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  double tot[6] = {0, 0, 0, 0, 0, 0};
+  constexpr int kBlocks = 296;   // fixed, not the SM count: the shape of the summation tree is part of the result
+  for (size_t k = 0; k < c->dev.size(); ++k) {       // devices in order: the collection's blocks in particle order
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    if (q.n == 0) continue;
+    double h[6];
+    auto go = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      O3D_TRY(d, q.totals.ensure((size_t)(kBlocks + 1) * 6 * sizeof(double)));
+      double* part = q.totals.as<double>();
+      pts_totals_kernel<<<kBlocks, kTotalsBlock, 0, d.stream>>>(q.n, prow(q.main, q.cap, kRowX), prow(q.main, q.cap, kRowX + 1),
+                                                                prow(q.main, q.cap, kRowX + 2), prow(q.main, q.cap, kRowS),
+                                                                prow(q.main, q.cap, kRowS + 1), prow(q.main, q.cap, kRowS + 2), part);
+      pts_totals_finish_kernel<<<1, 32, 0, d.stream>>>(kBlocks, part, part + (size_t)kBlocks * 6);
+      O3D_TRY(d, cudaGetLastError());
+      d.launches += 2;
+      O3D_TRY(d, cudaMemcpyAsync(h, part + (size_t)kBlocks * 6, sizeof h, cudaMemcpyDeviceToHost, d.stream));
+      O3D_TRY(d, cudaStreamSynchronize(d.stream));
+      return true;
+    };
+    if (!go()) break;
+    for (int a = 0; a < 6; ++a) tot[a] += h[a];
+  }
+  for (int a = 0; a < 3; ++a) {
+    if (circ) circ[a] = tot[a];
+    if (impulse) impulse[a] = tot[3 + a];
+  }
+  return collect(c);
+}
+
+// ---- status file (csrc/status_writer.h) ---------------------------------------------------------------------
+int o3d_cuda_status_open(const char* path, int csv, o3d_status** out) {
+  if (!path || !path[0] || !out) return O3D_ERR_INVALID;
+  o3d_status* st = new o3d_status();
+  st->fn = path;
+  st->csv = csv != 0;
+  *out = st;
+  return O3D_OK;
+}
+void o3d_cuda_status_close(o3d_status* st) { delete st; }
+int o3d_cuda_status_reset_sim(o3d_status* st) {
+  if (!st) return O3D_ERR_INVALID;
+  st->reset_sim();
+  return O3D_OK;
+}
+int o3d_cuda_status_append_float(o3d_status* st, const char* name, float value) {
+  if (!st) return O3D_ERR_INVALID;
+  st->append(name ? name : "float", value);       // StatusFile::append_value(float) names the column "float"
+  return O3D_OK;
+}
+int o3d_cuda_status_append_int(o3d_status* st, const char* name, int value) {
+  if (!st) return O3D_ERR_INVALID;
+  st->append(name ? name : "int", value);
+  return O3D_OK;
+}
+int o3d_cuda_status_write_line(o3d_status* st) {
+  if (!st) return O3D_ERR_INVALID;
+  return st->write_line() ? O3D_OK : O3D_ERR_INVALID;
+}
+
+// Simulation::dump_stats_to_status (src/Simulation.cpp:851-897) for a system that is one resident particle collection:
+// time, Nv, total circulation, and the force estimate of calculate_simple_forces (:900-924) - the time derivative of the
+// total impulse by a one-sided difference whose previous sample lives in the status object.
+int o3d_cuda_particles_write_status(o3d_ctx* c, o3d_particles* p, o3d_status* st, double time, double dt) {
+  if (!c || !p || !st) return fail(c, O3D_ERR_INVALID, "particles_write_status: bad argument");
+  double circ[3], imp[3];
+  const int rc = o3d_cuda_particles_totals(c, p, circ, imp);
+  if (rc != O3D_OK) return rc;
+  st->append("time", (float)time);
+  st->append("Nv", (int)p->n);
+  st->append("gx", (float)circ[0]);
+  st->append("gy", (float)circ[1]);
+  st->append("gz", (float)circ[2]);
+  if (time < 0.1 * dt) {           // a new run: the "last" sample is zero impulse one step before the start
+    st->last_time = -dt;
+    st->last_impulse[0] = st->last_impulse[1] = st->last_impulse[2] = 0.0f;
+  }
+  float force[3];
+  for (int a = 0; a < 3; ++a) {
+    const float now = (float)imp[a];
+    force[a] = (float)((now - st->last_impulse[a]) / (time - st->last_time));   // float difference over a double interval
+    st->last_impulse[a] = now;
+  }
+  st->last_time = time;
+  st->append("fx", force[0]);
+  st->append("fy", force[1]);
+  st->append("fz", force[2]);
+  if (!st->write_line()) return fail(c, O3D_ERR_INVALID, "particles_write_status: cannot write " + st->fn);
+  return O3D_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------

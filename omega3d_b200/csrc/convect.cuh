@@ -178,4 +178,45 @@ __global__ void __launch_bounds__(256) pts_stats_kernel(int64_t n, const float* 
   }
 }
 
+// Total circulation and linear impulse of a collection (the status-file quantities):
+//   circ = sum_i s_i                                        ElementBase::get_total_circ  (src/ElementBase.h:354-378)
+//   imp  = sum_i (s1 x2 - s2 x1, s2 x0 - s0 x2, s0 x1 - s1 x0)   Points::get_total_impulse  (src/Points.h:547-563)
+// The per-particle terms are formed in float with the reference's unfused operations; the SUMS are FP64 trees of fixed shape
+// (grid-stride per thread, shuffle tree per warp, warps in order, blocks in order in pts_totals_finish_kernel): deterministic,
+// and exact to ~1e-16 where the reference's own sums carry a double sequential (circulation) or a float sequential (impulse)
+// rounding. part: [gridDim.x][6] doubles.
+constexpr int kTotalsBlock = 256;
+__global__ void __launch_bounds__(kTotalsBlock) pts_totals_kernel(int64_t n, const float* x0, const float* x1, const float* x2, const float* s0,
+                                                                  const float* s1, const float* s2, double* part) {
+  double a[6] = {0, 0, 0, 0, 0, 0};
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float px = x0[i], py = x1[i], pz = x2[i], wx = s0[i], wy = s1[i], wz = s2[i];
+    a[0] += (double)wx; a[1] += (double)wy; a[2] += (double)wz;
+    a[3] += (double)__fsub_rn(__fmul_rn(wy, pz), __fmul_rn(wz, py));
+    a[4] += (double)__fsub_rn(__fmul_rn(wz, px), __fmul_rn(wx, pz));
+    a[5] += (double)__fsub_rn(__fmul_rn(wx, py), __fmul_rn(wy, px));
+  }
+  __shared__ double warp_sum[kTotalsBlock / 32][6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) a[k] += __shfl_down_sync(0xffffffffu, a[k], off);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5][k] = a[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double t = 0.0;
+    for (int w = 0; w < kTotalsBlock / 32; ++w) t += warp_sum[w][threadIdx.x];
+    part[(size_t)blockIdx.x * 6 + threadIdx.x] = t;
+  }
+}
+__global__ void pts_totals_finish_kernel(int nblocks, const double* part, double* out) {
+  if (threadIdx.x < 6) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; ++b) t += part[(size_t)b * 6 + threadIdx.x];
+    out[threadIdx.x] = t;
+  }
+}
+
 }  // namespace o3d

@@ -9,7 +9,7 @@
 #include <string>
 #include <cstring>
 #include <cuda.h>
-#include "../biot_pp.cuh"
+#include "pp_scalar.cuh"   // the scalar-FFMA kernel with its gridDim.y split (not a product kernel) + ../biot_pp.cuh
 
 using namespace o3d;
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
@@ -49,7 +49,10 @@ int main(int argc, char** argv) {
   pp_pack_kernel<<<(npad + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk);
   pp_pack2_kernel<<<(npad / 2 + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk2);
   float* out; CHECK(cudaMalloc(&out, (size_t)n * 12 * 4));
-  double* partial; CHECK(cudaMalloc(&partial, (size_t)n * 12 * 8 * 4));  // up to 4 source slices
+  double* partial; CHECK(cudaMalloc(&partial, (size_t)n * 12 * 8 * 4));  // scalar kernel: up to 4 source slices
+  // packed kernel: persistent CTAs, 3 per SM (capi.cu: pp_shape), 2 workspace slots each
+  const int resident = prop.multiProcessorCount * 3;
+  double* ppwork; CHECK(cudaMalloc(&ppwork, (size_t)resident * kPPSlots * 12 * 256 * 8));
   uint32_t* range; CHECK(cudaMalloc(&range, 16));
   CHECK(cudaMemset(range, 0, 16));
   pp_scan_kernel<<<prop.multiProcessorCount * 4, 256>>>(npad, pk2, n, d[3], range);
@@ -68,13 +71,33 @@ int main(int argc, char** argv) {
   }
 
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  auto run = [&](const char* name, auto kern, int T, int BLOCK, bool grad, const float4* src, int nsplit) {
-    PPArgs a{};
-    a.src = src; a.ntiles = (int)(npad / kTile); a.nsplit = nsplit; a.nt = n;
+  auto report = [&](const char* name, int T, int BLOCK, bool grad, int nsplit, int grid, float best, bool fnv) {
+    std::vector<float> o((size_t)n * 12);
+    CHECK(cudaMemcpy(o.data(), out, (size_t)n * 12 * 4, cudaMemcpyDeviceToHost));
+    double eu = 0, eg = 0;
+    for (int c = 0; c < nchk; ++c) {
+      const int i = (int)((long long)c * n / nchk);
+      for (int k = 0; k < 3; ++k) eu = std::fmax(eu, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
+      if (grad) for (int k = 3; k < 12; ++k) eg = std::fmax(eg, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
+    }
+    const double ips = (double)n * n / (best * 1e-3);
+    printf("%-36s T=%d B=%3d split=%2d grid=%6d  %8.3f ms  %.3e int/s  %6.2f TFLOP/s@%d  err u %.2e g %.2e", name, T, BLOCK, nsplit,
+           grid, best, ips, ips * (grad ? 70 : 33) * 1e-12, grad ? 70 : 33, eu / umax, eg / gmax);
+    if (fnv) {   // checksum over ALL outputs: a patched cubin must reproduce the linked kernel bit for bit
+      unsigned long long h = 1469598103934665603ull;
+      const size_t cnt = grad ? o.size() : (size_t)n * 3;
+      for (size_t q = 0; q < cnt; ++q) { unsigned v; memcpy(&v, &o[q], 4); h = (h ^ v) * 1099511628211ull; }
+      printf("  fnv %016llx", h);
+    }
+    printf("\n");
+  };
+  // scalar-FFMA kernel: one target block per CTA, gridDim.y source slices (pp_scalar.cuh)
+  auto run_scalar = [&](const char* name, auto kern, int T, int BLOCK, bool grad, int nsplit) {
+    PPScalarArgs a{};
+    a.src = pk; a.ntiles = (int)(npad / kTile); a.nsplit = nsplit; a.nt = n;
     a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
     a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = out + 3 * (size_t)n; a.tug_stride = n;
     a.partial = partial; a.sign = 1.0f;
-    a.radius_range = (src == pk2 && !no_uniform) ? range : nullptr;
     dim3 grid((n + BLOCK * T - 1) / (BLOCK * T), nsplit);
     float best = 1e30f;
     for (int r = 0; r < reps + 1; ++r) {
@@ -87,22 +110,46 @@ int main(int argc, char** argv) {
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       if (r > 0 && ms < best) best = ms;
     }
-    std::vector<float> o((size_t)n * 12);
-    CHECK(cudaMemcpy(o.data(), out, (size_t)n * 12 * 4, cudaMemcpyDeviceToHost));
-    double eu = 0, eg = 0;
-    for (int c = 0; c < nchk; ++c) {
-      const int i = (int)((long long)c * n / nchk);
-      for (int k = 0; k < 3; ++k) eu = std::fmax(eu, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
-      if (grad) for (int k = 3; k < 12; ++k) eg = std::fmax(eg, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
-    }
-    const double ips = (double)n * n / (best * 1e-3);
-    printf("%-22s T=%d B=%3d split=%2d grid=%6d  %8.3f ms  %.3e int/s  %6.2f TFLOP/s@%d  err u %.2e g %.2e\n", name, T, BLOCK, nsplit,
-           grid.x * grid.y, best, ips, ips * (grad ? 70 : 33) * 1e-12, grad ? 70 : 33, eu / umax, eg / gmax);
+    report(name, T, BLOCK, grad, nsplit, grid.x * grid.y, best, false);
   };
-#define RUN_S(T, B, G, SPLIT) run("scalar" #G, pp_kernel<T, G, B>, T, B, G, pk, SPLIT)
-#define RUN_P(T, B, G, SPLIT) run("packed" #G, pp2_kernel<T, G, B>, T, B, G, pk2, SPLIT)
-  // KBENCH_CUBIN=a.cubin[:b.cubin...]: time pp2_kernel<2,true,128> loaded from cubin files (tools/sass_patch.py output)
-  // through the driver API, next to the copy linked into this binary.
+  // packed kernel: persistent CTAs over the stream-K partition + fix-up of the shared target blocks (what capi.cu launches).
+  // `fn` != nullptr: the copy of the kernel in a cubin file, through the driver API.
+  auto run_packed = [&](const char* name, auto kern, CUfunction fn, int T, int BLOCK, bool grad, int per_sm) {
+    PPArgs a{};
+    a.src = pk2; a.ntiles = (int)(npad / kTile); a.nt = n;
+    a.nblocks = (n + BLOCK * T - 1) / (BLOCK * T);
+    a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
+    a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = grad ? out + 3 * (size_t)n : nullptr; a.tug_stride = n;
+    a.partial = ppwork; a.sign = 1.0f;
+    a.radius_range = no_uniform ? nullptr : range;
+    const int64_t units = (int64_t)a.nblocks * a.ntiles;
+    const int grid = (int)std::min<int64_t>(units, (int64_t)prop.multiProcessorCount * per_sm);
+    if (grid > resident || BLOCK * T * (grad ? 12 : 3) > 12 * 256) { printf("%s: workspace too small for this shape\n", name); return; }
+    const PPPlan plan{units, grid, a.ntiles};
+    float best = 1e30f;
+    for (int r = 0; r < reps + 1; ++r) {
+      CHECK(cudaMemset(out, 0, (size_t)n * 12 * 4));
+      cudaEventRecord(e0);
+      if (fn) {
+        void* params[] = {&a};
+        if (cuLaunchKernel(fn, grid, 1, 1, BLOCK, 1, 1, 0, 0, params, nullptr) != CUDA_SUCCESS) { printf("launch failed\n"); return; }
+      } else {
+        kern<<<grid, BLOCK>>>(a);
+      }
+      if (grid > 1) pp_fixup_kernel<<<grid - 1, BLOCK * T>>>(grad ? 12 : 3, plan, n, ppwork, a.tu, a.tv, a.tw, a.tug, n, 1.0f);
+      cudaEventRecord(e1);
+      CHECK(cudaDeviceSynchronize());
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      if (r > 0 && ms < best) best = ms;
+    }
+    report(name, T, BLOCK, grad, 1, grid, best, true);
+  };
+#define RUN_S(T, B, G, SPLIT) run_scalar("scalar" #G, pp_kernel<T, G, B>, T, B, G, SPLIT)
+#define RUN_P(T, B, G, PER_SM) run_packed("packed" #G " stage" O3D_STR(O3D_PP_STAGE), pp2_kernel<T, G, B>, nullptr, T, B, G, PER_SM)
+#define O3D_STR2(x) #x
+#define O3D_STR(x) O3D_STR2(x)
+  // KBENCH_CUBIN=a.cubin[:b.cubin...]: time the two product instantiations of pp2_kernel loaded from cubin files
+  // (tools/sass_patch.py output) through the driver API, next to the copies linked into this binary.
   if (const char* list = getenv("KBENCH_CUBIN")) {
     std::string all(list);
     size_t pos = 0;
@@ -118,42 +165,16 @@ int main(int argc, char** argv) {
                                                              {"_ZN3o3d10pp2_kernelILi4ELb0ELi128EEEvNS_6PPArgsE", 4, false}};
       for (auto& kd : kinds) {
         if (cuModuleGetFunction(&fn, mod, kd.sym) != CUDA_SUCCESS) continue;
-        PPArgs a{};
-        a.src = pk2; a.ntiles = (int)(npad / kTile); a.nsplit = 1; a.nt = n;
-        a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
-        a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = kd.grad ? out + 3 * (size_t)n : nullptr; a.tug_stride = n;
-        a.partial = partial; a.sign = 1.0f; a.radius_range = no_uniform ? nullptr : range;
-        const int T = kd.T, BLOCK = 128;
-        const unsigned grid = (n + BLOCK * T - 1) / (BLOCK * T);
-        float best = 1e30f;
-        for (int r = 0; r < reps + 1; ++r) {
-          CHECK(cudaMemset(out, 0, (size_t)n * 12 * 4));
-          cudaEventRecord(e0);
-          void* params[] = {&a};
-          if (cuLaunchKernel(fn, grid, 1, 1, BLOCK, 1, 1, 0, 0, params, nullptr) != CUDA_SUCCESS) { printf("launch failed\n"); break; }
-          cudaEventRecord(e1);
-          CHECK(cudaDeviceSynchronize());
-          float ms; cudaEventElapsedTime(&ms, e0, e1);
-          if (r > 0 && ms < best) best = ms;
-        }
-        std::vector<float> o((size_t)n * 12);
-        CHECK(cudaMemcpy(o.data(), out, (size_t)n * 12 * 4, cudaMemcpyDeviceToHost));
-        double eu = 0, eg = 0;
-        for (int c = 0; c < nchk; ++c) {
-          const int i = (int)((long long)c * n / nchk);
-          for (int k = 0; k < 3; ++k) eu = std::fmax(eu, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
-          if (kd.grad) for (int k = 3; k < 12; ++k) eg = std::fmax(eg, std::fabs(o[(size_t)k * n + i] - ref[c * 12 + k]));
-        }
-        // checksum over ALL outputs: a patched file must reproduce the linked kernel bit for bit
-        unsigned long long h = 1469598103934665603ull;
-        for (size_t q = 0; q < o.size(); ++q) { unsigned v; memcpy(&v, &o[q], 4); h = (h ^ v) * 1099511628211ull; }
-        const double ips = (double)n * n / (best * 1e-3);
-        const int fl = kd.grad ? 70 : 33;
-        printf("cubin %-36s %s %8.3f ms  %.3e int/s  %6.2f TFLOP/s@%d  err u %.2e g %.2e  fnv %016llx\n", path.c_str(), kd.grad ? "velgrad" : "vel    ",
-               best, ips, ips * fl * 1e-12, fl, eu / umax, eg / gmax, h);
+        const std::string label = "cubin " + path + (kd.grad ? " velgrad" : " vel");
+        run_packed(label.c_str(), pp2_kernel<2, true, 128>, fn, kd.T, 128, kd.grad, 3);
       }
     }
     if (getenv("KBENCH_CUBIN_ONLY")) return 0;
+  }
+  if (getenv("KBENCH_PRODUCT_ONLY")) {     // the two product shapes only (staging-variant builds: make kbench_stage)
+    RUN_P(2, 128, true, 3);
+    RUN_P(4, 128, false, 3);
+    return 0;
   }
   RUN_S(1, 256, true, 1);
   RUN_S(2, 256, true, 1);
@@ -162,16 +183,12 @@ int main(int argc, char** argv) {
   RUN_S(4, 128, true, 1);
   RUN_S(3, 128, true, 1);
   RUN_S(3, 256, true, 1);
-  RUN_P(1, 256, true, 1);
-  RUN_P(1, 128, true, 1);
-  RUN_P(2, 256, true, 1);
-  RUN_P(2, 128, true, 1);
-  RUN_P(3, 128, true, 1);
   RUN_S(2, 256, true, 4);
-  RUN_P(2, 128, true, 4);
+  RUN_P(1, 256, true, 2);
+  RUN_P(1, 128, true, 4);
+  RUN_P(2, 128, true, 3);
   RUN_S(4, 256, false, 1);
   RUN_S(8, 128, false, 1);
-  RUN_P(2, 256, false, 1);
-  RUN_P(4, 128, false, 1);
+  RUN_P(4, 128, false, 3);
   return 0;
 }

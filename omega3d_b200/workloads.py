@@ -122,6 +122,12 @@ EXAMPLES = {
         dict(center=(0.0, 0.0, 0.0), normal=(0.8999999761581421, 0.05000000074505806, 0.10000000149011612), majrad=0.5, circ=1.0),
         dict(center=(-0.18000000715255737, -0.009999999776482582, -0.019999999552965164),
              normal=(0.8999999761581421, 0.05000000074505806, 0.10000000149011612), majrad=0.5, circ=1.0)]),
+    # 3Dexamples/colliding_vortex_rings_nv.json (BASELINE configs[2], its inviscid form: "viscous": "none")
+    "colliding_vortex_rings_nv": dict(re=40.000003814697266, dt=0.0020000000949949026, fs=(0.0, 0.0, 0.0), rings=[
+        dict(center=(0.4000000059604645, 0.0, 0.0), normal=(-0.8999999761581421, -0.05000000074505806, -0.10000000149011612),
+             majrad=0.5, circ=1.0),
+        dict(center=(0.03999999910593033, -0.019999999552965164, -0.03999999910593033),
+             normal=(0.8999999761581421, 0.05000000074505806, 0.10000000149011612), majrad=0.5, circ=1.0)]),
 }
 
 

@@ -559,6 +559,24 @@ void o3d_oracle_stats(int64_t n, const float* s, const float* elong, float* max_
   *max_elong = me;
 }
 
+/* ElementBase::get_total_circ (src/ElementBase.h:354-378: std::accumulate with a DOUBLE init value over the float strengths, so
+ * a sequential double sum rounded to float once; the "< 40000" test reads the size of the 3-array, always the first branch)
+ * and Points::get_total_impulse (src/Points.h:547-563: float terms summed sequentially in float). x, s: 3 x n rows. */
+void o3d_oracle_totals(int64_t n, const float* x, const float* s, float* circ, float* impulse) {
+  for (int d = 0; d < 3; ++d) {
+    double acc = 0.0;
+    for (int64_t i = 0; i < n; ++i) acc += s[d * n + i];
+    circ[d] = (float)acc;
+  }
+  float i0 = 0.0f, i1 = 0.0f, i2 = 0.0f;
+  for (int64_t i = 0; i < n; ++i) {
+    i0 += s[n + i] * x[2 * n + i] - s[2 * n + i] * x[n + i];
+    i1 += s[2 * n + i] * x[i] - s[i] * x[2 * n + i];
+    i2 += s[i] * x[n + i] - s[n + i] * x[i];
+  }
+  impulse[0] = i0; impulse[1] = i1; impulse[2] = i2;
+}
+
 /* =====================================================================================================
  * Particle x panel closest-point loops (src/Reflect.h). Float throughout; "1.0 / x" is a double division
  * stored into a float, as in the reference.

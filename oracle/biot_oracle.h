@@ -76,6 +76,8 @@ void o3d_oracle_advect(int order, int nsteps, double dt, const double* fs, int64
 /* core function used by o3d_oracle_advect's evaluations (0 = Winckelmans-Leonard, the default; see o3d_oracle_pts_on_pts_core) */
 void o3d_oracle_set_advect_core(int core);
 void o3d_oracle_stats(int64_t n, const float* s, const float* elong, float* max_str, float* max_elong);
+/* ElementBase::get_total_circ (src/ElementBase.h:354-378) and Points::get_total_impulse (src/Points.h:547-563); x, s: 3 x n */
+void o3d_oracle_totals(int64_t n, const float* x, const float* s, float* circ, float* impulse);
 
 /* ---- particle x panel closest-point loops: reflect_panp2 (mode 0, src/Reflect.h:194-311) and clear_inner_panp2 with
  * _method 1 (mode 1, :446-620). nodes SoA, idx 3 per panel, nrm SoA 3 x np, x 3 x nt in/out. Returns particles moved. */

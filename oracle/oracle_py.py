@@ -66,6 +66,7 @@ class Restatement:
         L.o3d_oracle_stats.argtypes = [c_int64] + [c_void_p] * 4
         L.o3d_oracle_closest_pass.argtypes = [c_int, c_int64] + [c_void_p] * 5 + [c_int64, c_void_p, c_float, c_float]
         L.o3d_oracle_closest_pass.restype = c_int64
+        L.o3d_oracle_totals.argtypes = [c_int64] + [c_void_p] * 4
 
     def set_threads(self, n):
         self.lib.o3d_oracle_set_threads(int(n))
@@ -99,6 +100,12 @@ class Restatement:
         a, b = c_float(), c_float()
         self.lib.o3d_oracle_stats(s.shape[1], _p(s), _p(elong), ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
+
+    def totals(self, x, s):
+        """(get_total_circ, get_total_impulse) of a particle collection: two float32[3]."""
+        c, i = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self.lib.o3d_oracle_totals(x.shape[1], _p(_f32(x)), _p(_f32(s)), _p(c), _p(i))
+        return c, i
 
     def reflect(self, nodes, idx, nrm, x):
         """reflect_panp2: nodes (3,nn) SoA, idx (np,3), nrm (3,np); x (3,nt) updated in place. Returns particles moved."""
@@ -169,7 +176,8 @@ class Reference:
         """dropin=True: the patched, -DUSE_CUDA build of the same driver (oracle/_ref/libo3d_dropin.so); call
         set_accel(4) on it to route the reference's own routines into the CUDA arm.
         core != 0: the build whose src/CoreFunc.h has another core function #defined (oracle/Makefile core_build)."""
-        name = "libo3d_ref_fast.so" if fast else self.CORE_BUILDS[core]
+        # fast: True / "v3" = -march=x86-64-v3, "v4" = -march=x86-64-v4 (AVX-512 hosts only: check host_has_avx512())
+        name = ("libo3d_ref_fast_v4.so" if fast == "v4" else "libo3d_ref_fast.so") if fast else self.CORE_BUILDS[core]
         if dropin:   # dropin="exp": the drop-in build of a reference with the exponential core #defined
             name = "libo3d_dropin_exp.so" if dropin == "exp" else "libo3d_dropin.so"
         path = os.path.join(OUT, name)
@@ -199,6 +207,9 @@ class Reference:
             L.o3d_ref_reflect.restype = c_long
             L.o3d_ref_clear_inner.argtypes = [c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_float]
             L.o3d_ref_clear_inner.restype = c_long
+        if hasattr(L, "o3d_ref_totals"):
+            L.o3d_ref_totals.argtypes = [c_int] + [c_void_p] * 4
+            L.o3d_ref_status_lines.argtypes = [ctypes.c_char_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
         if hasattr(L, "o3d_ref_write_vtk"):
             L.o3d_ref_write_vtk.argtypes = [c_int] + [c_void_p] * 4 + [c_int, c_int, c_double, ctypes.c_char_p]
         if hasattr(L, "o3d_ref_has_features") and L.o3d_ref_has_features():
@@ -234,6 +245,21 @@ class Reference:
         a, b = c_float(), c_float()
         self.lib.o3d_ref_stats(s.shape[1], _p(s), _p(elong), ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
+
+    def totals(self, x, s):
+        """(ElementBase::get_total_circ, Points::get_total_impulse) through the reference's Points<float>: two float32[3]."""
+        c, i = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self.lib.o3d_ref_totals(x.shape[1], _p(_f32(x)), _p(_f32(s)), _p(c), _p(i))
+        return c, i
+
+    def status_lines(self, path, csv, vals, nv, reset_before):
+        """The reference's StatusFile appending len(nv) lines of (time, Nv, g[3], f[3]); vals (nlines,7) float32."""
+        vals = np.ascontiguousarray(vals, np.float32)
+        nv = np.ascontiguousarray(nv, np.int32)
+        rb = np.ascontiguousarray(reset_before, np.int32)
+        self.lib.o3d_ref_status_lines(path.encode(), int(csv), len(nv), _p(vals), _p(nv), _p(rb))
+        with open(path, "rb") as f:
+            return f.read()
 
     # ---- particle x panel closest-point loops (src/Reflect.h) ----
     def reflect(self, nodes_i, idx, x):
@@ -339,6 +365,24 @@ class Reference:
         fn = self.lib.o3d_ref_rkernel_2vs_0pg if grads else self.lib.o3d_ref_rkernel_2vs_0p
         flops = fn(_p(_f32(tri9)), _p(_f32(str4)), _p(_f32(t3)), c_float(sa), _p(out))
         return out, flops
+
+
+def host_threads() -> int:
+    """Host cores this process may run on. NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its ranks."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def host_has_avx512() -> bool:
+    """The x86-64-v4 feature set (what -march=x86-64-v4 code needs), from /proc/cpuinfo."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((l for l in f if l.startswith("flags")), "").split()
+    except OSError:
+        return False
+    return all(x in flags for x in ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"))
 
 
 def have_reference() -> bool:

@@ -23,6 +23,7 @@
 #include "Coefficients.h"
 #include <chrono>
 #include "Reflect.h"
+#include "StatusFile.h"          // src/StatusFile.cpp is compiled where it lies (oracle/Makefile)
 #ifdef USE_CUDA
 #include "O3DCudaConvection.h"   // what the patched Convection.h includes (integration/omega3d_use_cuda.patch)
 #endif
@@ -392,6 +393,34 @@ void o3d_ref_stats(int n, const float* s, const float* elong, float* max_str, fl
   std::memcpy(p.get_elong().data(), elong, sizeof(float)*n);
   *max_str = p.get_max_str();
   *max_elong = p.get_max_elong();
+}
+
+// ElementBase::get_total_circ (src/ElementBase.h:354-378) and Points::get_total_impulse (src/Points.h:547-563)
+void o3d_ref_totals(int n, const float* x /*3 x n*/, const float* s /*3 x n*/, float* circ, float* impulse) {
+  Mute m(g_mute);
+  Points<float> p = make_points(n, x, x + n, x + 2 * (size_t)n, s, nullptr, active, lagrangian);
+  const std::array<float,3> c = p.get_total_circ(0.0);
+  const std::array<float,3> i = p.get_total_impulse();
+  for (int d = 0; d < 3; ++d) { circ[d] = c[d]; impulse[d] = i[d]; }
+}
+
+// The reference's StatusFile driven the way Simulation::dump_stats_to_status drives it (src/Simulation.cpp:851-897): `nlines`
+// lines of (time, Nv, gx gy gz, fx fy fz) appended to `path`; reset_before[k] != 0 calls reset_sim() before line k (a new run
+// in the same process: src/Simulation.cpp:575). vals: nlines x 7 floats (time, g[3], f[3]); nv: nlines ints.
+int o3d_ref_status_lines(const char* path, int csv_format, int nlines, const float* vals, const int* nv, const int* reset_before) {
+  StatusFile sf;
+  sf.set_filename(path);
+  sf.format = csv_format ? csv : dat;
+  for (int k = 0; k < nlines; ++k) {
+    if (reset_before && reset_before[k]) sf.reset_sim();
+    const float* v = vals + 7 * (size_t)k;
+    sf.append_value("time", v[0]);
+    sf.append_value("Nv", nv[k]);
+    sf.append_value("gx", v[1]); sf.append_value("gy", v[2]); sf.append_value("gz", v[3]);
+    sf.append_value("fx", v[4]); sf.append_value("fy", v[5]); sf.append_value("fz", v[6]);
+    sf.write_line();
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -128,6 +128,46 @@ def vtk(ref):
     np.savez_compressed(os.path.join(OUT, "vtk.npz"), **g)
 
 
+def status(ref):
+    """tests/golden/status.npz: ElementBase::get_total_circ / Points::get_total_impulse of the reference's Points<float>
+    (oracle/ref_driver.cpp: o3d_ref_totals) on three collections, and the bytes of the files the reference's StatusFile writes
+    when driven like Simulation::dump_stats_to_status (o3d_ref_status_lines): two data sets in one file, both formats."""
+    import tempfile
+    g = {}
+    cases = {"ring": W.example_case("single_vortex_ring_nv")[:2],
+             "leap": W.example_case("leapfrog_vortex_rings_nv", minrad=0.05, ips=0.015)[:2],
+             "cloud": W.random_cloud(20000, seed=77)[:2]}
+    for name, (x, s) in cases.items():
+        if name == "cloud":
+            s = (s * f32(1000.0)).astype(f32)
+        c, i = ref.totals(x, s)
+        g.update({f"{name}_x": x, f"{name}_s": s, f"{name}_circ": c, f"{name}_imp": i})
+    # the totals AFTER the reference's own convection steps (Convection::advect order 2 through its Points methods,
+    # o3d_ref_advect): 10 steps of the single ring as shipped, 100 steps of the thick leapfrogging rings. (The thin 210-particle
+    # ring is not a conservation case: after 100 steps the reference's own two builds differ by 0.07 in total circulation;
+    # the thick rings conserve circulation to 5e-9 of sum|s| and impulse to 1.3e-3.)
+    for name, steps in (("ring", 10), ("leap", 100)):
+        x0, s0, r, dt, fs = (W.example_case("single_vortex_ring_nv") if name == "ring" else
+                             W.example_case("leapfrog_vortex_rings_nv", minrad=0.05, ips=0.015))
+        x, s, e = x0.copy(), s0.copy(), np.ones(x0.shape[1], f32)
+        ref.advect(2, steps, dt, fs, x, s, r, e)
+        c, i = ref.totals(x, s)
+        g.update({f"{name}_steps": np.int32(steps), f"{name}_dt": np.float64(dt), f"{name}_r": r, f"{name}_circ_after": c, f"{name}_imp_after": i})
+    rng = np.random.Generator(np.random.MT19937(5))
+    nl = 7
+    vals = (rng.standard_normal((nl, 7)) * np.array([1, 1e-6, 1e-3, 1, 10, 1e4, 1e-9])).astype(f32)
+    vals[:, 0] = (np.arange(nl) % 4 * 0.002).astype(f32)     # time restarts with the second data set
+    vals[3, 1:] = [0.0, -0.0, 1.0, 123456.0, 1234567.0, 1e-5]  # the %g corner cases
+    nv = np.array([210, 210, 215, 1048524, 0, 7, 123456789], np.int32)
+    reset = np.array([0, 0, 0, 0, 1, 0, 0], np.int32)
+    g.update(status_vals=vals, status_nv=nv, status_reset=reset)
+    for fmt, tag in ((0, "dat"), (1, "csv")):
+        with tempfile.TemporaryDirectory() as d:
+            data = ref.status_lines(os.path.join(d, "status." + tag), fmt, vals, nv, reset)
+        g["status_" + tag] = np.frombuffer(data, np.uint8)
+    np.savez_compressed(os.path.join(OUT, "status.npz"), **g)
+
+
 def cores():
     """tests/golden/cores.npz: particles -> points from the three builds of the reference whose src/CoreFunc.h has
     another core function #defined (oracle/Makefile: libo3d_ref_{rm,exp,v2}.so) - the four kernel variants each,
@@ -187,6 +227,10 @@ def main():
         reflect(ref)
         print("reflect.npz", os.path.getsize(os.path.join(OUT, "reflect.npz")))
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "status":
+        status(ref)
+        print("status.npz", os.path.getsize(os.path.join(OUT, "status.npz")))
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "convection":
         convection(ref)
         print("convection.npz", os.path.getsize(os.path.join(OUT, "convection.npz")))
@@ -194,6 +238,7 @@ def main():
     convection(ref)
     reflect(ref)
     vtk(ref)
+    status(ref)
     rng = np.random.Generator(np.random.MT19937(99))
 
     # ---- single-interaction known answers (src/Kernels.h) ----

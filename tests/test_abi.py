@@ -30,7 +30,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in include/o3d_cuda.h but not exported"
     # and the binding table covers exactly the header
     assert sorted(_lib.SYMBOLS) == names
-    assert _lib.load().o3d_cuda_abi_version() == 2
+    assert _lib.load().o3d_cuda_abi_version() == 3
 
 
 def test_library_targets_sm100a_with_bulk_copy_and_packed_fma():
@@ -148,22 +148,41 @@ def test_squared_threshold_identity():
 
 def test_launch_plan_fills_the_gpu_at_the_benchmark_sizes():
     """Host logic of the launch shape (capi.cu: pp_shape through o3d_cuda_plan_pts_on_pts, no device needed): at every
-    size of the BASELINE sweep, whole or sharded over 2/4/8 GPUs, the chosen source split leaves at most 1.5 % of the
-    launch's waves of resident CTAs empty on a 148-SM B200, and the FP64 slab workspace stays small."""
+    size of the BASELINE sweep, whole or sharded over 2/4/8 GPUs, the persistent CTAs of a 148-SM B200 all stream the
+    same number of tiles +-1 (balance >= 99.95 % from 2 M up, >= 99.3 % at 256 K over 8 GPUs: stream-K: no last-wave quantisation at any size), at most grid-1 target blocks
+    are shared between CTAs, and the workspace is the same few MB whatever the size."""
     lib = _lib.load()
     from ctypes import byref, c_double, c_int, c_int64
     for n in (1 << 18, 1 << 19, 1 << 20, 1 << 21, 1 << 22, 1 << 23, 1 << 24):
         for gpus in (1, 2, 4, 8):
             nt = n // gpus
-            gx, sp, eff, ws = c_int64(), c_int(), c_double(), c_int64()
-            assert lib.o3d_cuda_plan_pts_on_pts(148, n, nt, 1, byref(gx), byref(sp), byref(eff), byref(ws)) == 0
-            assert gx.value == (nt + 255) // 256 and 1 <= sp.value <= 64
-            assert eff.value >= 0.985, (n, gpus, sp.value, eff.value)
-            assert ws.value == (sp.value * 12 * nt * 8 if sp.value > 1 else 0) and ws.value <= 2 << 30
-    # tiny target counts: split until the GPU is covered, never more slices than tiles
-    gx, sp, eff, ws = c_int64(), c_int(), c_double(), c_int64()
-    assert lib.o3d_cuda_plan_pts_on_pts(148, 100000, 320, 0, byref(gx), byref(sp), byref(eff), byref(ws)) == 0
-    assert gx.value == 1 and 32 <= sp.value <= 64
-    assert lib.o3d_cuda_plan_pts_on_pts(148, 700, 5, 1, byref(gx), byref(sp), byref(eff), byref(ws)) == 0
-    assert sp.value <= 2            # 700 sources are two 512-record tiles
+            grid, sp, bal, ws = c_int64(), c_int(), c_double(), c_int64()
+            assert lib.o3d_cuda_plan_pts_on_pts(148, n, nt, 1, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
+            assert grid.value == 444 and 0 <= sp.value <= 443
+            assert bal.value >= (0.9995 if n >= 1 << 21 else 0.993), (n, gpus, bal.value)   # one tile of granularity
+            assert ws.value == 444 * 2 * 12 * 256 * 8
+    # tiny target counts: the source tiles of the one target block are dealt out over the CTAs
+    grid, sp, bal, ws = c_int64(), c_int(), c_double(), c_int64()
+    assert lib.o3d_cuda_plan_pts_on_pts(148, 100000, 320, 0, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
+    assert grid.value == 196 and sp.value == 1            # 196 tiles of 512 sources, one block of 512 targets
+    assert lib.o3d_cuda_plan_pts_on_pts(148, 700, 5, 1, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
+    assert grid.value == 2 and sp.value == 1              # 700 sources are two 512-record tiles
+    assert lib.o3d_cuda_plan_pts_on_pts(148, 100, 100, 1, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
+    assert grid.value == 1 and sp.value == 0 and bal.value == 1.0
     assert lib.o3d_cuda_plan_pts_on_pts(0, 10, 10, 1, None, None, None, None) == 1   # O3D_ERR_INVALID
+
+
+def test_stream_k_bookkeeping_replayed_on_the_host():
+    """o3d_cuda_plan_check walks every CTA's tiles with the kernels' own bookkeeping (pp_ring_start / pp2_walk) and
+    every boundary with pp_fixup_kernel's: each (target block, source tile) unit consumed once, each partial segment in
+    its own workspace slot, each shared block finished once from exactly the slots written. Ragged shapes, every regime:
+    fewer units than CTAs, blocks spanning many CTAs, CTAs spanning many blocks, boundaries on block edges."""
+    lib = _lib.load()
+    rng = np.random.Generator(np.random.MT19937(5))
+    shapes = [(1, 1), (512, 256), (513, 257), (700, 5), (100000, 320), (1 << 20, 1 << 20), (1 << 20, 1 << 17), (1 << 22, 1 << 22),
+              (1 << 24, 1 << 21), (444 * 512, 256), (443 * 512, 512), (445 * 512, 256 * 3), (512 * 37, 256 * 444), (512 * 37, 256 * 12)]
+    shapes += [(int(rng.integers(1, 300000)), int(rng.integers(1, 300000))) for _ in range(60)]
+    for ns, nt in shapes:
+        for grad in (0, 1):
+            for sms in (148, 132, 1, 7):
+                assert lib.o3d_cuda_plan_check(sms, ns, nt, grad) == 0, (ns, nt, grad, sms)

@@ -147,6 +147,41 @@ def test_graph_replay_equals_eager_bit_for_bit(cuda_ctx):
         assert np.array_equal(outs[0][k], outs[1][k]), k
 
 
+def test_graph_survives_other_calls_that_grow_context_scratch(cuda_ctx):
+    """A captured step holds device addresses. Everything it points into - the stream-K workspace and the radius-range block
+    of the context, the collection's own state - is fixed-size or collection-owned, so calls that make the context's
+    grow-only scratch reallocate (a panel evaluation with a source split, a large points-on-points with few targets)
+    between two replays must not change the replayed result. Sizes are chosen so that the collection has shared target
+    blocks (it uses the workspace) and the interleaved calls need more scratch than anything before them."""
+    lib = cuda_ctx.lib
+    x, s, r = W.random_cloud(20000, seed=41, radius=0.05)
+    s = (s * f32(2000.0)).astype(f32)
+    outs = []
+    for graphs in (1, 0):
+        cuda_ctx.check(lib.o3d_cuda_set_graphs(cuda_ctx.h, graphs))
+        p = C.DeviceParticles(cuda_ctx).upload(x, s, r)
+        p.advect(2, 0.0, 0.01, (0.0, 0.0, 0.0), 3)
+        assert p.graph_active() == bool(graphs)
+        # other work on the same context: few targets against many sources / panels (scratch grows, d.work reallocates)
+        bx, bs, br = W.random_cloud(700000 + 100000 * graphs, seed=43)
+        tu, tg = np.zeros((3, 40), f32), np.zeros((9, 40), f32)
+        cuda_ctx.pts_on_pts(bx, br, bs, np.ascontiguousarray(bx[:, :40]), br[:40].copy(), tu, tg)
+        nodes, idx = W.icosphere(3, 0.5)
+        surf = I.Surfaces(np.ascontiguousarray(nodes.T), idx, W.panel_strengths(idx.shape[0], seed=3), I.active)
+        pu = np.zeros((3, 3000 + 500 * graphs), f32)
+        cuda_ctx.pan_on_pts(surf.x, surf.idx, surf.ts, surf.area, surf.ps[2], np.ascontiguousarray(bx[:, :pu.shape[1]]), pu, None)
+        q = C.DeviceParticles(cuda_ctx).upload(bx[:, :50000], bs[:, :50000], br[:50000])   # a second collection, other size
+        q.advect(1, 0.0, 0.01, (0.0, 0.0, 0.0), 2)
+        q.close()
+        p.advect(2, 0.03, 0.01, (0.0, 0.0, 0.0), 3)      # replays the step captured before all of that
+        assert p.graph_active() == bool(graphs)
+        outs.append(p.download())
+        p.close()
+    cuda_ctx.check(lib.o3d_cuda_set_graphs(cuda_ctx.h, 1))
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
 def test_resident_find_vels_equals_host_entry_point(cuda_ctx):
     """The resident path and the drop-in host-pointer path run the same kernels on the same packed records."""
     x, s, r = W.random_cloud(3000, seed=5)
