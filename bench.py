@@ -340,6 +340,19 @@ def run_ours(args, rank, world, local_rank):
                    "d2h_bytes_per_step": 12 * nloc * 4, "steps": e2e_steps, "ms_per_step": t_e2e / e2e_steps * 1e3,
                    "kernel_ms": tm["kernel_ms"], "h2d_ms": tm["h2d_ms"], "d2h_ms": tm["d2h_ms"], "launches_per_step": tm["launches"],
                    "api": "o3d_cuda_pts_on_pts (include/o3d_cuda.h) with pinned host buffers"}
+            # ... and with PAGEABLE host arrays - what the patched reference passes (std::vector storage): the context's
+            # pinned staging ring carries them
+            pg = [np.array(a, copy=True) for a in (x_h, s_h, r_h, x_h[:, lo:hi], r_h[lo:hi])] + [np.zeros((3, nloc), np.float32), np.zeros((9, nloc), np.float32)]
+            pg_steps = 1 if long_steps else e2e_steps
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(pg_steps):
+                eng.ctx.pts_on_pts(pg[0], pg[2], pg[1], pg[3], pg[4], pg[5], pg[6])
+            t_pg = max_over_ranks(time.perf_counter() - t0)
+            tmp = eng.ctx.last_timing()
+            e2e["pageable"] = {"value": float(n) * float(n) * pg_steps / t_pg, "steps": pg_steps, "ms_per_step": t_pg / pg_steps * 1e3,
+                               "kernel_ms": tmp["kernel_ms"], "h2d_ms": tmp["h2d_ms"], "d2h_ms": tmp["d2h_ms"],
+                               "of_pinned": (float(n) * float(n) * pg_steps / t_pg) / e2e["value"]}
         flops = float(n) * nloc * FLOPS_PER_INTERACTION + 12.0 * nloc
         achieved = flops / (kern_ms_max * 1e-3) * 1e-12
         return dict(n=n, nloc=nloc, value=value, total_ms=total_ms, steps=steps, launches=launches, clocks=clocks, t_wall=t_wall,
@@ -394,6 +407,62 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_inproc(args):
+    """--inproc N: ONE process driving N GPUs through o3d_cuda_create(ndev = N) - what the single-process Omega3D does with
+    O3D_CUDA_NDEV - with PAGEABLE host arrays, end to end through o3d_cuda_pts_on_pts: sources cross PCIe once (device 0) and
+    reach the other devices as packed records over NVLink; every device uploads its target slice, computes, returns its
+    slice. Prints one JSON line whose value IS the end-to-end rate (there is no device-resident leg in this mode)."""
+    import torch
+    from omega3d_b200 import influence as I
+    from omega3d_b200 import workloads as W
+    if not torch.cuda.is_available() or torch.cuda.device_count() < args.inproc:
+        raise SystemExit(f"bench.py --inproc {args.inproc}: needs {args.inproc} CUDA devices")
+    n, g = args.n, args.inproc
+    x, s, r = W.random_cloud(n)
+    u, ug = np.zeros((3, n), np.float32), np.zeros((9, n), np.float32)
+    ctx = I.CudaContext(tuple(range(g)))
+    samplers = [ClockSampler(k) for k in range(g)]
+    for _ in range(max(1, min(args.warmup, 2))):
+        ctx.pts_on_pts(x, r, s, x, r, u, ug)
+    u[:] = 0; ug[:] = 0
+    for sm in samplers:
+        sm.start()
+    t0 = time.perf_counter()
+    ks = []
+    for _ in range(args.steps):
+        ctx.pts_on_pts(x, r, s, x, r, u, ug)
+        ks.append(ctx.last_timing())
+    dt = time.perf_counter() - t0
+    clocks = [sm.stop() for sm in samplers]
+    value = float(n) * float(n) * args.steps / dt
+    parity = None
+    if not args.no_cpu:
+        sel = W.strided_subset(n, 512)
+        eng, kind, threads, _ = cpu_engine()
+        ru, rg = np.zeros((3, sel.size), np.float32), np.zeros((9, sel.size), np.float32)
+        eng.pts_on_pts(x, r, s, np.ascontiguousarray(x[:, sel]), np.ascontiguousarray(r[sel]), ru, rg)
+        parity = parity_stats(u[:, sel] / args.steps, ug[:, sel] / args.steps, ru, rg)
+        parity.update({"targets_checked": int(sel.size), "against": kind, "vel_tol": 1e-5, "grad_tol": 1e-4,
+                       "ok": parity["vel_err"] <= 1e-5 and parity["grad_err"] <= 1e-4})
+    nloc = -(-n // g)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": g, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 kernel / f64 accumulate", "data": "synthetic", "impl": "ours-inproc",
+            "config": {"workload": f"synthetic uniform vortex-particle cloud N={n}, vel+grad blob-on-blob WL core", "n_particles": n,
+                       "parallelism": f"one process, one context over {g} GPUs (o3d_cuda_create ndev={g}); targets partitioned, sources "
+                                      "uploaded once and replicated as packed records over NVLink", "host_memory": "pageable"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": (7 * n + 16 * n) * 4, "d2h_bytes_per_step": 12 * n * 4,
+                    "kernel_ms": float(np.mean([k["kernel_ms"] for k in ks])), "h2d_ms": float(np.mean([k["h2d_ms"] for k in ks])),
+                    "d2h_ms": float(np.mean([k["d2h_ms"] for k in ks])),
+                    "api": "o3d_cuda_pts_on_pts (include/o3d_cuda.h), pageable host arrays, multi-device context"},
+            "tflops_at_70": value * FLOPS_PER_INTERACTION * 1e-12,
+            "gpu_launches": int(sum(k["launches"] for k in ks)), "targets_per_gpu": nloc,
+            "clocks": clocks[0], "clocks_all": clocks}
+    if parity is not None:
+        line["parity"] = parity
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -407,12 +476,16 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-no-warmup", action="store_true", help="time the first end-to-end call too (very large N)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg")
+    ap.add_argument("--inproc", type=int, default=0, help="N > 0: one process, one context over N GPUs, pageable host arrays (end to end only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.inproc > 0:
+        run_inproc(args)
         return
     if world != args.gpus and rank == 0 and args.gpus > 1:
         print(f"bench.py: --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})", file=sys.stderr)

@@ -194,12 +194,51 @@ int o3d_cuda_particles_find_vels(o3d_ctx* ctx, o3d_particles* p, const double* f
  * the last combined stage velocity) and the gradient the first-stage gradient of the last step. */
 int o3d_cuda_particles_advect(o3d_ctx* ctx, o3d_particles* p, int order, double time, double dt, const double* fs,
                               int nsteps, double* flops_out);
+/* panels -> points (o3d_cuda_pan_on_pts, bodies attached to resident collections) pools the (point, panel) pairs that need
+ * subdivision per warp and lets all 32 lanes drain the pool (default); off = every lane walks only its own pairs, the
+ * round-1 kernel, kept for A/B measurements. Same leaves, same counts; FP32 terms of a tile regrouped. */
+int o3d_cuda_set_panel_queue(o3d_ctx* ctx, int on);
+/* Host arrays of the entry points above may be pageable (the reference's std::vector storage) or pinned. Pageable arrays
+ * travel through a ring of pinned slots the context owns (4 x 8 MB per device; helper threads fill the next slot while the
+ * DMA engine moves the previous one; O3D_CUDA_COPY_THREADS sets their number); pinned ones go to the DMA engine directly.
+ * off = hand every pointer to cudaMemcpyAsync as it comes (the driver's own bounce buffers) - for A/B measurements. */
+int o3d_cuda_set_host_staging(o3d_ctx* ctx, int on);
 /* CUDA-graph replay of repeated steps is on by default; off = launch every kernel individually (same results,
  * bit for bit - tests compare the two). o3d_cuda_particles_graph_active: 1 if the collection holds a captured step. */
 int o3d_cuda_set_graphs(o3d_ctx* ctx, int on);
 int o3d_cuda_particles_graph_active(const o3d_particles* p);
 /* sqrt(max |s|^2) (ElementBase::get_max_str, src/ElementBase.h:339-351) and max elongation (src/Points.h:523-532). */
 int o3d_cuda_particles_stats(o3d_ctx* ctx, o3d_particles* p, float* max_str, float* max_elong);
+
+
+/* ---- a static body attached to a resident collection (Convection::find_vels / advect with boundaries) ---------------
+ * With a body attached, o3d_cuda_particles_find_vels adds panels -> particles to the particle sums (src/Convection.h:157-167)
+ * and o3d_cuda_particles_advect runs the reference's sequence for a system with a boundary: before every derivative
+ * evaluation the BEM right-hand side of that state - panel-centre velocities from the particles, zero_vels /
+ * points_affect_panels / finalize_vels(fs) (src/BEMHelper.h:83-103) - is formed on the device and handed to `solve`, which
+ * returns the panels' total vortex strengths (and source strengths): the solve itself is the reference's host code
+ * (src/BEM.h, Eigen GMRES) and stays there; after every move clear_inner_layer(1, body, particles, cutoff_mult, ips)
+ * (src/Reflect.h:625-655) runs on the moved state. Particle arrays never leave the device; per evaluation 3 np floats go
+ * to the host and 4 np come back.
+ *
+ * solve(user, np, pu, tsx, tsy, tsz, sss, have_source): pu = 3 x np floats (u | v | w rows) IN; tsx.. = np floats each OUT
+ * (Surfaces::get_str after set_str, src/Surfaces.h:267-335); sss = np source strengths OUT, used iff *have_source is set
+ * non-zero. Returns 0, anything else aborts the call with O3D_ERR_CUDA. solve may be NULL: the strengths then stay what
+ * o3d_cuda_particles_set_body_strengths last set (zero after set_body).
+ * nodes SoA (nn), idx 3 per panel, area np, nrm 3 x np (x | y | z rows) as the reference's Surfaces holds them. */
+typedef int (*o3d_bem_solve_fn)(void* user, int64_t np, const float* pu, float* tsx, float* tsy, float* tsz, float* sss, int* have_source);
+int o3d_cuda_particles_set_body(o3d_ctx* ctx, o3d_particles* p, int64_t nn, const float* nx, const float* ny, const float* nz,
+                                int64_t np, const uint32_t* idx, const float* area, const float* nrm, float cutoff_mult, float ips,
+                                o3d_bem_solve_fn solve, void* user);
+int o3d_cuda_particles_clear_body(o3d_ctx* ctx, o3d_particles* p);
+int o3d_cuda_particles_set_body_strengths(o3d_ctx* ctx, o3d_particles* p, const float* tsx, const float* tsy, const float* tsz,
+                                          const float* sss /* NULL: no source sheet */);
+/* The right-hand-side velocities of the current state alone (no solve, strengths untouched): np floats each. */
+int o3d_cuda_particles_body_vels(o3d_ctx* ctx, o3d_particles* p, const double* fs, float* pu, float* pv, float* pw);
+/* clear_inner_layer on the resident positions, outside a step (src/Simulation.cpp:839 after diffusion). */
+int o3d_cuda_particles_clear_inner(o3d_ctx* ctx, o3d_particles* p, int64_t* num_moved);
+/* Of the last o3d_cuda_particles_advect: particles pushed out by its clear-inner passes, BEM solves requested. */
+int o3d_cuda_particles_body_counters(const o3d_particles* p, int64_t* moved, int* solves);
 
 
 /* ---- status-file quantities and writer (src/StatusFile.cpp, src/Simulation.cpp:851-924) ------------ */

@@ -44,6 +44,12 @@ SYMBOLS = {
     "o3d_cuda_particles_find_vels": (c_int, [c_void_p, c_void_p, POINTER(c_double), c_int, POINTER(c_double)]),
     "o3d_cuda_particles_advect": (c_int, [c_void_p, c_void_p, c_int, c_double, c_double, POINTER(c_double), c_int, POINTER(c_double)]),
     "o3d_cuda_particles_stats": (c_int, [c_void_p, c_void_p, POINTER(ctypes.c_float), POINTER(ctypes.c_float)]),
+    "o3d_cuda_particles_set_body": (c_int, [c_void_p, c_void_p, c_int64, _P, _P, _P, c_int64, _P, _P, _P, ctypes.c_float, ctypes.c_float, _P, _P]),
+    "o3d_cuda_particles_clear_body": (c_int, [c_void_p, c_void_p]),
+    "o3d_cuda_particles_set_body_strengths": (c_int, [c_void_p, c_void_p, _P, _P, _P, _P]),
+    "o3d_cuda_particles_body_vels": (c_int, [c_void_p, c_void_p, POINTER(c_double), _P, _P, _P]),
+    "o3d_cuda_particles_clear_inner": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
+    "o3d_cuda_particles_body_counters": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int)]),
     "o3d_cuda_particles_totals": (c_int, [c_void_p, c_void_p, POINTER(c_double), POINTER(c_double)]),
     "o3d_cuda_status_open": (c_int, [c_char_p, c_int, POINTER(c_void_p)]),
     "o3d_cuda_status_close": (None, [c_void_p]),
@@ -67,6 +73,8 @@ SYMBOLS = {
     "o3d_cuda_tuned_kernels": (c_int, [c_void_p]),
     "o3d_cuda_plan_pts_on_pts": (c_int, [c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "o3d_cuda_plan_check": (c_int, [c_int, c_int64, c_int64, c_int]),
+    "o3d_cuda_set_host_staging": (c_int, [c_void_p, c_int]),
+    "o3d_cuda_set_panel_queue": (c_int, [c_void_p, c_int]),
     "o3d_cuda_set_core_func": (c_int, [c_void_p, c_int]),
     "o3d_cuda_core_func": (c_int, [c_void_p]),
     "o3d_cuda_set_profiling": (c_int, [c_void_p, c_int]),

@@ -73,6 +73,45 @@ class PanelOperator:
             pass
 
 
+def vels_to_rhs_panels(targ: Surfaces):
+    """src/RHS.h:55-121 with three unknowns per panel: the negated panel-centre velocity along x1, x2 and the normal, in
+    float, interleaved per panel."""
+    u = targ.pu
+    rhs = np.empty((targ.np_, 3), f32)
+    for k, b in enumerate((targ.b1, targ.b2, targ.nrm)):
+        rhs[:, k] = -((u[0] * b[0] + u[1] * b[1]).astype(f32) + u[2] * b[2]).astype(f32)
+    return rhs.reshape(-1)
+
+
+class DenseBEM:
+    """The reference's own arrangement (src/BEM.h:117-203): the dense matrix from panels_on_panels_coeff, assembled once on
+    the GPU, and a host solve. `A` is column-major (3 np) x (3 np) as the C ABI returns it; the factorisation is numpy's
+    (LAPACK, double) where the reference runs Eigen's GMRES to float epsilon - the same linear system."""
+
+    def __init__(self, A, n):
+        self.A = np.asarray(A, np.float64).reshape(n, n).T      # column-major -> rows are target unknowns
+        self.b = None
+        self.strengths = None
+
+    def set_rhs(self, b):
+        self.b = np.ascontiguousarray(b, f32)
+
+    def getStrengths(self):
+        return self.strengths
+
+    def solve(self):
+        self.strengths = np.linalg.solve(self.A, self.b.astype(np.float64)).astype(f32)
+        return self.strengths
+
+
+def solve_bem_for(targ: Surfaces, bem):
+    """The host half of solve_bem (src/BEMHelper.h:103-262) for one static reactive surface whose panel-centre velocities
+    targ.pu are already final: right-hand side, solve, strengths back into the surface."""
+    bem.set_rhs(vels_to_rhs_panels(targ))
+    bem.solve()
+    targ.set_str(bem.getStrengths())
+
+
 class BEM:
     """src/BEM.h:44-73 around a matrix-free operator: set_rhs, solve, getStrengths."""
 

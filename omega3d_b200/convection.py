@@ -13,7 +13,8 @@ Anything this module cannot run on the GPU raises; there is no host arithmetic i
 from __future__ import annotations
 
 import ctypes
-from ctypes import byref, c_double, c_float, c_void_p
+import math
+from ctypes import POINTER, byref, c_double, c_float, c_int, c_int64, c_void_p
 
 import numpy as np
 
@@ -24,6 +25,12 @@ from .influence import (CudaContext, ExecEnv, O3DError, Points, ResultsType, _pt
 def _fs(fs):
     a = (c_double * 3)(*[float(v) for v in fs])
     return a
+
+
+# include/o3d_cuda.h: o3d_bem_solve_fn
+SOLVE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int64, POINTER(c_float), POINTER(c_float), POINTER(c_float), POINTER(c_float),
+                            POINTER(c_float), POINTER(c_int))
+CLEAR_INNER_CUTOFF = 0.5 / math.sqrt(2.0 * math.pi)     # every clear_inner_layer call of src/Convection.h
 
 
 class DeviceParticles:
@@ -98,10 +105,70 @@ class DeviceParticles:
     def advect(self, order: int, time: float, dt: float, fs=(0.0, 0.0, 0.0), nsteps: int = 1):
         """`nsteps` x Convection::advect (order 1: :232-262, 2: Ralston :349-425, 3: :431-556), all on the device."""
         fl = c_double()
-        self.ctx.check(self.lib.o3d_cuda_particles_advect(self.ctx.h, self.h, int(order), float(time), float(dt), _fs(fs),
-                                                          int(nsteps), byref(fl)))
+        rc = self.lib.o3d_cuda_particles_advect(self.ctx.h, self.h, int(order), float(time), float(dt), _fs(fs), int(nsteps), byref(fl))
+        if rc != 0 and getattr(self, "_cb_error", None) is not None:
+            err, self._cb_error = self._cb_error, None
+            raise err
+        self.ctx.check(rc)
         self.flops = fl.value
         return fl.value
+
+    # ---- a static body attached to the collection (include/o3d_cuda.h: o3d_cuda_particles_set_body) ----
+    def set_body(self, surf, ips: float, solve=None, cutoff_mult: float = CLEAR_INNER_CUTOFF):
+        """surf: influence.Surfaces. solve(pu (3,np) float32 - the finalized panel-centre velocities of the state) must return
+        (ts (3,np), sss (np,) or None): the panels' total vortex strengths and source strengths - the BEM solve, host code as in
+        the reference. None: strengths stay what set_body_strengths last set."""
+        self._cb_error = None
+        cb = None
+        if solve is not None:
+            def _cb(user, np_, pu, tsx, tsy, tsz, sss, have_source):
+                try:
+                    v = np.ctypeslib.as_array(pu, shape=(3 * np_,)).reshape(3, np_).copy()
+                    ts, src = solve(v)
+                    for dst, row in zip((tsx, tsy, tsz), ts):
+                        np.ctypeslib.as_array(dst, shape=(np_,))[:] = row
+                    if src is not None:
+                        np.ctypeslib.as_array(sss, shape=(np_,))[:] = src
+                        have_source[0] = 1
+                    return 0
+                except Exception as e:          # noqa: BLE001 - must not unwind through the C frames
+                    self._cb_error = e
+                    return 1
+            cb = SOLVE_FN(_cb)
+        self._cb = cb                            # keep the trampoline alive as long as the body is attached
+        self._body = surf
+        self.ctx.check(self.lib.o3d_cuda_particles_set_body(
+            self.ctx.h, self.h, surf.x.shape[1], _ptr(surf.x[0]), _ptr(surf.x[1]), _ptr(surf.x[2]), surf.np_, _ptr(surf.idx),
+            _ptr(surf.area), _ptr(surf.nrm), c_float(float(f32(cutoff_mult))), c_float(float(f32(ips))),
+            ctypes.cast(cb, c_void_p) if cb is not None else None, None))
+        return self
+
+    def clear_body(self):
+        self.ctx.check(self.lib.o3d_cuda_particles_clear_body(self.ctx.h, self.h))
+        self._cb = self._body = None
+
+    def set_body_strengths(self, ts, sss=None):
+        ts = np.ascontiguousarray(ts, f32)
+        sss = None if sss is None else np.ascontiguousarray(sss, f32)
+        self.ctx.check(self.lib.o3d_cuda_particles_set_body_strengths(self.ctx.h, self.h, _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(sss)))
+
+    def body_vels(self, fs=(0.0, 0.0, 0.0)):
+        """Finalized panel-centre velocities induced by the resident particles (+ freestream): the BEM right-hand side before
+        projection (src/BEMHelper.h:83-103). Returns (3,np) float32."""
+        pu = np.zeros((3, self._body.np_), f32)
+        self.ctx.check(self.lib.o3d_cuda_particles_body_vels(self.ctx.h, self.h, _fs(fs), _ptr(pu[0]), _ptr(pu[1]), _ptr(pu[2])))
+        return pu
+
+    def clear_inner(self) -> int:
+        n = c_int64()
+        self.ctx.check(self.lib.o3d_cuda_particles_clear_inner(self.ctx.h, self.h, byref(n)))
+        return n.value
+
+    def body_counters(self):
+        """(particles pushed out by the clear-inner passes, BEM solves requested) of the last advect call."""
+        m, k = c_int64(), c_int()
+        self.lib.o3d_cuda_particles_body_counters(self.h, byref(m), byref(k))
+        return m.value, k.value
 
     def graph_active(self) -> bool:
         return bool(self.lib.o3d_cuda_particles_graph_active(self.h))
@@ -156,10 +223,29 @@ class Convection:
         self._store(vort[0], ("u", "ug") if ResultsType(results).compute_grad() else ("u",))
 
     def advect(self, time, dt, fs, ips, vort, bdry=(), fldpt=(), bem=None, nsteps: int = 1):
-        if bdry or fldpt or len(vort) != 1:
-            raise O3DError("Convection.advect on the device handles particle-only systems (one collection, no boundaries, "
-                           "no field points)")
+        """src/Convection.h:208-228. `bdry` may hold ONE static reactive Surfaces together with `bem`, an object with
+        set_rhs / solve / getStrengths over that surface's self-influence system (bem.DenseBEM, bem.BEM): every derivative
+        evaluation then solves the BEM for the state first (find_derivs) - right-hand side formed on the device, the solve
+        here on the host as in the reference - and every move is followed by clear_inner_layer. The particles stay resident
+        throughout."""
+        from .bem import solve_bem_for
+        if fldpt or len(vort) != 1 or len(bdry) > 1:
+            raise O3DError("Convection.advect on the device handles one particle collection, at most one static body, no field points")
         d = self._resident(vort[0])
-        d.advect(self.convection_order, time, dt, fs, nsteps)
+        if bdry:
+            surf = bdry[0]
+            if bem is None:
+                raise O3DError("Convection.advect: a boundary needs its BEM system")
+
+            def solve(pu):
+                surf.pu[:] = pu
+                solve_bem_for(surf, bem)
+                return surf.ts, surf.ps[2]
+            d.set_body(surf, ips, solve)
+        try:
+            d.advect(self.convection_order, time, dt, fs, nsteps)
+        finally:
+            if bdry:
+                d.clear_body()
         self._store(vort[0], ("x", "s", "elong", "u", "ug"))
         return d.flops

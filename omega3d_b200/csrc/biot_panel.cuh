@@ -360,6 +360,136 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_kernel(const PanPtsArgs p) {
   }
 }
 
+// panels -> points with a WARP-LEVEL WORK QUEUE for the pairs that subdivide (the product kernel; pan_pts_kernel above is kept
+// as the measured baseline - o3d_cuda_set_panel_queue). Phase A is the same convergent pass over the tile. What it defers
+// differs from lane to lane by an order of magnitude - a point next to the body is near dozens of panels, a point in the wake
+// near none - and a lane that walks only its own list leaves the others idle (ncu on the baseline: 16 of 32 lanes active,
+// profiles/r01_pan_pts_ncu_v9.txt). Here the warp pools its deferred (point, panel) items: every lane writes its items to a
+// shared list (owner lane | panel, in owner order), the warp takes them 32 at a time - lane l walks item base + l for
+// WHOSEVER point it belongs to - and the item's partial sums go back through shared memory, where every owner adds the
+// partials of its own items in item order. Per target the FP32 terms of a tile are only regrouped (one partial sum per deferred
+// panel instead of one running sum); leaf and split counts are those of the reference.
+template <bool GRAD, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pan_pts_queue_kernel(const PanPtsArgs p) {
+  constexpr int NA = PanAcc<GRAD>::N;
+  constexpr int NS = GRAD ? 12 : 3;
+  constexpr int NW = BLOCK / 32;
+  constexpr int RET = NA + 1;                                   // row stride of the return buffer: odd, conflict-free columns
+  __shared__ alignas(16) float4 tiles[NW][kPanTile * kPanRec];  // per-warp panel tile (5 KB)
+  __shared__ unsigned short lists[NW][32 * kPanTile];           // per-warp item list: owner << 6 | panel (4 KB)
+  __shared__ float rets[NW][32 * RET];                          // per-warp partial sums of the 32 items in flight
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* tile = tiles[warp];
+  unsigned short* list = lists[warp];
+  float* ret = rets[warp];
+
+  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int k0 = blockIdx.y * per;
+  const int k1 = min(p.ntiles, k0 + per);
+
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  const int64_t ic = min(i, p.nt - 1);
+  const float tx = p.tx[ic], ty = p.ty[ic], tz = p.tz[ic];
+  const bool live = i < p.nt;                                   // clamped duplicate threads defer nothing and count nothing
+
+  float acc[NA];
+  double sum[NS];
+  unsigned counts[2] = {0u, 0u};
+#pragma unroll
+  for (int k = 0; k < NA; ++k) acc[k] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < NS; ++k) sum[k] = 0.0;
+
+  for (int k = k0; k < k1; ++k) {
+    __syncwarp();
+    const float4* g = p.pan + (size_t)k * (kPanTile * kPanRec);
+#pragma unroll
+    for (int e = lane; e < kPanTile * kPanRec; e += 32) tile[e] = g[e];
+    __syncwarp();
+    // (A) every panel's level-0 test and, where the pair is well separated, its single leaf
+    unsigned long long near = 0ull;
+    unsigned leaves0 = 0u;
+#pragma unroll 2
+    for (int j = 0; j < kPanTile; ++j) {
+      const float4 r2 = tile[j * kPanRec + 2], r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
+      if (pan_node<GRAD>(r3.y, r3.z, r3.w, r4.z, false, tx, ty, tz, r2.y, r2.z, r2.w, r3.x, acc)) leaves0 += 1;
+      else near |= 1ull << j;
+    }
+    if (live) counts[0] += leaves0;
+    else near = 0ull;
+    // (B) pool the deferred pairs of the warp
+    const int mine = __popcll(near);
+    int first = mine;                                            // exclusive prefix over the lanes
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, first, off);
+      if (lane >= off) first += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, first, 31);
+    first -= mine;
+    if (total == 0) {
+      pan_promote<GRAD>(acc, sum);
+      continue;
+    }
+    {
+      unsigned long long m = near;
+      int at = first;
+      while (m) {
+        const int j = __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+        list[at++] = (unsigned short)((lane << 6) | j);
+      }
+    }
+    __syncwarp();
+    for (int base = 0; base < total; base += 32) {
+      const int gi = base + lane;
+      const bool have = gi < total;
+      const unsigned e = have ? list[gi] : (unsigned)(lane << 6);
+      const int owner = (int)(e >> 6), j = (int)(e & 63u);
+      const float ox = __shfl_sync(0xffffffffu, tx, owner), oy = __shfl_sync(0xffffffffu, ty, owner), oz = __shfl_sync(0xffffffffu, tz, owner);
+      float part[NA];
+#pragma unroll
+      for (int q = 0; q < NA; ++q) part[q] = 0.0f;
+      if (have) {
+        const float4 r0 = tile[j * kPanRec], r1 = tile[j * kPanRec + 1], r2 = tile[j * kPanRec + 2],
+                     r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
+        const Tri t{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+        pan_subdivide<GRAD>(t, r4.z, r2.y, r2.z, r2.w, r3.x, ox, oy, oz, part, counts);
+      }
+      __syncwarp();                                              // the previous batch's partials have been consumed
+#pragma unroll
+      for (int q = 0; q < NA; ++q) ret[lane * RET + q] = part[q];
+      __syncwarp();
+      // every owner adds the partials of its own items of this batch, in item order: slots [a, b) of the batch
+      const int a = max(first, base) - base, b = min(first + mine, base + 32) - base;
+      for (int sl = a; sl < b; ++sl) {
+#pragma unroll
+        for (int q = 0; q < NA; ++q) acc[q] += ret[sl * RET + q];
+      }
+    }
+    pan_promote<GRAD>(acc, sum);
+  }
+
+  add_counts(p.counts, counts);
+  if (!live) return;
+  if (p.nsplit > 1) {
+    double* slab = p.partial + (size_t)blockIdx.y * NS * p.nt;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) slab[(size_t)k * p.nt + i] = sum[k];
+  } else {
+    p.tu[i] = (float)((double)p.tu[i] + sum[0]);
+    p.tv[i] = (float)((double)p.tv[i] + sum[1]);
+    p.tw[i] = (float)((double)p.tw[i] + sum[2]);
+    if constexpr (GRAD) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        float* g = p.tug + (size_t)k * p.tug_stride + i;
+        *g = (float)((double)*g + sum[3 + k]);
+      }
+    }
+  }
+}
+
 // ---- particles -> panels (BEM right-hand side) ---------------------------------------------------------
 // One target PANEL per thread (its triangle stays in registers); the particles stream through shared
 // memory in the packed pair-interleaved layout of biot_pp.cuh (positions negated). The particle axis is

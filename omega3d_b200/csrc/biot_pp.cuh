@@ -139,6 +139,11 @@ struct PPArgs {
   float* tug;             // 9 rows of stride tug_stride, or nullptr
   int64_t tug_stride;
   double* partial;        // [gridDim.x][kPPSlots][12 or 3][BLOCK * T] FP64: sums of the target blocks this CTA shares
+  double* acc64;          // nullptr: results are added into tu/tv/tw/tug (read-modify-write). Otherwise the FP64 sums are STORED
+                          // here, [12 or 3][acc_stride], and the outputs are not touched: the host entry points add them to
+                          // the caller's initial values afterwards (pp_accumulate_kernel), so that the upload of those values
+                          // overlaps the kernel instead of preceding it
+  int64_t acc_stride;
   float sign;             // +1
   const uint32_t* radius_range;  // pp_scan_kernel output, or nullptr: no uniform-radius fast path
 };
@@ -255,6 +260,16 @@ __device__ __forceinline__ void pp_store(const PPArgs& p, const int b, const boo
     return;
   }
   const int64_t base = (int64_t)b * PER + threadIdx.x;
+  if (p.acc64) {
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int64_t i = base + (int64_t)t * BLOCK;
+      if (i >= p.nt) continue;
+#pragma unroll
+      for (int k = 0; k < NS; ++k) p.acc64[(size_t)k * p.acc_stride + i] = sum[t][k];
+    }
+    return;
+  }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int64_t i = base + (int64_t)t * BLOCK;
@@ -278,7 +293,8 @@ __device__ __forceinline__ void pp_store(const PPArgs& p, const int b, const boo
 // CTAs j, j+1, ... that start inside the block - and finish the block: out = float(double(out) + sign * sum).
 // blockDim.x = targets per block (BLOCK * T of the main kernel).
 __global__ void pp_fixup_kernel(const int nrows, const PPPlan plan, const int64_t nt, const double* __restrict__ partial,
-                                float* tu, float* tv, float* tw, float* tug, const int64_t tug_stride, const float sign) {
+                                float* tu, float* tv, float* tw, float* tug, const int64_t tug_stride, const float sign,
+                                double* acc64, const int64_t acc_stride) {
   const int j = blockIdx.x + 1;
   const int64_t cut = plan.begin(j);
   const int64_t b = cut / plan.ntiles, start = b * plan.ntiles, end = start + plan.ntiles;
@@ -293,8 +309,24 @@ __global__ void pp_fixup_kernel(const int nrows, const PPPlan plan, const int64_
     double acc = partial[((size_t)(j - 1) * kPPSlots + (prev == start ? 0 : 1)) * slot_elems + (size_t)k * per + threadIdx.x];
     for (int c = j; c < plan.P && plan.begin(c) < end; ++c)
       acc += partial[((size_t)c * kPPSlots) * slot_elems + (size_t)k * per + threadIdx.x];
+    if (acc64) {
+      acc64[(size_t)k * acc_stride + i] = acc;
+      continue;
+    }
     float* o = k == 0 ? tu + i : k == 1 ? tv + i : k == 2 ? tw + i : tug + (size_t)(k - 3) * tug_stride + i;
     *o = (float)((double)*o + (double)sign * acc);
+  }
+}
+
+// out[k][i] = float(double(out[k][i]) + sign * acc64[k][i]): the read-modify-write of the kernels' epilogue as its own pass, for
+// launches that stored their FP64 sums (PPArgs::acc64). Same operation, same rounding: the bits are those of the fused path.
+__global__ void pp_accumulate_kernel(const int nrows, const int64_t nt, const double* __restrict__ acc64, const int64_t acc_stride,
+                                     float* tu, float* tv, float* tw, float* tug, const int64_t tug_stride, const float sign) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nt) return;
+  for (int k = 0; k < nrows; ++k) {
+    float* o = k == 0 ? tu + i : k == 1 ? tv + i : k == 2 ? tw + i : tug + (size_t)(k - 3) * tug_stride + i;
+    *o = (float)((double)*o + (double)sign * acc64[(size_t)k * acc_stride + i]);
   }
 }
 
@@ -337,11 +369,12 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y
 template <bool GRAD, bool UNI>
 __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
                                              const float2 tx, const float2 ty, const float2 tz, const float2 tr2,
-                                             float2 (&acc)[PPAcc<GRAD>::N]) {
+                                             const float k15, const float k75, float2 (&acc)[PPAcc<GRAD>::N]) {
 #if O3D_PP_POW
 #if O3D_PP_POW == 2
-  // scalar constants: ptxas reads them as 32-bit broadcast operands (.F32) instead of 64-bit pairs
-  const float k15 = 1.5f * tr2.x, k75 = -7.5f * tr2.x;
+  // k15 = 1.5 r2, k75 = -7.5 r2 (UNI only): scalar constants, which ptxas reads as 32-bit broadcast operands (.F32) instead of
+  // 64-bit pairs. They arrive as arguments, formed once per kernel and passed through a warp reduction (pp2_walk): inside the
+  // loop they would be re-derived from r2 on every trip (two FMUL, and moves between the register files) to save two registers
   const float2 tk = f2(k15, k15), tk5 = f2(k75, k75);
 #else
   const float2 tk = __fmul2_rn(f2(1.5f, 1.5f), tr2), tk5 = __fmul2_rn(f2(-7.5f, -7.5f), tr2);   // UNI only; loop-invariant (hoisted)
@@ -439,15 +472,84 @@ __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, c
   }
 }
 
-// The whole share of one persistent CTA: ONE loop over its tiles (the nest is two deep - tiles, source pairs - like a
-// one-block-per-CTA kernel's, which is the shape ptxas keeps the inner loop's counter and LDS addresses in uniform registers
-// for); the target block changes inside that loop, at the tiles where a segment starts / ends. The UNI flag is warp-uniform,
-// so the two instantiations are two straight-line copies of the loop selected once per kernel.
+// Per-target-block state of a persistent CTA's walk (pp2_walk / ppc_kernel)
+struct PPBlock {
+  int b, kt;        // target block and source tile of the current unit
+  bool seg_first;   // the current segment is the CTA's first
+  bool fresh;       // the current tile starts a segment: (re)load the targets, clear the FP64 sums
+};
+
+// One tile of the walk, out of ring buffer BUF. BUF is a template argument - the walk alternates two copies of this body - so
+// that every shared-memory address of the inner loop is [uniform base + immediate] with a base that does not depend on the tile:
+// with a run-time buffer index ptxas re-derives the buffer's address (a chain of five uniform-datapath instructions) at the
+// top of every trip of the inner loop, ahead of its first LDS, and at three warps per scheduler that latency is exposed (+3 %).
+template <int BUF, int T, bool GRAD, bool UNI, int BLOCK>
+__device__ __forceinline__ void pp2_tile(const PPArgs& p, PPWalk& w, PPBlock& s, float4 (&tile)[2][kTile * 2], uint64_t (&full)[2],
+                                         const float r2u, const float k15, const float k75, float2 (&tx)[T], float2 (&ty)[T],
+                                         float2 (&tz)[T], float2 (&tr2)[T],
+                                         float2 (&acc)[T][PPAcc<GRAD>::N], double (&sum)[T][GRAD ? 12 : 3]) {
+  constexpr int NA = PPAcc<GRAD>::N;
+  constexpr int NS = GRAD ? 12 : 3;
+  constexpr int U = GRAD ? kPPUnrollGrad : kPPUnrollVel;
+  if (s.fresh) {
+    const int64_t base = (int64_t)s.b * (BLOCK * T) + threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
+      tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
+      const float r = p.tr ? p.tr[i] : 0.0f;
+      tr2[t] = UNI ? f2(r2u, r2u) : f2(r * r, r * r);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
+    }
+  }
+  pp_ring_wait(full, w.kring);
+  const float4* __restrict__ src = tile[BUF];
+#pragma unroll(U)
+  for (int j = 0; j < kTile / 2; ++j) {
+    const float4 q0 = src[4 * j], q1 = src[4 * j + 1], q2 = src[4 * j + 2], q3 = src[4 * j + 3];
+#if O3D_PP_JOINT
+    if constexpr (GRAD && UNI && T == 2) {
+      const float2 tk = f2(k15, k15), tk5 = f2(k75, k75);          // 32-bit broadcast operands, as in pp_interact2
+#include O3D_PP_JOINT_FILE
+    } else
+#endif
+    {
+#pragma unroll
+      for (int t = 0; t < T; ++t) pp_interact2<GRAD, UNI>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tr2[t], k15, k75, acc[t]);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float h[NA];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { h[q] = acc[t][q].x + acc[t][q].y; acc[t][q] = f2(0.f, 0.f); }
+#if O3D_PP_TRACE
+    if constexpr (GRAD) h[11] = -(h[3] + h[7]);
+#endif
+    pp_promote<GRAD>(h, sum[t]);
+  }
+  pp_ring_refill<BLOCK>(p, w, tile[BUF], &full[BUF]);         // ++w.kring
+  ++s.kt;
+  s.fresh = s.kt == p.ntiles || w.kring == w.nk;              // the segment ends with this tile
+  if (s.fresh) {
+    // whole block <=> the segment ran from tile 0 to the last tile: kt == ntiles and (not the first segment or kt0 == 0)
+    const bool whole = s.kt == p.ntiles && (!s.seg_first || w.kt0 == 0);
+    pp_store<T, GRAD, BLOCK>(p, s.b, whole, s.seg_first ? 0 : 1, sum);
+    s.seg_first = false;
+    s.kt = 0;
+    ++s.b;
+  }
+}
+
+// The whole share of one persistent CTA: ONE loop over its tiles, two per trip (ring buffer 0, ring buffer 1), so that the nest
+// is two deep - tiles, source pairs - like a one-block-per-CTA kernel's, which is the shape ptxas keeps the inner loop's counter
+// and LDS addresses in uniform registers for; the target block changes inside that loop, at the tiles where a segment starts /
+// ends. The UNI flag is warp-uniform: the two instantiations are two straight-line copies selected once per kernel.
 template <int T, bool GRAD, bool UNI, int BLOCK>
 __device__ __forceinline__ void pp2_walk(const PPArgs& p, PPWalk& w, float4 (&tile)[2][kTile * 2], uint64_t (&full)[2], const float r2u) {
   constexpr int NA = PPAcc<GRAD>::N;
   constexpr int NS = GRAD ? 12 : 3;
-  constexpr int U = GRAD ? kPPUnrollGrad : kPPUnrollVel;
   float2 tx[T], ty[T], tz[T], tr2[T];
   double sum[T][NS];
   float2 acc[T][NA];
@@ -456,61 +558,14 @@ __device__ __forceinline__ void pp2_walk(const PPArgs& p, PPWalk& w, float4 (&ti
 #pragma unroll
     for (int k = 0; k < NA; ++k) acc[t][k] = f2(0.f, 0.f);
   }
-  int b = w.b0, kt = w.kt0;                // target block and source tile of the current unit
-  bool seg_first = true;                   // the current segment is the CTA's first
-  bool fresh = true;                       // the current tile starts a segment
-  for (; w.kring < w.nk;) {
-    if (fresh) {
-      const int64_t base = (int64_t)b * (BLOCK * T) + threadIdx.x;
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
-        tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
-        const float r = p.tr ? p.tr[i] : 0.0f;
-        tr2[t] = UNI ? f2(r2u, r2u) : f2(r * r, r * r);
-#pragma unroll
-        for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
-      }
-    }
-    const int buf = w.kring & 1;
-    pp_ring_wait(full, w.kring);
-    const float4* __restrict__ s = tile[buf];
-#pragma unroll(U)
-    for (int j = 0; j < kTile / 2; ++j) {
-      const float4 q0 = s[4 * j], q1 = s[4 * j + 1], q2 = s[4 * j + 2], q3 = s[4 * j + 3];
-#if O3D_PP_JOINT
-      if constexpr (GRAD && UNI && T == 2) {
-        const float k15 = 1.5f * tr2[0].x, k75 = -7.5f * tr2[0].x;   // 32-bit broadcast operands, as in pp_interact2
-        const float2 tk = f2(k15, k15), tk5 = f2(k75, k75);
-#include O3D_PP_JOINT_FILE
-      } else
-#endif
-      {
-#pragma unroll
-        for (int t = 0; t < T; ++t) pp_interact2<GRAD, UNI>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tr2[t], acc[t]);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      float h[NA];
-#pragma unroll
-      for (int q = 0; q < NA; ++q) { h[q] = acc[t][q].x + acc[t][q].y; acc[t][q] = f2(0.f, 0.f); }
-#if O3D_PP_TRACE
-      if constexpr (GRAD) h[11] = -(h[3] + h[7]);
-#endif
-      pp_promote<GRAD>(h, sum[t]);
-    }
-    pp_ring_refill<BLOCK>(p, w, tile[buf], &full[buf]);       // ++w.kring
-    ++kt;
-    fresh = kt == p.ntiles || w.kring == w.nk;                // the segment ends with this tile
-    if (fresh) {
-      // whole block <=> the segment ran from tile 0 to the last tile: then kt == ntiles and (not the first segment or kt0 == 0)
-      const bool whole = kt == p.ntiles && (!seg_first || w.kt0 == 0);
-      pp_store<T, GRAD, BLOCK>(p, b, whole, seg_first ? 0 : 1, sum);
-      seg_first = false;
-      kt = 0;
-      ++b;
-    }
+  // the two constants of the uniform-radius core: the same value in every thread; a warp reduction (REDUX writes a uniform
+  // register) hands them to ptxas as values it neither has to keep in the vector register file nor can re-derive in the loop
+  const float k15 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(1.5f * r2u)));
+  const float k75 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(-7.5f * r2u)));
+  PPBlock s{w.b0, w.kt0, true, true};
+  while (w.kring < w.nk) {
+    pp2_tile<0, T, GRAD, UNI, BLOCK>(p, w, s, tile, full, r2u, k15, k75, tx, ty, tz, tr2, acc, sum);
+    if (w.kring < w.nk) pp2_tile<1, T, GRAD, UNI, BLOCK>(p, w, s, tile, full, r2u, k15, k75, tx, ty, tz, tr2, acc, sum);
   }
 }
 

@@ -153,6 +153,53 @@ __device__ __forceinline__ void ppc_interact2(const float4 q0, const float4 q1, 
   }
 }
 
+// One tile of a persistent CTA's walk out of ring buffer BUF: pp2_tile (biot_pp.cuh) with this file's interaction.
+template <int BUF, int CORE, int T, bool GRAD, int BLOCK>
+__device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s, float4 (&tile)[2][kTile * 2], uint64_t (&full)[2],
+                                         float2 (&tx)[T], float2 (&ty)[T], float2 (&tz)[T], float2 (&tt)[T],
+                                         float2 (&acc)[T][PPAcc<GRAD>::N], double (&sum)[T][GRAD ? 12 : 3]) {
+  constexpr int NS = GRAD ? 12 : 3;
+  constexpr int NA = PPAcc<GRAD>::N;
+  if (s.fresh) {
+    const int64_t base = (int64_t)s.b * (BLOCK * T) + threadIdx.x;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
+      tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
+      const float term = core_radius_term(CORE, p.tr ? p.tr[i] : 0.0f);
+      tt[t] = f2(term, term);
+#pragma unroll
+      for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
+    }
+  }
+  pp_ring_wait(full, w.kring);
+  const float4* __restrict__ src = tile[BUF];
+#pragma unroll(CORE == kCoreEXP ? 2 : GRAD ? kPPUnrollGrad : kPPUnrollVel)
+  for (int j = 0; j < kTile / 2; ++j) {
+    const float4 q0 = src[4 * j], q1 = src[4 * j + 1], q2 = src[4 * j + 2], q3 = src[4 * j + 3];
+#pragma unroll
+    for (int t = 0; t < T; ++t) ppc_interact2<CORE, GRAD>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tt[t], acc[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    float h[NA];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { h[q] = acc[t][q].x + acc[t][q].y; acc[t][q] = f2(0.f, 0.f); }
+    if constexpr (GRAD) h[11] = -(h[3] + h[7]);
+    pp_promote<GRAD>(h, sum[t]);
+  }
+  pp_ring_refill<BLOCK>(p, w, tile[BUF], &full[BUF]);         // ++w.kring
+  ++s.kt;
+  s.fresh = s.kt == p.ntiles || w.kring == w.nk;
+  if (s.fresh) {
+    const bool whole = s.kt == p.ntiles && (!s.seg_first || w.kt0 == 0);
+    pp_store<T, GRAD, BLOCK>(p, s.b, whole, s.seg_first ? 0 : 1, sum);
+    s.seg_first = false;
+    s.kt = 0;
+    ++s.b;
+  }
+}
+
 template <int CORE, int T, bool GRAD, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) ppc_kernel(const PPArgs p) {
   constexpr int NS = GRAD ? 12 : 3;
@@ -160,9 +207,9 @@ __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) ppc_kernel(const PPArgs p)
   __shared__ alignas(128) float4 tile[2][kTile * 2];
   __shared__ alignas(8) uint64_t full[2];
 
-  // persistent CTA: one loop over the tiles of its share, the target block changing at segment boundaries (pp2_walk, biot_pp.cuh)
+  // persistent CTA: one loop over the tiles of its share, two per trip (ring buffer 0, 1), the target block changing at
+  // segment boundaries (pp2_walk, biot_pp.cuh)
   PPWalk w = pp_ring_start<BLOCK>(p, tile, full);
-
   float2 tx[T], ty[T], tz[T], tt[T];
   double sum[T][NS];
   float2 acc[T][NA];
@@ -171,48 +218,10 @@ __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) ppc_kernel(const PPArgs p)
 #pragma unroll
     for (int k = 0; k < NA; ++k) acc[t][k] = f2(0.f, 0.f);
   }
-  int b = w.b0, kt = w.kt0;
-  bool seg_first = true, fresh = true;
-  for (; w.kring < w.nk;) {
-    if (fresh) {
-      const int64_t base = (int64_t)b * (BLOCK * T) + threadIdx.x;
-#pragma unroll
-      for (int t = 0; t < T; ++t) {
-        const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
-        tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
-        const float term = core_radius_term(CORE, p.tr ? p.tr[i] : 0.0f);
-        tt[t] = f2(term, term);
-#pragma unroll
-        for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
-      }
-    }
-    const int buf = w.kring & 1;
-    pp_ring_wait(full, w.kring);
-    const float4* __restrict__ s = tile[buf];
-#pragma unroll(CORE == kCoreEXP ? 2 : GRAD ? kPPUnrollGrad : kPPUnrollVel)
-    for (int j = 0; j < kTile / 2; ++j) {
-      const float4 q0 = s[4 * j], q1 = s[4 * j + 1], q2 = s[4 * j + 2], q3 = s[4 * j + 3];
-#pragma unroll
-      for (int t = 0; t < T; ++t) ppc_interact2<CORE, GRAD>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tt[t], acc[t]);
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      float h[NA];
-#pragma unroll
-      for (int q = 0; q < NA; ++q) { h[q] = acc[t][q].x + acc[t][q].y; acc[t][q] = f2(0.f, 0.f); }
-      if constexpr (GRAD) h[11] = -(h[3] + h[7]);
-      pp_promote<GRAD>(h, sum[t]);
-    }
-    pp_ring_refill<BLOCK>(p, w, tile[buf], &full[buf]);       // ++w.kring
-    ++kt;
-    fresh = kt == p.ntiles || w.kring == w.nk;
-    if (fresh) {
-      const bool whole = kt == p.ntiles && (!seg_first || w.kt0 == 0);
-      pp_store<T, GRAD, BLOCK>(p, b, whole, seg_first ? 0 : 1, sum);
-      seg_first = false;
-      kt = 0;
-      ++b;
-    }
+  PPBlock s{w.b0, w.kt0, true, true};
+  while (w.kring < w.nk) {
+    ppc_tile<0, CORE, T, GRAD, BLOCK>(p, w, s, tile, full, tx, ty, tz, tt, acc, sum);
+    if (w.kring < w.nk) ppc_tile<1, CORE, T, GRAD, BLOCK>(p, w, s, tile, full, tx, ty, tz, tt, acc, sum);
   }
 }
 

@@ -5,7 +5,11 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -75,15 +79,122 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// ---- host staging for pageable callers --------------------------------------------------------------------------------
+// The reference hands this library plain std::vector<float> storage: pageable memory, which the driver can only move
+// through its own bounce buffers, synchronously and at a few GB/s. The context therefore owns a small ring of pinned
+// slots per device; large host arrays travel through it in chunks - a few helper threads copy the next chunk into (out of)
+// a slot while the DMA engine moves the previous one - and arrays that already are pinned go to the DMA engine directly.
+class CopyPool {
+ public:
+  explicit CopyPool(int helpers) {
+    for (int k = 0; k < helpers; ++k) th_.emplace_back([this, k] { run(k); });
+  }
+  ~CopyPool() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      stop_ = true;
+    }
+    go_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // memcpy split over the helpers and the calling thread; returns when every byte is in place
+  void copy(void* dst, const void* src, size_t bytes) {
+    const size_t parts = th_.size() + 1;
+    if (th_.empty() || bytes < (size_t(1) << 20)) {
+      std::memcpy(dst, src, bytes);
+      return;
+    }
+    const size_t per = ((bytes + parts - 1) / parts + 4095) & ~size_t(4095);
+    {
+      std::lock_guard<std::mutex> l(m_);
+      dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; per_ = per;
+      pending_ = (int)th_.size();
+      ++gen_;
+    }
+    go_.notify_all();
+    if (bytes > per * th_.size()) std::memcpy((char*)dst + per * th_.size(), (const char*)src + per * th_.size(), bytes - per * th_.size());
+    std::unique_lock<std::mutex> l(m_);
+    done_.wait(l, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void run(int k) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::unique_lock<std::mutex> l(m_);
+      go_.wait(l, [&] { return stop_ || gen_ != seen; });
+      if (stop_) return;
+      seen = gen_;
+      char* d = dst_; const char* s = src_;
+      const size_t b = bytes_, per = per_;
+      l.unlock();
+      const size_t off = per * k;
+      if (off < b) std::memcpy(d + off, s + off, std::min(per, b - off));
+      l.lock();
+      if (--pending_ == 0) done_.notify_one();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable go_, done_;
+  char* dst_ = nullptr; const char* src_ = nullptr;
+  size_t bytes_ = 0, per_ = 0;
+  int pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
+constexpr int kStageSlots = 4;
+constexpr size_t kStageBytes = size_t(8) << 20;
+struct Stage {
+  void* slot[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t idle[kStageSlots] = {nullptr, nullptr, nullptr, nullptr};   // the last DMA out of / into the slot has finished
+  int next = 0;
+  CopyPool* pool = nullptr;
+  bool enabled = true;       // o3d_cuda_set_host_staging(ctx, 0): hand every pointer to cudaMemcpyAsync as it comes (A/B runs)
+  cudaError_t ensure() {
+    for (int k = 0; k < kStageSlots; ++k) {
+      if (slot[k]) continue;
+      cudaError_t e = cudaHostAlloc(&slot[k], kStageBytes, cudaHostAllocPortable);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&idle[k], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  void release() {
+    for (int k = 0; k < kStageSlots; ++k) {
+      if (slot[k]) cudaFreeHost(slot[k]);
+      if (idle[k]) cudaEventDestroy(idle[k]);
+      slot[k] = nullptr; idle[k] = nullptr;
+    }
+    delete pool;
+    pool = nullptr;
+  }
+};
+
+bool host_is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 struct Device {
   int id = 0;
   int sm_count = 0;
   int clock_khz = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;                            // uploads that overlap the kernel running on `stream`
+  cudaEvent_t evx[2] = {nullptr, nullptr};                   // cross-stream / cross-device ordering (no timing)
+  Stage stage;
+  DevBuf acc;                                                // FP64 sums of a host call (PPArgs::acc64)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // h2d start, compute start, compute end, d2h end
   cudaEvent_t evk[2] = {nullptr, nullptr};                   // around the dominant kernel of a *_dev call
   bool profile = false;
   bool tuned = true;                                         // launch pp2_kernel from the post-processed cubin (TunedKernels)
+  bool pan_queue = true;                                     // panels -> points with the warp-level work queue (pan_pts_queue_kernel)
   int core = O3D_CORE_WL;                                    // core function of the particle kernels (o3d_cuda_set_core_func)
   DevBuf src, packed, targ, out, work, ppwork, geom, panels, tpanels, cnt, rng;
   unsigned long long counts[2] = {0, 0};  // leaves, splits of the last panel call on this device
@@ -166,6 +277,62 @@ bool finish_timing(Device& d) {
   O3D_TRY(d, cudaEventElapsedTime(&d.h2d_ms, d.ev[0], d.ev[1]));
   O3D_TRY(d, cudaEventElapsedTime(&d.kernel_ms, d.ev[1], d.ev[2]));
   O3D_TRY(d, cudaEventElapsedTime(&d.d2h_ms, d.ev[2], d.ev[3]));
+  return true;
+}
+
+// host -> device of `bytes` on stream st: straight to the DMA engine when the caller's memory is pinned, else through the
+// device's pinned ring (helper threads fill slot k+1 while slot k is in flight)
+bool h2d(Device& d, cudaStream_t st, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return true;
+  Stage& g = d.stage;
+  if (!g.enabled || bytes < (size_t(256) << 10) || host_is_pinned(src)) {
+    O3D_TRY(d, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    return true;
+  }
+  O3D_TRY(d, g.ensure());
+  for (size_t off = 0; off < bytes; off += kStageBytes) {
+    const size_t len = std::min(kStageBytes, bytes - off);
+    const int k = g.next;
+    g.next = (g.next + 1) % kStageSlots;
+    O3D_TRY(d, cudaEventSynchronize(g.idle[k]));
+    g.pool->copy(g.slot[k], (const char*)src + off, len);
+    O3D_TRY(d, cudaMemcpyAsync((char*)dst + off, g.slot[k], len, cudaMemcpyHostToDevice, st));
+    O3D_TRY(d, cudaEventRecord(g.idle[k], st));
+  }
+  return true;
+}
+
+// device -> host, complete on return for pageable destinations (the DMA into slot k+1.. runs while slot k is copied out);
+// pinned destinations are only enqueued - the caller synchronises the stream as before
+bool d2h(Device& d, cudaStream_t st, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return true;
+  Stage& g = d.stage;
+  if (!g.enabled || bytes < (size_t(256) << 10) || host_is_pinned(dst)) {
+    O3D_TRY(d, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    return true;
+  }
+  O3D_TRY(d, g.ensure());
+  struct Pending { int k; size_t off, len; };
+  std::deque<Pending> fifo;
+  auto drain_one = [&]() {
+    const Pending q = fifo.front();
+    fifo.pop_front();
+    O3D_TRY(d, cudaEventSynchronize(g.idle[q.k]));
+    g.pool->copy((char*)dst + q.off, g.slot[q.k], q.len);
+    return true;
+  };
+  for (size_t off = 0; off < bytes; off += kStageBytes) {
+    const size_t len = std::min(kStageBytes, bytes - off);
+    if ((int)fifo.size() == kStageSlots && !drain_one()) return false;
+    const int k = g.next;
+    g.next = (g.next + 1) % kStageSlots;
+    O3D_TRY(d, cudaEventSynchronize(g.idle[k]));            // (a slot last used by an upload)
+    O3D_TRY(d, cudaMemcpyAsync(g.slot[k], (const char*)src + off, len, cudaMemcpyDeviceToHost, st));
+    O3D_TRY(d, cudaEventRecord(g.idle[k], st));
+    fifo.push_back({k, off, len});
+  }
+  while (!fifo.empty())
+    if (!drain_one()) return false;
   return true;
 }
 
@@ -255,8 +422,10 @@ PPShape pp_shape(int sm_count, int64_t ntiles, int64_t nt, bool grad) {
 
 bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, int64_t nt, const float* tx,
                const float* ty, const float* tz, const float* tr, float* tu, float* tv, float* tw, float* tug,
-               int64_t tug_stride) {
-  const bool grad = tug != nullptr;
+               int64_t tug_stride, double* acc64 = nullptr, int64_t acc_stride = 0, int want_grad = -1) {
+  // acc64 != nullptr: store the FP64 sums there instead of adding them into tu.. (which may then be NULL; want_grad says
+  // whether gradients are computed)
+  const bool grad = want_grad < 0 ? tug != nullptr : want_grad != 0;
   const int64_t ntiles = nrec / kTile;
   const PPShape s = pp_shape(d.sm_count, ntiles, nt, grad);
   PPArgs a{};
@@ -269,6 +438,8 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   a.tug = tug;
   a.tug_stride = tug_stride;
   a.sign = 1.0f;
+  a.acc64 = acc64;
+  a.acc_stride = acc_stride;
   // fixed-size, allocated once per device and never moved: captured CUDA graphs may hold its address
   O3D_TRY(d, d.ppwork.ensure(pp_workspace_bytes(d.sm_count)));
   a.partial = d.ppwork.as<double>();
@@ -314,7 +485,7 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
     // the target blocks cut by a CTA-range boundary: add their pieces in unit order (one CTA per boundary)
     const PPPlan plan{s.units, s.grid, (int)ntiles};
     pp_fixup_kernel<<<(unsigned)(s.grid - 1), kPPBlock * (grad ? kPPTgrad : kPPTvel), 0, st>>>(grad ? 12 : 3, plan, nt, a.partial, tu, tv, tw,
-                                                                                              tug, tug_stride, 1.0f);
+                                                                                              tug, tug_stride, 1.0f, a.acc64, a.acc_stride);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
   }
@@ -381,7 +552,19 @@ enum { kRowX = 0, kRowS = 3, kRowR = 6, kRowE = 7, kRowU = 8, kRowG = 11, kRowsM
 // an interim Runge-Kutta copy keeps position, strength, velocity, gradient: x 0-2, s 3-5, u 6-8, ug 9-17
 enum { kIntX = 0, kIntS = 3, kIntU = 6, kIntG = 9, kRowsInterim = 18 };
 
+// A static body attached to a resident collection (include/o3d_cuda.h: o3d_cuda_particles_set_body): its geometry and the
+// packed records of the three panel kernels live on every device of the context for as long as it is attached.
+struct BodyDev {
+  DevBuf geom;      // nodes 3*nn | idx 3*np | ts 3*np | area np | sss np | normals 3*np
+  DevBuf panels;    // pan_pts / pts_pan records (80 B per panel, carry the current strengths)
+  DevBuf refl;      // closest-point records of reflect_kernel (144 B per panel)
+  DevBuf pu;        // 3 x np floats: panel-centre velocities (the BEM right-hand side before projection)
+  DevBuf work;      // FP64 slabs of the panel kernels
+  DevBuf cnt;       // leaf / split / moved counters
+};
+
 struct PartDev {
+  BodyDev body;
   DevBuf main, interim[2], packed, stats, totals;
   cudaEvent_t packed_ready = nullptr;   // this device's slice of the packed stream is written
   cudaEvent_t pulled = nullptr;         // this device has copied every peer's slice
@@ -400,6 +583,16 @@ struct PartDev {
 }  // namespace
 
 struct o3d_particles {
+  // the attached body (has_body): panel counts, the host callback that turns panel-centre velocities into strengths (the
+  // reference's BEM solve stays host code), the clear-inner-layer parameters of Convection::advect, host staging
+  bool has_body = false;
+  int64_t b_nn = 0, b_np = 0;
+  o3d_bem_solve_fn solve = nullptr;
+  void* solve_user = nullptr;
+  float cutoff_mult = 0.0f, ips = 0.0f;
+  std::vector<float> h_pu, h_str;
+  int64_t moved = 0;        // particles pushed out by clear-inner passes of the last call
+  int solves = 0;           // callbacks made by the last call
   int64_t n = 0;
   int64_t per = 0;          // particles per device, a whole number of tiles
   int64_t nrec = 0;         // packed records in the whole stream = ndev slices of `per`, the last one padded
@@ -475,10 +668,34 @@ PartView view_interim(PartDev& q, int which) {
   return v;
 }
 
+// gridDim.y split of the source tiles when the target axis alone cannot fill the GPU
+int pan_nsplit(const Device& d, int64_t gx, int64_t ntiles) {
+  const int64_t fill = (int64_t)d.sm_count * 8;
+  int64_t n = 1;
+  if (gx < fill) n = std::min<int64_t>(std::min<int64_t>(ntiles, (fill + gx - 1) / gx), 4096);
+  return (int)std::max<int64_t>(n, 1);
+}
+
+// panels -> points, 128-thread CTAs: the warp-queue kernel (product) or the per-lane baseline (o3d_cuda_set_panel_queue)
+void launch_pan_pts(const Device& d, cudaStream_t st, const PanPtsArgs& a, dim3 grid, bool grad) {
+  constexpr int B = 128;
+  if (d.pan_queue) {
+    if (grad) pan_pts_queue_kernel<true, B><<<grid, B, 0, st>>>(a);
+    else      pan_pts_queue_kernel<false, B><<<grid, B, 0, st>>>(a);
+  } else {
+    if (grad) pan_pts_kernel<true, B><<<grid, B, 0, st>>>(a);
+    else      pan_pts_kernel<false, B><<<grid, B, 0, st>>>(a);
+  }
+}
+
+struct BodyDev;
+bool body_solve(o3d_ctx* c, o3d_particles* p, const double* fs);
+bool body_on_particles(Device& d, cudaStream_t st, o3d_particles* p, PartDev& q, const PartView& v, bool grad);
+
 // Convection::find_vels for one state, on every device of the context (src/Convection.h:130-184 with no boundaries):
 // zero_vels; pack own slice; exchange packed slices; particles -> own targets; finalize_vels(fs).
 // `sel`: 0 = main state, 1/2 = interim copy 0/1. Everything is enqueued on the per-device streams; no host sync.
-bool part_find_vels(o3d_ctx* c, o3d_particles* p, int sel, const double* fs, bool grad, bool in_capture) {
+bool part_find_vels(o3d_ctx* c, o3d_particles* p, int sel, const double* fs, bool grad, bool in_capture, bool solve_body = false) {
   const int nd = (int)c->dev.size();
   // 1. each device: (wait until every peer has finished reading its previous packed slice) zero, pack own slice
   for (int k = 0; k < nd; ++k) {
@@ -500,32 +717,191 @@ bool part_find_vels(o3d_ctx* c, o3d_particles* p, int sel, const double* fs, boo
     if (!launch_pack(d, st, q.n, v.x[0], v.x[1], v.x[2], v.r, v.s[0], v.s[1], v.s[2], slice, padded_sources(q.n))) return false;
     if (nd > 1) O3D_TRY(d, cudaEventRecord(q.packed_ready, st));
   }
-  // 2. each device pulls every peer's slice of the packed stream (NVLink peer copy), then evaluates its targets
+  // 2. each device pulls every peer's slice of the packed stream (NVLink peer copy)
+  for (int k = 0; k < nd && nd > 1; ++k) {
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    if (q.n == 0) continue;
+    O3D_TRY(d, cudaSetDevice(d.id));
+    cudaStream_t st = d.stream;
+    for (int j = 0; j < nd; ++j) {
+      PartDev& o = p->dev[j];
+      if (j == k || o.n == 0) continue;
+      O3D_TRY(d, cudaStreamWaitEvent(st, o.packed_ready, 0));
+      const size_t off = (size_t)o.t0 * 32, bytes = (size_t)padded_sources(o.n) * 32;
+      O3D_TRY(d, cudaMemcpyPeerAsync((char*)q.packed.p + off, d.id, (const char*)o.packed.p + off, c->dev[j].id, bytes, st));
+    }
+    O3D_TRY(d, cudaEventRecord(q.pulled, st));
+  }
+  // 2b. with a body whose strengths are solved for: the BEM right-hand side from this state, the host solve, new panel records
+  if (solve_body && p->has_body && p->solve && !body_solve(c, p, fs)) return false;
+  // 3. each device evaluates its targets: particles (then the body's panels) on its particles, finalize_vels(fs)
   for (int k = 0; k < nd; ++k) {
     Device& d = c->dev[k];
     PartDev& q = p->dev[k];
     if (q.n == 0) continue;
     O3D_TRY(d, cudaSetDevice(d.id));
     cudaStream_t st = d.stream;
-    if (nd > 1) {
-      for (int j = 0; j < nd; ++j) {
-        PartDev& o = p->dev[j];
-        if (j == k || o.n == 0) continue;
-        O3D_TRY(d, cudaStreamWaitEvent(st, o.packed_ready, 0));
-        const size_t off = (size_t)o.t0 * 32, bytes = (size_t)padded_sources(o.n) * 32;
-        O3D_TRY(d, cudaMemcpyPeerAsync((char*)q.packed.p + off, d.id, (const char*)o.packed.p + off, c->dev[j].id, bytes, st));
-      }
-      O3D_TRY(d, cudaEventRecord(q.pulled, st));
-    }
     PartView v = sel == 0 ? view_main(q) : view_interim(q, sel - 1);
     if (d.profile && !in_capture) O3D_TRY(d, cudaEventRecord(q.ev[0], st));
     if (!launch_pp(d, st, p->nrec, q.packed.as<float4>(), q.n, v.x[0], v.x[1], v.x[2], v.r, v.u[0], v.u[1], v.u[2],
                    grad ? v.ug : nullptr, v.stride))
       return false;
+    if (p->has_body && !body_on_particles(d, st, p, q, v, grad)) return false;
     pts_finalize_kernel<<<(unsigned)((q.n + 255) / 256), 256, 0, st>>>(q.n, v.u[0], v.u[1], v.u[2], grad ? v.ug : nullptr, v.stride,
                                                                       fs[0], fs[1], fs[2]);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
+  }
+  return true;
+}
+
+// ---- resident body --------------------------------------------------------------------------------------------------
+float* body_row(BodyDev& b, int64_t nn, int64_t np, int which) {
+  // geom layout: nodes 3*nn | idx 3*np | ts 3*np | area np | sss np | normals 3*np
+  float* g = b.geom.as<float>();
+  switch (which) {
+    case 0: return g;                        // node x (y at +nn, z at +2nn)
+    case 1: return g + 3 * nn;               // idx (uint32)
+    case 2: return g + 3 * nn + 3 * np;      // ts x (y, z at +np, +2np)
+    case 3: return g + 3 * nn + 6 * np;      // area
+    case 4: return g + 3 * nn + 7 * np;      // sss
+    default: return g + 3 * nn + 8 * np;     // normals x (y, z at +np, +2np)
+  }
+}
+
+bool body_repack(Device& d, cudaStream_t st, o3d_particles* p, BodyDev& b, bool with_source) {
+  const int64_t nn = p->b_nn, np = p->b_np, npad = padded_panels(np);
+  float* ts = body_row(b, nn, np, 2);
+  pan_pack_kernel<<<(unsigned)((npad + 127) / 128), 128, 0, st>>>(np, npad, body_row(b, nn, np, 0), body_row(b, nn, np, 0) + nn,
+                                                                 body_row(b, nn, np, 0) + 2 * nn, (const uint32_t*)body_row(b, nn, np, 1), ts,
+                                                                 ts + np, ts + 2 * np, body_row(b, nn, np, 3),
+                                                                 with_source ? body_row(b, nn, np, 4) : nullptr, b.panels.as<float4>());
+  O3D_TRY(d, cudaGetLastError());
+  d.launches += 1;
+  return true;
+}
+
+// panels -> the particles of one state on one device, added into its u (and ug): the second half of Convection::find_vels
+bool body_on_particles(Device& d, cudaStream_t st, o3d_particles* p, PartDev& q, const PartView& v, bool grad) {
+  BodyDev& b = q.body;
+  const int64_t npad = padded_panels(p->b_np);
+  PanPtsArgs a{};
+  a.pan = b.panels.as<float4>();
+  a.ntiles = (int)(npad / kPanTile);
+  a.nt = q.n;
+  a.tx = v.x[0]; a.ty = v.x[1]; a.tz = v.x[2];
+  a.tu = v.u[0]; a.tv = v.u[1]; a.tw = v.u[2];
+  a.tug = grad ? v.ug : nullptr;
+  a.tug_stride = v.stride;
+  a.counts = nullptr;
+  constexpr int B = 128;
+  const int64_t gx = (q.n + B - 1) / B;
+  const int nout = grad ? 12 : 3;
+  a.nsplit = pan_nsplit(d, gx, a.ntiles);
+  if (a.nsplit > 1) {
+    O3D_TRY(d, b.work.ensure((size_t)a.nsplit * nout * q.n * sizeof(double)));
+    a.partial = b.work.as<double>();
+  }
+  const dim3 grid((unsigned)gx, (unsigned)a.nsplit);
+  launch_pan_pts(d, st, a, grid, grad);
+  O3D_TRY(d, cudaGetLastError());
+  d.launches += 1;
+  if (a.nsplit > 1) {
+    pp_finish_kernel<<<(unsigned)((q.n + 255) / 256), 256, 0, st>>>(nout, a.nsplit, q.n, a.partial, a.tu, a.tv, a.tw, a.tug, v.stride, 1.0f);
+    O3D_TRY(d, cudaGetLastError());
+    d.launches += 1;
+  }
+  return true;
+}
+
+// clear_inner_layer(1, bdry, state, cutoff_mult, ips) on one state of every device (src/Reflect.h:625-655, :446-620)
+bool body_clear_inner(o3d_ctx* c, o3d_particles* p, int sel) {
+  const int64_t np = p->b_np, npad = ((np + kRefTile - 1) / kRefTile) * kRefTile;
+  for (size_t k = 0; k < c->dev.size(); ++k) {
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    if (q.n == 0) continue;
+    O3D_TRY(d, cudaSetDevice(d.id));
+    PartView v = sel == 0 ? view_main(q) : view_interim(q, sel - 1);
+    ReflectArgs a{};
+    a.pan = q.body.refl.as<float4>();
+    a.np = np;
+    a.ntiles = (int)(npad / kRefTile);
+    a.nt = q.n;
+    a.tx = v.x[0]; a.ty = v.x[1]; a.tz = v.x[2];
+    a.mode = 1;
+    a.cutoff = p->cutoff_mult * p->ips;      // float product, as "_cutoff_mult*_ips" with S = float (src/Reflect.h:537)
+    a.count = q.body.cnt.as<unsigned long long>() + 2;
+    constexpr int B = 128;
+    reflect_kernel<B><<<(unsigned)((q.n + B - 1) / B), B, 0, d.stream>>>(a);
+    O3D_TRY(d, cudaGetLastError());
+    d.launches += 1;
+  }
+  return true;
+}
+
+// Right-hand side of the BEM solve for one state (solve_bem, src/BEMHelper.h:83-103): zero the panel-centre velocities,
+// particles -> panels (subtracting, src/Influence.h:1210-1212), finalize_vels(fs) (src/Surfaces.h:877-887) on device 0, whose
+// packed stream holds every particle of the state; then the host callback solves for the strengths (the reference's BEM
+// stays host code) and every device repacks its panel records with them. Needs the state's packed stream: call after
+// part_pack_exchange.
+bool body_solve(o3d_ctx* c, o3d_particles* p, const double* fs) {
+  const int nd = (int)c->dev.size();
+  const int64_t np = p->b_np, nn = p->b_nn;
+  Device& d = c->dev[0];
+  PartDev& q = p->dev[0];
+  BodyDev& b = q.body;
+  O3D_TRY(d, cudaSetDevice(d.id));
+  cudaStream_t st = d.stream;
+  float* pu = b.pu.as<float>();
+  pts_fill_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(np, 3, pu, np, 0.0f);
+  O3D_TRY(d, cudaGetLastError());
+  d.launches += 1;
+  for (int k = 0; k < nd; ++k) {             // one launch per device slice of the stream: padding records are never read
+    const PartDev& o = p->dev[k];
+    if (o.n == 0) continue;
+    PtsPanArgs a{};
+    a.src = q.packed.as<float4>() + (size_t)o.t0 * 2;
+    a.ns = o.n;
+    a.ntiles = (int)(padded_sources(o.n) / kTile);
+    a.np = np;
+    a.pan = b.panels.as<float4>();
+    a.counts = nullptr;
+    constexpr int B = 64;
+    const int64_t gx = (np + B - 1) / B;
+    a.nsplit = pan_nsplit(d, gx, a.ntiles);
+    O3D_TRY(d, b.work.ensure((size_t)a.nsplit * 3 * np * sizeof(double)));
+    a.partial = b.work.as<double>();
+    pts_pan_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
+    O3D_TRY(d, cudaGetLastError());
+    pp_finish_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(3, a.nsplit, np, a.partial, pu, pu + np, pu + 2 * np, nullptr, np, -1.0f);
+    O3D_TRY(d, cudaGetLastError());
+    d.launches += 2;
+  }
+  pts_finalize_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(np, pu, pu + np, pu + 2 * np, nullptr, np, fs[0], fs[1], fs[2]);
+  O3D_TRY(d, cudaGetLastError());
+  d.launches += 1;
+  p->h_pu.resize((size_t)3 * np);
+  p->h_str.assign((size_t)4 * np, 0.0f);
+  O3D_TRY(d, cudaMemcpyAsync(p->h_pu.data(), pu, (size_t)3 * np * 4, cudaMemcpyDeviceToHost, st));
+  O3D_TRY(d, cudaStreamSynchronize(st));
+  int have_source = 0;
+  float* hs = p->h_str.data();
+  if (p->solve(p->solve_user, np, p->h_pu.data(), hs, hs + np, hs + 2 * np, hs + 3 * np, &have_source) != 0) {
+    d.status = cudaErrorUnknown;
+    d.where = "the BEM solve callback reported a failure";
+    return false;
+  }
+  p->solves += 1;
+  for (int k = 0; k < nd; ++k) {
+    Device& dk = c->dev[k];
+    PartDev& qk = p->dev[k];
+    if (qk.n == 0 && k != 0) continue;
+    O3D_TRY(dk, cudaSetDevice(dk.id));
+    O3D_TRY(dk, cudaMemcpyAsync(body_row(qk.body, nn, np, 2), hs, (size_t)3 * np * 4, cudaMemcpyHostToDevice, dk.stream));
+    O3D_TRY(dk, cudaMemcpyAsync(body_row(qk.body, nn, np, 4), hs + 3 * np, (size_t)np * 4, cudaMemcpyHostToDevice, dk.stream));
+    if (!body_repack(dk, dk.stream, p, qk.body, have_source != 0)) return false;
   }
   return true;
 }
@@ -567,7 +943,10 @@ MoveArgs euler_args(const PartDev& q, const PartView& src, const PartView& dst, 
   return a;
 }
 
-// One Convection::advect call (src/Convection.h:208-228) for a particle-only system, enqueued on every device.
+// One Convection::advect call (src/Convection.h:208-228) for one particle collection, optionally around a static body,
+// enqueued on every device. With a body every derivative evaluation is find_derivs (:186-202) = solve the BEM for the state,
+// then velocities from particles and panels; and every move is followed by clear_inner_layer on the moved state (:258,
+// :372, :405, advect_3rd).
 bool part_advect_once(o3d_ctx* c, o3d_particles* p, int order, double dt, const double* fs, bool in_capture) {
   const int nd = (int)c->dev.size();
   auto each = [&](auto&& f) {
@@ -580,8 +959,9 @@ bool part_advect_once(o3d_ctx* c, o3d_particles* p, int order, double dt, const 
     }
     return true;
   };
-  // find_derivs at the current state (no BEM to solve)
-  if (!part_find_vels(c, p, 0, fs, true, in_capture)) return false;
+  auto clear = [&](int sel) { return !p->has_body || body_clear_inner(c, p, sel); };
+  // find_derivs at the current state
+  if (!part_find_vels(c, p, 0, fs, true, in_capture, true)) return false;
   if (order == 1) {
     // advect_1st :247-250 - elem.move(time, dt, 1.0, elem)
     return each([&](Device& d, PartDev& q) {
@@ -589,7 +969,7 @@ bool part_advect_once(o3d_ctx* c, o3d_particles* p, int order, double dt, const 
       MoveArgs a = euler_args(q, m, m, m, m, dt);
       a.ein = a.eout = prow(q.main, q.cap, kRowE);
       return launch_move(d, d.stream, a, 1);
-    });
+    }) && clear(0);
   }
   if (order == 2) {
     // advect_2nd_ralston :366-405 - interim = copy moved by 2/3 dt; derivatives there; combine 1/4, 3/4
@@ -599,7 +979,8 @@ bool part_advect_once(o3d_ctx* c, o3d_particles* p, int order, double dt, const 
           return launch_move(d, d.stream, euler_args(q, m, i1, m, m, twothirds * dt), 1);
         }))
       return false;
-    if (!part_find_vels(c, p, 1, fs, true, in_capture)) return false;
+    if (!clear(1)) return false;
+    if (!part_find_vels(c, p, 1, fs, true, in_capture, true)) return false;
     return each([&](Device& d, PartDev& q) {
       PartView m = view_main(q), i1 = view_interim(q, 0);
       MoveArgs a{};
@@ -608,7 +989,7 @@ bool part_advect_once(o3d_ctx* c, o3d_particles* p, int order, double dt, const 
       for (int k = 0; k < 3; ++k) { a.xin[k] = a.xout[k] = m.x[k]; a.sin[k] = a.sout[k] = m.s[k]; a.uout[k] = m.u[k]; }
       a.ein = a.eout = prow(q.main, q.cap, kRowE);
       return launch_move(d, d.stream, a, 2);
-    });
+    }) && clear(0);
   }
   // advect_3rd :446-532 - vort1 = copy moved 1/2 dt with its own derivatives; vort2 = copy of the ORIGINAL moved
   // 3/4 dt with vort1's velocity (and, being a one-stage move, its own = the original's gradient); combine 2/9, 3/9, 4/9
@@ -617,13 +998,15 @@ bool part_advect_once(o3d_ctx* c, o3d_particles* p, int order, double dt, const 
         return launch_move(d, d.stream, euler_args(q, m, i1, m, m, 0.5 * dt), 1);
       }))
     return false;
-  if (!part_find_vels(c, p, 1, fs, true, in_capture)) return false;
+  if (!clear(1)) return false;
+  if (!part_find_vels(c, p, 1, fs, true, in_capture, true)) return false;
   if (!each([&](Device& d, PartDev& q) {
         PartView m = view_main(q), i1 = view_interim(q, 0), i2 = view_interim(q, 1);
         return launch_move(d, d.stream, euler_args(q, m, i2, i1, m, 0.75 * dt), 1);
       }))
     return false;
-  if (!part_find_vels(c, p, 2, fs, true, in_capture)) return false;
+  if (!clear(2)) return false;
+  if (!part_find_vels(c, p, 2, fs, true, in_capture, true)) return false;
   return each([&](Device& d, PartDev& q) {
     PartView m = view_main(q), i1 = view_interim(q, 0), i2 = view_interim(q, 1);
     MoveArgs a{};
@@ -632,7 +1015,7 @@ bool part_advect_once(o3d_ctx* c, o3d_particles* p, int order, double dt, const 
     for (int k = 0; k < 3; ++k) { a.xin[k] = a.xout[k] = m.x[k]; a.sin[k] = a.sout[k] = m.s[k]; a.uout[k] = m.u[k]; }
     a.ein = a.eout = prow(q.main, q.cap, kRowE);
     return launch_move(d, d.stream, a, 3);
-  });
+  }) && clear(0);
 }
 
 bool part_sync_all(o3d_ctx* c, o3d_particles* p) {
@@ -696,13 +1079,32 @@ int o3d_cuda_create(o3d_ctx** out, int ndev, const int* devices) {
     cudaDeviceGetAttribute(&d.clock_khz, cudaDevAttrClockRate, d.id);
     bool ok = cudaSetDevice(d.id) == cudaSuccess &&
               cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&d.stream2, cudaStreamNonBlocking) == cudaSuccess;
     for (int e = 0; ok && e < 4; ++e) ok = cudaEventCreate(&d.ev[e]) == cudaSuccess;
     for (int e = 0; ok && e < 2; ++e) ok = cudaEventCreate(&d.evk[e]) == cudaSuccess;
+    for (int e = 0; ok && e < 2; ++e) ok = cudaEventCreateWithFlags(&d.evx[e], cudaEventDisableTiming) == cudaSuccess;
+    if (ok) {
+      // helper threads for staging copies: O3D_CUDA_COPY_THREADS, default min(6, cores / devices) - 1 beside the caller
+      const char* env_ct = getenv("O3D_CUDA_COPY_THREADS");
+      int total = env_ct ? atoi(env_ct) : std::min(6, std::max(1, (int)std::thread::hardware_concurrency() / ndev));
+      d.stage.pool = new CopyPool(std::max(0, std::min(total, 16) - 1));
+    }
     if (!ok) {
       o3d_cuda_destroy(c);
       return O3D_ERR_CUDA;
     }
     d.tuned = want_tuned;
+  }
+  if (ndev > 1) {   // peers read each other's packed source stream over NVLink (host entry points, resident collections)
+    for (int k = 0; k < ndev; ++k) {
+      cudaSetDevice(c->dev[k].id);
+      for (int j = 0; j < ndev; ++j) {
+        int can = 0;
+        if (j != k && cudaDeviceCanAccessPeer(&can, c->dev[k].id, c->dev[j].id) == cudaSuccess && can &&
+            cudaDeviceEnablePeerAccess(c->dev[j].id, 0) != cudaSuccess)
+          cudaGetLastError();   // already enabled is fine
+      }
+    }
   }
   if (tuned_kernels().status != cudaSuccess) {               // no silent fallback: the library is broken
     fprintf(stderr, "o3d_cuda_create: %s failed: %s\n", tuned_kernels().where, cudaGetErrorString(tuned_kernels().status));
@@ -717,6 +1119,11 @@ void o3d_cuda_destroy(o3d_ctx* c) {
   if (!c) return;
   for (Device& d : c->dev) {
     cudaSetDevice(d.id);
+    d.stage.release();
+    d.acc.release();
+    for (cudaEvent_t e : d.evx)
+      if (e) cudaEventDestroy(e);
+    if (d.stream2) cudaStreamDestroy(d.stream2);
     for (DevBuf* b : {&d.src, &d.packed, &d.targ, &d.out, &d.work, &d.ppwork, &d.geom, &d.panels, &d.tpanels, &d.cnt, &d.rng}) b->release();
     for (cudaEvent_t e : d.ev)
       if (e) cudaEventDestroy(e);
@@ -769,41 +1176,88 @@ int o3d_cuda_pts_on_pts(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
   for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
   if (ns == 0 || nt == 0) return collect(c);
 
+  // Per device (one host thread each): its slice of the targets against all sources.
+  //   sources  -> device 0 only (PCIe once), packed there; the other devices copy the PACKED stream from device 0 over NVLink
+  //   targets  -> each device its slice
+  //   kernel   -> stores FP64 sums (PPArgs::acc64) and never reads the outputs, so ...
+  //   outputs  -> ... the caller's initial values are uploaded on a second stream WHILE the kernel runs, then one
+  //               O(n) pass adds the sums into them with the rounding of the fused epilogue, and they travel back.
   const int ndev = (int)c->dev.size();
+  const int64_t nrec = padded_sources(ns);
+  std::atomic<int> packed_posted{0};        // 1: device 0 has recorded evx[0] after its pack; -1: it failed before that
   for_each_device(c, [&](int k) {
     Device& d = c->dev[k];
+    auto bail = [&]() {
+      if (k == 0 && packed_posted.load() == 0) packed_posted.store(-1);
+      return false;
+    };
     int64_t t0, t1;
     partition(nt, ndev, k, &t0, &t1);
     const int64_t n = t1 - t0;
-    if (n == 0) return true;
-    O3D_TRY(d, cudaSetDevice(d.id));
-    const int64_t nrec = padded_sources(ns);
+    if (n == 0 && k != 0) return true;       // device 0 always packs: its peers wait for it
+    if (cudaSetDevice(d.id) != cudaSuccess) { d.status = cudaGetLastError(); d.where = "cudaSetDevice"; return bail(); }
     const int nout = grad ? 12 : 3;
-    O3D_TRY(d, d.src.ensure((size_t)7 * ns * 4));
-    O3D_TRY(d, d.packed.ensure((size_t)nrec * 32));
-    O3D_TRY(d, d.targ.ensure((size_t)4 * n * 4));
-    O3D_TRY(d, d.out.ensure((size_t)nout * n * 4));
+    auto prep = [&]() {
+      if (k == 0) O3D_TRY(d, d.src.ensure((size_t)7 * ns * 4));
+      O3D_TRY(d, d.packed.ensure((size_t)nrec * 32));
+      O3D_TRY(d, d.targ.ensure((size_t)4 * std::max<int64_t>(n, 1) * 4));
+      O3D_TRY(d, d.out.ensure((size_t)nout * std::max<int64_t>(n, 1) * 4));
+      O3D_TRY(d, d.acc.ensure((size_t)nout * std::max<int64_t>(n, 1) * sizeof(double)));
+      return true;
+    };
+    if (!prep()) return bail();
     cudaStream_t st = d.stream;
     float* ds = d.src.as<float>();
     float* dt = d.targ.as<float>();
     float* dout = d.out.as<float>();
-    O3D_TRY(d, cudaEventRecord(d.ev[0], st));
-    const float* hs[7] = {sx, sy, sz, sr, ssx, ssy, ssz};
-    for (int a = 0; a < 7; ++a) O3D_TRY(d, cudaMemcpyAsync(ds + (size_t)a * ns, hs[a], (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+    auto upload_sources = [&]() {
+      O3D_TRY(d, cudaEventRecord(d.ev[0], st));
+      if (k == 0) {
+        const float* hs[7] = {sx, sy, sz, sr, ssx, ssy, ssz};
+        for (int a = 0; a < 7; ++a)
+          if (!h2d(d, st, ds + (size_t)a * ns, hs[a], (size_t)ns * 4)) return false;
+        if (!launch_pack(d, st, ns, ds, ds + ns, ds + 2 * ns, ds + 3 * ns, ds + 4 * ns, ds + 5 * ns, ds + 6 * ns, d.packed.as<float4>()))
+          return false;
+        if (ndev > 1) O3D_TRY(d, cudaEventRecord(d.evx[0], st));
+      }
+      return true;
+    };
+    const bool up = upload_sources();
+    if (k == 0 && ndev > 1) packed_posted.store(up ? 1 : -1);
+    if (!up) return bail();
+    if (n == 0) {
+      O3D_TRY(d, cudaStreamSynchronize(st));
+      return true;
+    }
+    if (k != 0) {
+      int state;
+      while ((state = packed_posted.load()) == 0) std::this_thread::yield();
+      if (state < 0) return true;            // device 0 reports the error
+      Device& d0 = c->dev[0];
+      O3D_TRY(d, cudaStreamWaitEvent(st, d0.evx[0], 0));
+      O3D_TRY(d, cudaMemcpyPeerAsync(d.packed.p, d.id, d0.packed.p, d0.id, (size_t)nrec * 32, st));
+    }
     const float* ht[4] = {tx, ty, tz, tr};
     for (int a = 0; a < 4; ++a)
-      if (ht[a]) O3D_TRY(d, cudaMemcpyAsync(dt + (size_t)a * n, ht[a] + t0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+      if (ht[a] && !h2d(d, st, dt + (size_t)a * n, ht[a] + t0, (size_t)n * 4)) return false;
+    O3D_TRY(d, cudaEventRecord(d.ev[1], st));
+    if (!launch_pp(d, st, nrec, d.packed.as<float4>(), n, dt, dt + n, dt + 2 * n, tr ? dt + 3 * n : nullptr, nullptr, nullptr, nullptr,
+                   nullptr, n, d.acc.as<double>(), n, grad ? 1 : 0))
+      return false;
+    // the caller's initial values go up while the kernel runs
     float* ho[12] = {tu, tv, tw};
     for (int a = 0; a < 9; ++a) ho[3 + a] = grad ? tug[a] : nullptr;
-    for (int a = 0; a < nout; ++a) O3D_TRY(d, cudaMemcpyAsync(dout + (size_t)a * n, ho[a] + t0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    O3D_TRY(d, cudaEventRecord(d.ev[1], st));
-    if (!launch_pack(d, st, ns, ds, ds + ns, ds + 2 * ns, ds + 3 * ns, ds + 4 * ns, ds + 5 * ns, ds + 6 * ns, d.packed.as<float4>()))
-      return false;
-    if (!launch_pp(d, st, nrec, d.packed.as<float4>(), n, dt, dt + n, dt + 2 * n, tr ? dt + 3 * n : nullptr, dout, dout + n,
-                   dout + 2 * n, grad ? dout + 3 * n : nullptr, n))
-      return false;
+    for (int a = 0; a < nout; ++a)
+      if (!h2d(d, d.stream2, dout + (size_t)a * n, ho[a] + t0, (size_t)n * 4)) return false;
+    O3D_TRY(d, cudaEventRecord(d.evx[1], d.stream2));
+    O3D_TRY(d, cudaStreamWaitEvent(st, d.evx[1], 0));
+    pp_accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(nout, n, d.acc.as<double>(), n, dout, dout + n, dout + 2 * n,
+                                                                     grad ? dout + 3 * n : nullptr, n, 1.0f);
+    O3D_TRY(d, cudaGetLastError());
+    d.launches += 1;
     O3D_TRY(d, cudaEventRecord(d.ev[2], st));
-    for (int a = 0; a < nout; ++a) O3D_TRY(d, cudaMemcpyAsync(ho[a] + t0, dout + (size_t)a * n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    for (int a = 0; a < nout; ++a)
+      if (!d2h(d, st, ho[a] + t0, dout + (size_t)a * n, (size_t)n * 4)) return false;
     O3D_TRY(d, cudaEventRecord(d.ev[3], st));
     return finish_timing(d);
   });
@@ -828,15 +1282,15 @@ bool upload_panels(Device& d, cudaStream_t st, DevBuf& dst, int64_t nn, const fl
   float* gts = g + 3 * nn + 3 * np;
   float* garea = gts + 3 * np;
   float* gsss = garea + np;
-  O3D_TRY(d, cudaMemcpyAsync(gnx, nx, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
-  O3D_TRY(d, cudaMemcpyAsync(gny, ny, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
-  O3D_TRY(d, cudaMemcpyAsync(gnz, nz, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
-  O3D_TRY(d, cudaMemcpyAsync(gidx, idx, (size_t)3 * np * 4, cudaMemcpyHostToDevice, st));
+  if (!h2d(d, st, gnx, nx, (size_t)nn * 4)) return false;
+  if (!h2d(d, st, gny, ny, (size_t)nn * 4)) return false;
+  if (!h2d(d, st, gnz, nz, (size_t)nn * 4)) return false;
+  if (!h2d(d, st, gidx, idx, (size_t)3 * np * 4)) return false;
   const float* hts[3] = {tsx, tsy, tsz};
   for (int a = 0; a < 3; ++a)
-    if (hts[a]) O3D_TRY(d, cudaMemcpyAsync(gts + (size_t)a * np, hts[a], (size_t)np * 4, cudaMemcpyHostToDevice, st));
-  O3D_TRY(d, cudaMemcpyAsync(garea, area, (size_t)np * 4, cudaMemcpyHostToDevice, st));
-  if (sss) O3D_TRY(d, cudaMemcpyAsync(gsss, sss, (size_t)np * 4, cudaMemcpyHostToDevice, st));
+    if (hts[a]) if (!h2d(d, st, gts + (size_t)a * np, hts[a], (size_t)np * 4)) return false;
+  if (!h2d(d, st, garea, area, (size_t)np * 4)) return false;
+  if (sss) if (!h2d(d, st, gsss, sss, (size_t)np * 4)) return false;
   pan_pack_kernel<<<(unsigned)((npad + 127) / 128), 128, 0, st>>>(np, npad, gnx, gny, gnz, gidx, tsx ? gts : nullptr,
                                                                  tsy ? gts + np : nullptr, tsz ? gts + 2 * np : nullptr,
                                                                  garea, sss ? gsss : nullptr, dst.as<float4>());
@@ -851,16 +1305,8 @@ bool zero_counts(Device& d, cudaStream_t st) {
   return true;
 }
 bool fetch_counts(Device& d, cudaStream_t st) {
-  O3D_TRY(d, cudaMemcpyAsync(d.counts, d.cnt.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+  if (!d2h(d, st, d.counts, d.cnt.p, 2 * sizeof(unsigned long long))) return false;
   return true;
-}
-
-// gridDim.y split of the source tiles when the target axis alone cannot fill the GPU
-int pan_nsplit(const Device& d, int64_t gx, int64_t ntiles) {
-  const int64_t fill = (int64_t)d.sm_count * 8;
-  int64_t n = 1;
-  if (gx < fill) n = std::min<int64_t>(std::min<int64_t>(ntiles, (fill + gx - 1) / gx), 4096);
-  return (int)std::max<int64_t>(n, 1);
 }
 
 bool valid_indices(const uint32_t* idx, int64_t np, int64_t nn) {
@@ -904,10 +1350,10 @@ int o3d_cuda_pan_on_pts(o3d_ctx* c, int64_t nn, const float* nx, const float* ny
     float* dout = d.out.as<float>();
     O3D_TRY(d, cudaEventRecord(d.ev[0], st));
     const float* ht[3] = {tx, ty, tz};
-    for (int a = 0; a < 3; ++a) O3D_TRY(d, cudaMemcpyAsync(dt + (size_t)a * n, ht[a] + t0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    for (int a = 0; a < 3; ++a) if (!h2d(d, st, dt + (size_t)a * n, ht[a] + t0, (size_t)n * 4)) return false;
     float* ho[12] = {tu, tv, tw};
     for (int a = 0; a < 9; ++a) ho[3 + a] = grad ? tug[a] : nullptr;
-    for (int a = 0; a < nout; ++a) O3D_TRY(d, cudaMemcpyAsync(dout + (size_t)a * n, ho[a] + t0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    for (int a = 0; a < nout; ++a) if (!h2d(d, st, dout + (size_t)a * n, ho[a] + t0, (size_t)n * 4)) return false;
     if (!zero_counts(d, st)) return false;
     O3D_TRY(d, cudaEventRecord(d.ev[1], st));
     if (!upload_panels(d, st, d.panels, nn, nx, ny, nz, np, idx, tsx, tsy, tsz, area, sss)) return false;
@@ -928,8 +1374,7 @@ int o3d_cuda_pan_on_pts(o3d_ctx* c, int64_t nn, const float* nx, const float* ny
       a.partial = d.work.as<double>();
     }
     const dim3 grid((unsigned)gx, (unsigned)a.nsplit);
-    if (grad) pan_pts_kernel<true, B><<<grid, B, 0, st>>>(a);
-    else      pan_pts_kernel<false, B><<<grid, B, 0, st>>>(a);
+    launch_pan_pts(d, st, a, grid, grad);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
     if (a.nsplit > 1) {
@@ -938,7 +1383,7 @@ int o3d_cuda_pan_on_pts(o3d_ctx* c, int64_t nn, const float* nx, const float* ny
       d.launches += 1;
     }
     O3D_TRY(d, cudaEventRecord(d.ev[2], st));
-    for (int a2 = 0; a2 < nout; ++a2) O3D_TRY(d, cudaMemcpyAsync(ho[a2] + t0, dout + (size_t)a2 * n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    for (int a2 = 0; a2 < nout; ++a2) if (!d2h(d, st, ho[a2] + t0, dout + (size_t)a2 * n, (size_t)n * 4)) return false;
     if (!fetch_counts(d, st)) return false;
     O3D_TRY(d, cudaEventRecord(d.ev[3], st));
     return finish_timing(d);
@@ -985,9 +1430,9 @@ int o3d_cuda_pts_on_pan(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
     float* dout = d.out.as<float>();
     O3D_TRY(d, cudaEventRecord(d.ev[0], st));
     const float* hs[6] = {sx, sy, sz, ssx, ssy, ssz};
-    for (int a = 0; a < 6; ++a) O3D_TRY(d, cudaMemcpyAsync(ds + (size_t)a * ns, hs[a], (size_t)ns * 4, cudaMemcpyHostToDevice, st));
+    for (int a = 0; a < 6; ++a) if (!h2d(d, st, ds + (size_t)a * ns, hs[a], (size_t)ns * 4)) return false;
     float* ho[3] = {pu, pv, pw};
-    for (int a = 0; a < 3; ++a) O3D_TRY(d, cudaMemcpyAsync(dout + (size_t)a * n, ho[a] + p0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    for (int a = 0; a < 3; ++a) if (!h2d(d, st, dout + (size_t)a * n, ho[a] + p0, (size_t)n * 4)) return false;
     if (!zero_counts(d, st)) return false;
     O3D_TRY(d, cudaEventRecord(d.ev[1], st));
     // this device's slice of the target panels (connectivity offset by p0; nodes whole)
@@ -1012,7 +1457,7 @@ int o3d_cuda_pts_on_pan(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
     O3D_TRY(d, cudaEventRecord(d.ev[2], st));
-    for (int a2 = 0; a2 < 3; ++a2) O3D_TRY(d, cudaMemcpyAsync(ho[a2] + p0, dout + (size_t)a2 * n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    for (int a2 = 0; a2 < 3; ++a2) if (!d2h(d, st, ho[a2] + p0, dout + (size_t)a2 * n, (size_t)n * 4)) return false;
     if (!fetch_counts(d, st)) return false;
     O3D_TRY(d, cudaEventRecord(d.ev[3], st));
     return finish_timing(d);
@@ -1060,11 +1505,11 @@ int o3d_cuda_pan_on_pan_coeff(o3d_ctx* c, int64_t snn, const float* snx, const f
     float* dsb1 = db; float* dsb2 = db + 3 * nsp;
     float* dtb1 = db + 6 * nsp; float* dtb2 = dtb1 + 3 * ntp; float* dtn = dtb2 + 3 * ntp;
     O3D_TRY(d, cudaEventRecord(d.ev[0], st));
-    O3D_TRY(d, cudaMemcpyAsync(dsb1, sb1, (size_t)3 * nsp * 4, cudaMemcpyHostToDevice, st));
-    O3D_TRY(d, cudaMemcpyAsync(dsb2, sb2, (size_t)3 * nsp * 4, cudaMemcpyHostToDevice, st));
-    O3D_TRY(d, cudaMemcpyAsync(dtb1, tb1, (size_t)3 * ntp * 4, cudaMemcpyHostToDevice, st));
-    O3D_TRY(d, cudaMemcpyAsync(dtb2, tb2, (size_t)3 * ntp * 4, cudaMemcpyHostToDevice, st));
-    O3D_TRY(d, cudaMemcpyAsync(dtn, tnrm, (size_t)3 * ntp * 4, cudaMemcpyHostToDevice, st));
+    if (!h2d(d, st, dsb1, sb1, (size_t)3 * nsp * 4)) return false;
+    if (!h2d(d, st, dsb2, sb2, (size_t)3 * nsp * 4)) return false;
+    if (!h2d(d, st, dtb1, tb1, (size_t)3 * ntp * 4)) return false;
+    if (!h2d(d, st, dtb2, tb2, (size_t)3 * ntp * 4)) return false;
+    if (!h2d(d, st, dtn, tnrm, (size_t)3 * ntp * 4)) return false;
     if (!zero_counts(d, st)) return false;
     O3D_TRY(d, cudaEventRecord(d.ev[1], st));
     if (!upload_panels(d, st, d.panels, snn, snx, sny, snz, nsp, sidx, nullptr, nullptr, nullptr, sarea, nullptr)) return false;
@@ -1084,7 +1529,7 @@ int o3d_cuda_pan_on_pan_coeff(o3d_ctx* c, int64_t snn, const float* snx, const f
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
     O3D_TRY(d, cudaEventRecord(d.ev[2], st));
-    O3D_TRY(d, cudaMemcpyAsync(coeffs + (size_t)3 * j0 * nrows, d.out.p, (size_t)3 * n * nrows * 4, cudaMemcpyDeviceToHost, st));
+    if (!d2h(d, st, coeffs + (size_t)3 * j0 * nrows, d.out.p, (size_t)3 * n * nrows * 4)) return false;
     if (!fetch_counts(d, st)) return false;
     O3D_TRY(d, cudaEventRecord(d.ev[3], st));
     return finish_timing(d);
@@ -1289,7 +1734,9 @@ void o3d_cuda_particles_destroy(o3d_ctx* c, o3d_particles* p) {
     if (c && k < c->dev.size()) cudaSetDevice(c->dev[k].id);
     PartDev& q = p->dev[k];
     part_release_graph(q);
-    for (DevBuf* b : {&q.main, &q.interim[0], &q.interim[1], &q.packed, &q.stats, &q.totals}) b->release();
+    for (DevBuf* b : {&q.main, &q.interim[0], &q.interim[1], &q.packed, &q.stats, &q.totals, &q.body.geom, &q.body.panels, &q.body.refl,
+                      &q.body.pu, &q.body.work, &q.body.cnt})
+      b->release();
     for (cudaEvent_t e : {q.packed_ready, q.pulled, q.ev[0], q.ev[1]})
       if (e) cudaEventDestroy(e);
   }
@@ -1314,7 +1761,7 @@ int o3d_cuda_particles_upload(o3d_ctx* c, o3d_particles* p, int64_t n, const flo
       O3D_TRY(d, cudaSetDevice(d.id));
       for (int a = 0; a < 8; ++a) {
         float* dst = prow(q.main, q.cap, a);
-        if (rows[a]) O3D_TRY(d, cudaMemcpyAsync(dst, rows[a] + q.t0, (size_t)q.n * 4, cudaMemcpyHostToDevice, d.stream));
+        if (rows[a]) if (!h2d(d, d.stream, dst, rows[a] + q.t0, (size_t)q.n * 4)) return false;
       }
       if (!elong) {   // a fresh collection: elong = 1 (src/Points.h:120-127)
         pts_fill_kernel<<<(unsigned)((q.n + 255) / 256), 256, 0, d.stream>>>(q.n, 1, prow(q.main, q.cap, kRowE), q.cap, 1.0f);
@@ -1345,7 +1792,7 @@ int o3d_cuda_particles_download(o3d_ctx* c, o3d_particles* p, float* x, float* y
     auto go = [&]() {
       O3D_TRY(d, cudaSetDevice(d.id));
       for (int a = 0; a < 20; ++a)
-        if (rows[a]) O3D_TRY(d, cudaMemcpyAsync(rows[a] + q.t0, prow(q.main, q.cap, a), (size_t)q.n * 4, cudaMemcpyDeviceToHost, d.stream));
+        if (rows[a]) if (!d2h(d, d.stream, rows[a] + q.t0, prow(q.main, q.cap, a), (size_t)q.n * 4)) return false;
       O3D_TRY(d, cudaStreamSynchronize(d.stream));
       return true;
     };
@@ -1373,7 +1820,16 @@ int o3d_cuda_particles_advect(o3d_ctx* c, o3d_particles* p, int order, double ti
   for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
   const double n = (double)p->n;
   if (flops_out) *flops_out = (double)nsteps * order * n * (12.0 + pp_pair_flops(c->dev[0].core, true, true) * n);
+  p->solves = 0;
+  p->moved = 0;
   if (p->n == 0 || nsteps == 0) return collect(c);
+  if (p->has_body) {
+    for (size_t k = 0; k < c->dev.size(); ++k) {
+      if (p->dev[k].n == 0) continue;
+      cudaSetDevice(c->dev[k].id);
+      cudaMemsetAsync(p->dev[k].body.cnt.p, 0, 4 * sizeof(unsigned long long), c->dev[k].stream);
+    }
+  }
   const int nd = (int)c->dev.size();
   auto run = [&]() {
     for (int k = 0; k < nd; ++k) {
@@ -1389,7 +1845,7 @@ int o3d_cuda_particles_advect(o3d_ctx* c, o3d_particles* p, int order, double ti
     // grow-only buffer has its final size before capture.
     Device& d0 = c->dev[0];
     PartDev& q0 = p->dev[0];
-    const bool same = c->use_graphs && q0.graph && q0.graph_n == p->n && q0.graph_order == order && q0.graph_dt == dt &&
+    const bool same = c->use_graphs && !p->has_body && q0.graph && q0.graph_n == p->n && q0.graph_order == order && q0.graph_dt == dt &&
                       q0.graph_core == d0.core && q0.graph_tuned == d0.tuned &&
                       q0.graph_fs[0] == fs[0] && q0.graph_fs[1] == fs[1] && q0.graph_fs[2] == fs[2];
     if (!same) part_release_graph(q0);
@@ -1400,7 +1856,7 @@ int o3d_cuda_particles_advect(o3d_ctx* c, o3d_particles* p, int order, double ti
       per_step = d0.launches - before;
       done = 1;
     }
-    if (nd == 1 && c->use_graphs && done < nsteps && !q0.graph_failed) {
+    if (nd == 1 && c->use_graphs && !p->has_body && done < nsteps && !q0.graph_failed) {   // (a body's solve is a host call)
       if (!q0.graph) {
         const bool prof = d0.profile;
         d0.profile = false;
@@ -1447,6 +1903,12 @@ int o3d_cuda_particles_advect(o3d_ctx* c, o3d_particles* p, int order, double ti
     for (int k = 0; k < nd; ++k) {
       Device& d = c->dev[k];
       O3D_TRY(d, cudaEventElapsedTime(&d.kernel_ms, p->dev[k].ev[0], p->dev[k].ev[1]));
+      if (p->has_body && p->dev[k].n > 0) {
+        unsigned long long m = 0;
+        O3D_TRY(d, cudaSetDevice(d.id));
+        O3D_TRY(d, cudaMemcpy(&m, p->dev[k].body.cnt.as<unsigned long long>() + 2, sizeof m, cudaMemcpyDeviceToHost));
+        p->moved += (int64_t)m;
+      }
     }
     return true;
   };
@@ -1470,7 +1932,7 @@ int o3d_cuda_particles_stats(o3d_ctx* c, o3d_particles* p, float* max_str, float
                                                              prow(q.main, q.cap, kRowS + 2), prow(q.main, q.cap, kRowE), q.stats.as<uint32_t>());
       O3D_TRY(d, cudaGetLastError());
       d.launches += 1;
-      O3D_TRY(d, cudaMemcpyAsync(h, q.stats.p, sizeof h, cudaMemcpyDeviceToHost, d.stream));
+      if (!d2h(d, d.stream, h, q.stats.p, sizeof h)) return false;
       O3D_TRY(d, cudaStreamSynchronize(d.stream));
       return true;
     };
@@ -1484,6 +1946,181 @@ int o3d_cuda_particles_stats(o3d_ctx* c, o3d_particles* p, float* max_str, float
   if (max_str) *max_str = std::sqrt(ms);   // ElementBase::get_max_str returns sqrt of the largest |s|^2
   if (max_elong) *max_elong = me;
   return collect(c);
+}
+
+// ---- a static body attached to a resident collection (SURVEY.md 8 f: Convection::find_vels / advect with boundaries) ----
+int o3d_cuda_particles_set_body(o3d_ctx* c, o3d_particles* p, int64_t nn, const float* nx, const float* ny, const float* nz, int64_t np,
+                                const uint32_t* idx, const float* area, const float* nrm, float cutoff_mult, float ips,
+                                o3d_bem_solve_fn solve, void* user) {
+  if (!c || !p || p->dev.size() != c->dev.size() || nn < 1 || np < 1 || nn >= (int64_t(1) << 31) || np >= (int64_t(1) << 31))
+    return fail(c, O3D_ERR_INVALID, "particles_set_body: bad argument");
+  if (!nx || !ny || !nz || !idx || !area || !nrm) return fail(c, O3D_ERR_INVALID, "particles_set_body: NULL array");
+  if (!valid_indices(idx, np, nn)) return fail(c, O3D_ERR_INVALID, "particles_set_body: node index out of range");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  const int64_t npad = padded_panels(np), rpad = ((np + kRefTile - 1) / kRefTile) * kRefTile;
+  p->b_nn = nn; p->b_np = np;
+  p->solve = solve; p->solve_user = user;
+  p->cutoff_mult = cutoff_mult; p->ips = ips;
+  for (size_t k = 0; k < c->dev.size(); ++k) {
+    Device& d = c->dev[k];
+    BodyDev& b = p->dev[k].body;
+    part_release_graph(p->dev[k]);
+    auto go = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      cudaStream_t st = d.stream;
+      O3D_TRY(d, b.geom.ensure(((size_t)3 * nn + (size_t)11 * np) * 4));
+      O3D_TRY(d, b.panels.ensure((size_t)npad * kPanRec * sizeof(float4)));
+      O3D_TRY(d, b.refl.ensure((size_t)rpad * kRefRec * sizeof(float4)));
+      O3D_TRY(d, b.pu.ensure((size_t)3 * np * 4));
+      O3D_TRY(d, b.cnt.ensure(4 * sizeof(unsigned long long)));
+      float* gx = body_row(b, nn, np, 0);
+      O3D_TRY(d, cudaMemcpyAsync(gx, nx, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemcpyAsync(gx + nn, ny, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemcpyAsync(gx + 2 * nn, nz, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemcpyAsync(body_row(b, nn, np, 1), idx, (size_t)3 * np * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemsetAsync(body_row(b, nn, np, 2), 0, (size_t)3 * np * 4, st));        // strengths start at zero
+      O3D_TRY(d, cudaMemcpyAsync(body_row(b, nn, np, 3), area, (size_t)np * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemsetAsync(body_row(b, nn, np, 4), 0, (size_t)np * 4, st));
+      O3D_TRY(d, cudaMemcpyAsync(body_row(b, nn, np, 5), nrm, (size_t)3 * np * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemsetAsync(b.cnt.p, 0, 4 * sizeof(unsigned long long), st));
+      if (!body_repack(d, st, p, b, false)) return false;
+      ref_pack_kernel<<<(unsigned)((rpad + 127) / 128), 128, 0, st>>>(np, rpad, gx, gx + nn, gx + 2 * nn, (const uint32_t*)body_row(b, nn, np, 1),
+                                                                     body_row(b, nn, np, 5), b.refl.as<float4>());
+      O3D_TRY(d, cudaGetLastError());
+      d.launches += 1;
+      O3D_TRY(d, cudaStreamSynchronize(st));
+      return true;
+    };
+    if (!go()) break;
+  }
+  const int rc = collect(c);
+  p->has_body = rc == O3D_OK;
+  return rc;
+}
+
+int o3d_cuda_particles_clear_body(o3d_ctx* c, o3d_particles* p) {
+  if (!c || !p || p->dev.size() != c->dev.size()) return fail(c, O3D_ERR_INVALID, "particles_clear_body: bad argument");
+  p->has_body = false;
+  p->solve = nullptr;
+  for (size_t k = 0; k < p->dev.size(); ++k) {
+    cudaSetDevice(c->dev[k].id);
+    BodyDev& b = p->dev[k].body;
+    for (DevBuf* q : {&b.geom, &b.panels, &b.refl, &b.pu, &b.work, &b.cnt}) q->release();
+  }
+  return O3D_OK;
+}
+
+int o3d_cuda_particles_set_body_strengths(o3d_ctx* c, o3d_particles* p, const float* tsx, const float* tsy, const float* tsz, const float* sss) {
+  if (!c || !p || p->dev.size() != c->dev.size() || !p->has_body || !tsx || !tsy || !tsz)
+    return fail(c, O3D_ERR_INVALID, "particles_set_body_strengths: bad argument or no body attached");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  const int64_t nn = p->b_nn, np = p->b_np;
+  for (size_t k = 0; k < c->dev.size(); ++k) {
+    Device& d = c->dev[k];
+    BodyDev& b = p->dev[k].body;
+    auto go = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      cudaStream_t st = d.stream;
+      float* ts = body_row(b, nn, np, 2);
+      O3D_TRY(d, cudaMemcpyAsync(ts, tsx, (size_t)np * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemcpyAsync(ts + np, tsy, (size_t)np * 4, cudaMemcpyHostToDevice, st));
+      O3D_TRY(d, cudaMemcpyAsync(ts + 2 * np, tsz, (size_t)np * 4, cudaMemcpyHostToDevice, st));
+      if (sss) O3D_TRY(d, cudaMemcpyAsync(body_row(b, nn, np, 4), sss, (size_t)np * 4, cudaMemcpyHostToDevice, st));
+      if (!body_repack(d, st, p, b, sss != nullptr)) return false;
+      O3D_TRY(d, cudaStreamSynchronize(st));
+      return true;
+    };
+    if (!go()) break;
+  }
+  return collect(c);
+}
+
+// The BEM right-hand-side velocities of the CURRENT state without solving: zero, particles -> panels, finalize_vels(fs)
+int o3d_cuda_particles_body_vels(o3d_ctx* c, o3d_particles* p, const double* fs, float* pu, float* pv, float* pw) {
+  if (!c || !p || !fs || !pu || !pv || !pw || p->dev.size() != c->dev.size() || !p->has_body)
+    return fail(c, O3D_ERR_INVALID, "particles_body_vels: bad argument or no body attached");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  if (p->n == 0) return collect(c);
+  struct Grab { float* out[3]; int64_t np; };
+  Grab g{{pu, pv, pw}, p->b_np};
+  const o3d_bem_solve_fn keep = p->solve;
+  void* keep_user = p->solve_user;
+  p->solve = [](void* user, int64_t np, const float* v, float*, float*, float*, float*, int*) {
+    Grab* q = (Grab*)user;
+    for (int a = 0; a < 3; ++a) std::memcpy(q->out[a], v + (size_t)a * np, (size_t)np * 4);
+    return 1;     // "do not touch the strengths": reported as a refusal, recognised below
+  };
+  p->solve_user = &g;
+  // pack + exchange the main state, then the right-hand side; the evaluation that normally follows is skipped
+  const int nd = (int)c->dev.size();
+  bool ok = true;
+  for (int k = 0; k < nd && ok; ++k) {
+    Device& d = c->dev[k];
+    PartDev& q = p->dev[k];
+    if (q.n == 0) continue;
+    auto go = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      PartView v = view_main(q);
+      float4* slice = q.packed.as<float4>() + (size_t)q.t0 * 2;
+      if (!launch_pack(d, d.stream, q.n, v.x[0], v.x[1], v.x[2], v.r, v.s[0], v.s[1], v.s[2], slice, padded_sources(q.n))) return false;
+      if (nd > 1) O3D_TRY(d, cudaEventRecord(q.packed_ready, d.stream));
+      return true;
+    };
+    ok = go();
+  }
+  if (ok && nd > 1) {
+    Device& d = c->dev[0];
+    PartDev& q = p->dev[0];
+    auto pull = [&]() {
+      O3D_TRY(d, cudaSetDevice(d.id));
+      for (int j = 1; j < nd; ++j) {
+        PartDev& o = p->dev[j];
+        if (o.n == 0) continue;
+        O3D_TRY(d, cudaStreamWaitEvent(d.stream, o.packed_ready, 0));
+        const size_t off = (size_t)o.t0 * 32, bytes = (size_t)padded_sources(o.n) * 32;
+        O3D_TRY(d, cudaMemcpyPeerAsync((char*)q.packed.p + off, d.id, (const char*)o.packed.p + off, c->dev[j].id, bytes, d.stream));
+      }
+      return true;
+    };
+    ok = pull();
+  }
+  if (ok) {
+    body_solve(c, p, fs);
+    Device& d0 = c->dev[0];
+    if (d0.status == cudaErrorUnknown) d0.status = cudaSuccess;     // the grabber's "refusal" is not an error
+  }
+  p->solve = keep;
+  p->solve_user = keep_user;
+  if (ok) part_sync_all(c, p);
+  return collect(c);
+}
+
+int o3d_cuda_particles_clear_inner(o3d_ctx* c, o3d_particles* p, int64_t* num_moved) {
+  if (!c || !p || p->dev.size() != c->dev.size() || !p->has_body) return fail(c, O3D_ERR_INVALID, "particles_clear_inner: bad argument or no body attached");
+  for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
+  if (num_moved) *num_moved = 0;
+  if (p->n == 0) return collect(c);
+  for (size_t k = 0; k < c->dev.size(); ++k) {
+    if (p->dev[k].n == 0) continue;
+    cudaSetDevice(c->dev[k].id);
+    cudaMemsetAsync(p->dev[k].body.cnt.p, 0, 4 * sizeof(unsigned long long), c->dev[k].stream);
+  }
+  if (body_clear_inner(c, p, 0) && part_sync_all(c, p)) {
+    for (size_t k = 0; k < c->dev.size(); ++k) {
+      if (p->dev[k].n == 0) continue;
+      unsigned long long m = 0;
+      cudaSetDevice(c->dev[k].id);
+      if (cudaMemcpy(&m, p->dev[k].body.cnt.as<unsigned long long>() + 2, sizeof m, cudaMemcpyDeviceToHost) == cudaSuccess && num_moved) *num_moved += (int64_t)m;
+    }
+  }
+  return collect(c);
+}
+
+int o3d_cuda_particles_body_counters(const o3d_particles* p, int64_t* moved, int* solves) {
+  if (!p) return O3D_ERR_INVALID;
+  if (moved) *moved = p->moved;
+  if (solves) *solves = p->solves;
+  return O3D_OK;
 }
 
 // Status-file quantities of a resident collection: total circulation and linear impulse
@@ -1507,7 +2144,7 @@ int o3d_cuda_particles_totals(o3d_ctx* c, o3d_particles* p, double* circ, double
       pts_totals_finish_kernel<<<1, 32, 0, d.stream>>>(kBlocks, part, part + (size_t)kBlocks * 6);
       O3D_TRY(d, cudaGetLastError());
       d.launches += 2;
-      O3D_TRY(d, cudaMemcpyAsync(h, part + (size_t)kBlocks * 6, sizeof h, cudaMemcpyDeviceToHost, d.stream));
+      if (!d2h(d, d.stream, h, part + (size_t)kBlocks * 6, sizeof h)) return false;
       O3D_TRY(d, cudaStreamSynchronize(d.stream));
       return true;
     };
@@ -1617,11 +2254,11 @@ int o3d_cuda_bem_op_create(o3d_ctx* c, int64_t snn, const float* snx, const floa
       O3D_TRY(d, q.y.ensure((size_t)3 * q.ni * 4));
       O3D_TRY(d, q.cnt.ensure(2 * sizeof(unsigned long long)));
       float* db = q.bases.as<float>();
-      O3D_TRY(d, cudaMemcpyAsync(db, sb1, (size_t)3 * nsp * 4, cudaMemcpyHostToDevice, st));
-      O3D_TRY(d, cudaMemcpyAsync(db + 3 * nsp, sb2, (size_t)3 * nsp * 4, cudaMemcpyHostToDevice, st));
-      O3D_TRY(d, cudaMemcpyAsync(db + 6 * nsp, tb1, (size_t)3 * ntp * 4, cudaMemcpyHostToDevice, st));
-      O3D_TRY(d, cudaMemcpyAsync(db + 6 * nsp + 3 * ntp, tb2, (size_t)3 * ntp * 4, cudaMemcpyHostToDevice, st));
-      O3D_TRY(d, cudaMemcpyAsync(db + 6 * nsp + 6 * ntp, tnrm, (size_t)3 * ntp * 4, cudaMemcpyHostToDevice, st));
+      if (!h2d(d, st, db, sb1, (size_t)3 * nsp * 4)) return false;
+      if (!h2d(d, st, db + 3 * nsp, sb2, (size_t)3 * nsp * 4)) return false;
+      if (!h2d(d, st, db + 6 * nsp, tb1, (size_t)3 * ntp * 4)) return false;
+      if (!h2d(d, st, db + 6 * nsp + 3 * ntp, tb2, (size_t)3 * ntp * 4)) return false;
+      if (!h2d(d, st, db + 6 * nsp + 6 * ntp, tnrm, (size_t)3 * ntp * 4)) return false;
       if (!upload_panels(d, st, q.spanels, snn, snx, sny, snz, nsp, sidx, nullptr, nullptr, nullptr, sarea, nullptr)) return false;
       O3D_TRY(d, cudaStreamSynchronize(st));   // d.geom is reused by the second upload
       if (!upload_panels(d, st, q.tpanels, tnn, tnx, tny, tnz, ntp, tidx, nullptr, nullptr, nullptr, tarea, nullptr)) return false;
@@ -1663,7 +2300,7 @@ int o3d_cuda_bem_op_apply(o3d_ctx* c, o3d_bem_op* op, const float* x, float* y, 
       O3D_TRY(d, cudaSetDevice(d.id));
       cudaStream_t st = d.stream;
       O3D_TRY(d, cudaEventRecord(d.ev[0], st));
-      O3D_TRY(d, cudaMemcpyAsync(q.x.p, x, (size_t)3 * nsp * 4, cudaMemcpyHostToDevice, st));
+      if (!h2d(d, st, q.x.p, x, (size_t)3 * nsp * 4)) return false;
       O3D_TRY(d, cudaMemsetAsync(q.cnt.p, 0, 2 * sizeof(unsigned long long), st));
       O3D_TRY(d, cudaEventRecord(d.ev[1], st));
       float* db = q.bases.as<float>();
@@ -1688,8 +2325,8 @@ int o3d_cuda_bem_op_apply(o3d_ctx* c, o3d_bem_op* op, const float* x, float* y, 
       O3D_TRY(d, cudaGetLastError());
       d.launches += 2;
       O3D_TRY(d, cudaEventRecord(d.ev[2], st));
-      O3D_TRY(d, cudaMemcpyAsync(y + 3 * q.i0, q.y.p, (size_t)3 * q.ni * 4, cudaMemcpyDeviceToHost, st));
-      O3D_TRY(d, cudaMemcpyAsync(d.counts, q.cnt.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      if (!d2h(d, st, y + 3 * q.i0, q.y.p, (size_t)3 * q.ni * 4)) return false;
+      if (!d2h(d, st, d.counts, q.cnt.p, 2 * sizeof(unsigned long long))) return false;
       O3D_TRY(d, cudaEventRecord(d.ev[3], st));
       return true;
     };
@@ -1743,13 +2380,13 @@ int closest_point_pass(o3d_ctx* c, const char* who, int mode, float cutoff, int6
     float* gnrm = g + 3 * nn + 3 * np;
     float* dt = d.targ.as<float>();
     O3D_TRY(d, cudaEventRecord(d.ev[0], st));
-    O3D_TRY(d, cudaMemcpyAsync(g, nx, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
-    O3D_TRY(d, cudaMemcpyAsync(g + nn, ny, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
-    O3D_TRY(d, cudaMemcpyAsync(g + 2 * nn, nz, (size_t)nn * 4, cudaMemcpyHostToDevice, st));
-    O3D_TRY(d, cudaMemcpyAsync(gidx, idx, (size_t)3 * np * 4, cudaMemcpyHostToDevice, st));
-    O3D_TRY(d, cudaMemcpyAsync(gnrm, nrm, (size_t)3 * np * 4, cudaMemcpyHostToDevice, st));
+    if (!h2d(d, st, g, nx, (size_t)nn * 4)) return false;
+    if (!h2d(d, st, g + nn, ny, (size_t)nn * 4)) return false;
+    if (!h2d(d, st, g + 2 * nn, nz, (size_t)nn * 4)) return false;
+    if (!h2d(d, st, gidx, idx, (size_t)3 * np * 4)) return false;
+    if (!h2d(d, st, gnrm, nrm, (size_t)3 * np * 4)) return false;
     float* hx[3] = {tx, ty, tz};
-    for (int a = 0; a < 3; ++a) O3D_TRY(d, cudaMemcpyAsync(dt + (size_t)a * n, hx[a] + t0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    for (int a = 0; a < 3; ++a) if (!h2d(d, st, dt + (size_t)a * n, hx[a] + t0, (size_t)n * 4)) return false;
     if (!zero_counts(d, st)) return false;
     O3D_TRY(d, cudaEventRecord(d.ev[1], st));
     ref_pack_kernel<<<(unsigned)((npad + 127) / 128), 128, 0, st>>>(np, npad, g, g + nn, g + 2 * nn, gidx, gnrm, d.panels.as<float4>());
@@ -1768,7 +2405,7 @@ int closest_point_pass(o3d_ctx* c, const char* who, int mode, float cutoff, int6
     O3D_TRY(d, cudaGetLastError());
     d.launches += 2;
     O3D_TRY(d, cudaEventRecord(d.ev[2], st));
-    for (int a2 = 0; a2 < 3; ++a2) O3D_TRY(d, cudaMemcpyAsync(hx[a2] + t0, dt + (size_t)a2 * n, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    for (int a2 = 0; a2 < 3; ++a2) if (!d2h(d, st, hx[a2] + t0, dt + (size_t)a2 * n, (size_t)n * 4)) return false;
     if (!fetch_counts(d, st)) return false;
     O3D_TRY(d, cudaEventRecord(d.ev[3], st));
     return finish_timing(d);
@@ -1828,6 +2465,18 @@ int o3d_cuda_particles_write_vtu(o3d_ctx* c, o3d_particles* p, const char* path,
 int o3d_cuda_set_graphs(o3d_ctx* c, int on) {
   if (!c) return O3D_ERR_INVALID;
   c->use_graphs = on != 0;
+  return O3D_OK;
+}
+
+int o3d_cuda_set_panel_queue(o3d_ctx* c, int on) {
+  if (!c) return O3D_ERR_INVALID;
+  for (Device& d : c->dev) d.pan_queue = on != 0;
+  return O3D_OK;
+}
+
+int o3d_cuda_set_host_staging(o3d_ctx* c, int on) {
+  if (!c) return O3D_ERR_INVALID;
+  for (Device& d : c->dev) d.stage.enabled = on != 0;
   return O3D_OK;
 }
 

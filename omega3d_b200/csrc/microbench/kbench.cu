@@ -136,7 +136,7 @@ int main(int argc, char** argv) {
       } else {
         kern<<<grid, BLOCK>>>(a);
       }
-      if (grid > 1) pp_fixup_kernel<<<grid - 1, BLOCK * T>>>(grad ? 12 : 3, plan, n, ppwork, a.tu, a.tv, a.tw, a.tug, n, 1.0f);
+      if (grid > 1) pp_fixup_kernel<<<grid - 1, BLOCK * T>>>(grad ? 12 : 3, plan, n, ppwork, a.tu, a.tv, a.tw, a.tug, n, 1.0f, nullptr, 0);
       cudaEventRecord(e1);
       CHECK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, e0, e1);

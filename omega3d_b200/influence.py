@@ -233,6 +233,17 @@ class Surfaces:
         """src/Surfaces.h:309-335: ts = (ps0 * x1 + ps1 * x2) * area."""
         self.ts = np.ascontiguousarray(((self.ps[0] * self.b1 + self.ps[1] * self.b2) * self.area).astype(f32))
 
+    def num_unknowns_per_panel(self):
+        """src/Surfaces.h: two vortex-sheet components plus the source sheet (flow_over_sphere.json's body)."""
+        return 3
+
+    def set_str(self, new_s):
+        """src/Surfaces.h:267-306: the BEM-solved (x1, x2, source) sheet strengths per panel, interleaved, into ps; then
+        the total panel strengths ts."""
+        new_s = np.ascontiguousarray(new_s, f32).reshape(self.np_, 3)
+        self.ps[:] = new_s.T
+        self.vortex_sheet_to_panel_strength()
+
     def represent_as_particles(self, offset: float, ips: float = -1.0) -> "Points":
         """src/Surfaces.h:959-1010: one inert-position / total-strength particle per panel at
         centroid + offset * normal (used by panels_affect_panels with offset 1e-4)."""
@@ -294,6 +305,14 @@ class CudaContext:
 
     def tuned_kernels(self) -> bool:
         return bool(self.lib.o3d_cuda_tuned_kernels(self.h))
+
+    def set_panel_queue(self, on: bool):
+        """panels -> points with the warp-level work queue for subdividing pairs (default) or the per-lane round-1 kernel."""
+        self.check(self.lib.o3d_cuda_set_panel_queue(self.h, int(on)))
+
+    def set_host_staging(self, on: bool):
+        """Pageable host arrays through the context's pinned staging ring (default) or straight to cudaMemcpyAsync."""
+        self.check(self.lib.o3d_cuda_set_host_staging(self.h, int(on)))
 
     def set_core_func(self, core):
         """Core function of the particle kernels: a core_t / its number / its name ("wl", "rm", "exp", "v2"). The

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Secondary measurement (not the headline bench): the panel kernels on the flow_over_sphere geometry
 (BASELINE configs[3]) through the host C ABI, next to the reference's CPU routines on a bounded sample.
-Prints one JSON line per routine. Usage: python tests/perf/bench_panels.py [levels=2] [particles=1000000]"""
+Prints one JSON line per routine. Usage: python tests/perf/bench_panels.py [levels=2] [particles=1000000] [queue|noqueue]
+(noqueue: panels -> points with the per-lane round-1 kernel instead of the warp-level work queue)"""
 import json
 import os
 import sys
@@ -33,6 +34,8 @@ def main():
     x = np.ascontiguousarray(x.astype(f32))
     s = ((rng.random((3, n), dtype=f32) - f32(0.5)) / f32(n)).astype(f32)
     ctx = I.CudaContext((0,))
+    queue = not (len(sys.argv) > 3 and sys.argv[3] == "noqueue")
+    ctx.set_panel_queue(queue)
     try:
         ref = oracle_py.Reference(fast=True)
     except Exception:
@@ -41,7 +44,7 @@ def main():
     sel = W.strided_subset(n, 2048)
 
     def emit(name, pairs, ms, flops, cpu_rate, err):
-        print(json.dumps({"routine": name, "panels": npan, "particles": n, "pairs_per_s": pairs / (ms * 1e-3), "kernel_ms": ms,
+        print(json.dumps({"routine": name, "panel_queue": queue, "panels": npan, "particles": n, "pairs_per_s": pairs / (ms * 1e-3), "kernel_ms": ms,
                           "gflops_reference_count": flops / (ms * 1e-3) * 1e-9, "cpu_pairs_per_s": cpu_rate,
                           "cpu_cores": res.max_threads(), "max_rel_err_vs_oracle_sample": err}), flush=True)
 
@@ -103,7 +106,7 @@ def main():
         xs = np.ascontiguousarray(x[:, sel])
         t0 = time.perf_counter(); ofn(xs); dt = time.perf_counter() - t0
         same = bool(np.array_equal(pts.x[:, sel], xs))
-        print(json.dumps({"routine": name, "panels": npan, "particles": n, "pairs_per_s": npan * n / (t["kernel_ms"] * 1e-3),
+        print(json.dumps({"routine": name, "panel_queue": queue, "panels": npan, "particles": n, "pairs_per_s": npan * n / (t["kernel_ms"] * 1e-3),
                           "kernel_ms": t["kernel_ms"], "gflops_reference_count": 149.0 * npan * n / (t["kernel_ms"] * 1e-3) * 1e-9,
                           "cpu_pairs_per_s": npan * sel.size / dt, "cpu_cores": res.max_threads(), "moved": moved,
                           "bit_identical_to_oracle_on_sample": same}), flush=True)

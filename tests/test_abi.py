@@ -186,3 +186,18 @@ def test_stream_k_bookkeeping_replayed_on_the_host():
         for grad in (0, 1):
             for sms in (148, 132, 1, 7):
                 assert lib.o3d_cuda_plan_check(sms, ns, nt, grad) == 0, (ns, nt, grad, sms)
+
+
+def test_patch_keeps_the_reference_else_chain():
+    """integration/omega3d_use_cuda.patch, Influence.h hunk: the reference's GL arm ends in a dangling `} else // if not
+    gpu_opengl` whose statement is the CPU block. The CUDA arm inserted between the two must itself end in `else`, or - in a
+    build with USE_OGL_COMPUTE and USE_CUDA both defined - the CPU block would run unconditionally after a GL dispatch that
+    found its compute state busy."""
+    import re
+    text = open(os.path.join(ROOT, "integration", "omega3d_use_cuda.patch")).read()
+    hunk = text[text.index("   } else // if not gpu_opengl"):text.index("   { // perform summations using internal CPU solver")]
+    added = [l[1:] for l in hunk.splitlines() if l.startswith("+")]
+    assert added[0] == "#ifdef USE_CUDA" and added[-2] == "#endif"
+    body = "\n".join(added[1:-2])
+    assert re.match(r"\s*if \(env\.is_internal\(\) and env\.get_instrs\(\) == gpu_cuda\) \{", body)
+    assert re.search(r"return;\s*\} else\b[^\n]*$", body), "the CUDA arm must end in `} else`"

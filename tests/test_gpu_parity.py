@@ -254,6 +254,51 @@ def test_translation_invariance_and_self_term(cuda_ctx):
     assert g[1, 0] == -g[3, 0] != 0 and g[2, 0] == -g[6, 0] != 0 and g[5, 0] == -g[7, 0] != 0
 
 
+def test_host_path_pageable_pinned_and_unstaged_give_the_same_bits(cuda_ctx):
+    """The host entry point stages pageable arrays through pinned slots, uploads the caller's initial outputs while the kernel
+    runs and adds the FP64 sums afterwards; pinned arrays skip the staging; staging can be switched off. All of that is
+    plumbing: the outputs (accumulated onto non-zero initial values) must be the same bits in every mode, and equal to the
+    device-resident path with its fused read-modify-write."""
+    import torch
+    from omega3d_b200.device import DeviceBiotSavart
+    n = 300000                 # 1.2 MB per array: several staging decisions per call, ragged tail
+    x, s, r = W.random_cloud(n, seed=61)
+    nt = 150001
+    tx, tr = np.ascontiguousarray(x[:, :nt]), r[:nt].copy()
+    rng = np.random.Generator(np.random.MT19937(62))
+    u0 = rng.standard_normal((3, nt)).astype(f32)
+    g0 = rng.standard_normal((9, nt)).astype(f32)
+    outs = []
+    for mode in ("pageable", "unstaged", "pinned"):
+        cuda_ctx.set_host_staging(mode != "unstaged")
+        if mode == "pinned":
+            keep = [torch.from_numpy(a.copy()).pin_memory() for a in (x, s, r, tx, tr, u0, g0)]
+            ax, as_, ar, atx, atr, u, g = [k.numpy() for k in keep]
+        else:
+            ax, as_, ar, atx, atr, u, g = x, s, r, tx, tr, u0.copy(), g0.copy()
+        cuda_ctx.pts_on_pts(ax, ar, as_, atx, atr, u, g)
+        outs.append((u.copy(), g.copy()))
+    cuda_ctx.set_host_staging(True)
+    for u, g in outs[1:]:
+        assert np.array_equal(u.view(np.uint32), outs[0][0].view(np.uint32)) and np.array_equal(g.view(np.uint32), outs[0][1].view(np.uint32))
+    # device-resident path: fused read-modify-write in the kernel's epilogue
+    eng = DeviceBiotSavart(0, cuda_ctx)
+    dev = eng.device
+    packed = eng.pack(torch.from_numpy(x).to(dev), torch.from_numpy(s).to(dev), torch.from_numpy(r).to(dev))
+    du, dg = torch.from_numpy(u0).to(dev), torch.from_numpy(g0).to(dev)
+    eng.pts_on_pts(packed, torch.from_numpy(tx).to(dev), torch.from_numpy(tr).to(dev), du, dg)
+    torch.cuda.synchronize()
+    assert np.array_equal(du.cpu().numpy().view(np.uint32), outs[0][0].view(np.uint32))
+    assert np.array_equal(dg.cpu().numpy().view(np.uint32), outs[0][1].view(np.uint32))
+    # velocity only, singular targets, through the same plumbing
+    u1, u2 = u0.copy(), u0.copy()
+    cuda_ctx.pts_on_pts(x, r, s, tx, None, u1, None)
+    cuda_ctx.set_host_staging(False)
+    cuda_ctx.pts_on_pts(x, r, s, tx, None, u2, None)
+    cuda_ctx.set_host_staging(True)
+    assert np.array_equal(u1.view(np.uint32), u2.view(np.uint32)) and not np.array_equal(u1, u0)
+
+
 def test_two_device_context_equals_one_device(cuda_ctx):
     """In-process multi-GPU (one context driving 2 GPUs): targets are partitioned across the devices, sources
     replicated; every target's sum is computed by exactly one device."""
