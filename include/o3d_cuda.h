@@ -214,17 +214,18 @@ int o3d_cuda_particles_stats(o3d_ctx* ctx, o3d_particles* p, float* max_str, flo
 /* ---- a static body attached to a resident collection (Convection::find_vels / advect with boundaries) ---------------
  * With a body attached, o3d_cuda_particles_find_vels adds panels -> particles to the particle sums (src/Convection.h:157-167)
  * and o3d_cuda_particles_advect runs the reference's sequence for a system with a boundary: before every derivative
- * evaluation the BEM right-hand side of that state - panel-centre velocities from the particles, zero_vels /
- * points_affect_panels / finalize_vels(fs) (src/BEMHelper.h:83-103) - is formed on the device and handed to `solve`, which
- * returns the panels' total vortex strengths (and source strengths): the solve itself is the reference's host code
- * (src/BEM.h, Eigen GMRES) and stays there; after every move clear_inner_layer(1, body, particles, cutoff_mult, ips)
- * (src/Reflect.h:625-655) runs on the moved state. Particle arrays never leave the device; per evaluation 3 np floats go
- * to the host and 4 np come back.
+ * evaluation the device forms what solve_bem (src/BEMHelper.h:44-262) starts with - panel-centre velocities zeroed, then
+ * points_affect_panels from the state's particles (:83-94; un-normalised, subtracted as the reference subtracts them) - and
+ * hands them to `solve`, the REST of solve_bem: finalize_vels(fs), right-hand side (src/RHS.h), A, the solve (src/BEM.h,
+ * Eigen GMRES), set_str. That is the reference's host code and stays there; it returns the panels' total vortex strengths
+ * (and source strengths). After every move clear_inner_layer(1, body, particles, cutoff_mult, ips) (src/Reflect.h:625-655)
+ * runs on the moved state. Particle arrays never leave the device; per evaluation 3 np floats go to the host and 4 np
+ * come back.
  *
- * solve(user, np, pu, tsx, tsy, tsz, sss, have_source): pu = 3 x np floats (u | v | w rows) IN; tsx.. = np floats each OUT
- * (Surfaces::get_str after set_str, src/Surfaces.h:267-335); sss = np source strengths OUT, used iff *have_source is set
- * non-zero. Returns 0, anything else aborts the call with O3D_ERR_CUDA. solve may be NULL: the strengths then stay what
- * o3d_cuda_particles_set_body_strengths last set (zero after set_body).
+ * solve(user, np, pu, tsx, tsy, tsz, sss, have_source): pu = 3 x np floats (u | v | w rows), the raw sums, IN; tsx.. = np
+ * floats each OUT (Surfaces::get_str after set_str, src/Surfaces.h:267-335); sss = np source strengths OUT, used iff
+ * *have_source is set non-zero. Returns 0, anything else aborts the call with O3D_ERR_CUDA. solve may be NULL: the
+ * strengths then stay what o3d_cuda_particles_set_body_strengths last set (zero after set_body).
  * nodes SoA (nn), idx 3 per panel, area np, nrm 3 x np (x | y | z rows) as the reference's Surfaces holds them. */
 typedef int (*o3d_bem_solve_fn)(void* user, int64_t np, const float* pu, float* tsx, float* tsy, float* tsz, float* sss, int* have_source);
 int o3d_cuda_particles_set_body(o3d_ctx* ctx, o3d_particles* p, int64_t nn, const float* nx, const float* ny, const float* nz,
@@ -233,8 +234,8 @@ int o3d_cuda_particles_set_body(o3d_ctx* ctx, o3d_particles* p, int64_t nn, cons
 int o3d_cuda_particles_clear_body(o3d_ctx* ctx, o3d_particles* p);
 int o3d_cuda_particles_set_body_strengths(o3d_ctx* ctx, o3d_particles* p, const float* tsx, const float* tsy, const float* tsz,
                                           const float* sss /* NULL: no source sheet */);
-/* The right-hand-side velocities of the current state alone (no solve, strengths untouched): np floats each. */
-int o3d_cuda_particles_body_vels(o3d_ctx* ctx, o3d_particles* p, const double* fs, float* pu, float* pv, float* pw);
+/* Those raw panel-centre sums of the current state alone (no solve, strengths untouched): np floats each. */
+int o3d_cuda_particles_body_vels(o3d_ctx* ctx, o3d_particles* p, float* pu, float* pv, float* pw);
 /* clear_inner_layer on the resident positions, outside a step (src/Simulation.cpp:839 after diffusion). */
 int o3d_cuda_particles_clear_inner(o3d_ctx* ctx, o3d_particles* p, int64_t* num_moved);
 /* Of the last o3d_cuda_particles_advect: particles pushed out by its clear-inner passes, BEM solves requested. */

@@ -72,6 +72,19 @@ inline void cuda_check(int rc, const char* what) {
   std::abort();
 }
 
+// While a convection step runs on RESIDENT particles around a body (O3DCudaConvection.h), the host copy of the particle
+// collection is stale. The reference's solve_bem (src/BEMHelper.h:83-94) still asks for points_affect_panels(vort, bdry) at that
+// moment; the sums it wants have just been formed on the device from the resident state. This slot carries them: when it
+// is armed, the gpu_cuda arm of points_affect_panels adds them into the target instead of evaluating the (stale) host arrays.
+struct ResidentPanelSums {
+  const float* raw = nullptr;    // 3 x np floats (u | v | w rows): zero minus the particle sums, un-normalised
+  int64_t np = 0;
+};
+inline ResidentPanelSums& resident_panel_sums() {
+  static thread_local ResidentPanelSums s;
+  return s;
+}
+
 // `want_grad`: the caller's results type asks for gradients (ResultsType::compute_grad / get_type()==velandgrad).
 template <class PointsT>
 double cuda_points_affect_points(const PointsT& src, PointsT& targ, const bool want_grad) {
@@ -131,6 +144,13 @@ double cuda_points_affect_panels(const PointsT& src, SurfacesT& targ) {
   const auto& ta = targ.get_area();
   auto& tu = targ.get_vel();
   double flops = 0.0;
+  const ResidentPanelSums& rs = resident_panel_sums();
+  if (rs.raw) {                  // a resident step is in flight: its device state is the source, not src's host arrays
+    if ((int64_t)targ.get_npanels() != rs.np) cuda_check(O3D_ERR_INVALID, "points_affect_panels (resident sums for another surface)");
+    for (int d = 0; d < 3; ++d)
+      for (int64_t i = 0; i < rs.np; ++i) tu[d][i] += rs.raw[(size_t)d * rs.np + i];
+    return 3.0 * (double)rs.np;
+  }
   cuda_check(o3d_cuda_pts_on_pan(cuda_context(), (int64_t)src.get_n(), sx[0].data(), sx[1].data(), sx[2].data(), ss[0].data(),
                                  ss[1].data(), ss[2].data(), (int64_t)tx[0].size(), tx[0].data(), tx[1].data(), tx[2].data(),
                                  (int64_t)targ.get_npanels(), ti.data(), ta.data(), tu[0].data(), tu[1].data(), tu[2].data(), &flops),

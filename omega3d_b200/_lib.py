@@ -47,7 +47,7 @@ SYMBOLS = {
     "o3d_cuda_particles_set_body": (c_int, [c_void_p, c_void_p, c_int64, _P, _P, _P, c_int64, _P, _P, _P, ctypes.c_float, ctypes.c_float, _P, _P]),
     "o3d_cuda_particles_clear_body": (c_int, [c_void_p, c_void_p]),
     "o3d_cuda_particles_set_body_strengths": (c_int, [c_void_p, c_void_p, _P, _P, _P, _P]),
-    "o3d_cuda_particles_body_vels": (c_int, [c_void_p, c_void_p, POINTER(c_double), _P, _P, _P]),
+    "o3d_cuda_particles_body_vels": (c_int, [c_void_p, c_void_p, _P, _P, _P]),
     "o3d_cuda_particles_clear_inner": (c_int, [c_void_p, c_void_p, POINTER(c_int64)]),
     "o3d_cuda_particles_body_counters": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int)]),
     "o3d_cuda_particles_totals": (c_int, [c_void_p, c_void_p, POINTER(c_double), POINTER(c_double)]),

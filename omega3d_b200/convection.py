@@ -115,9 +115,10 @@ class DeviceParticles:
 
     # ---- a static body attached to the collection (include/o3d_cuda.h: o3d_cuda_particles_set_body) ----
     def set_body(self, surf, ips: float, solve=None, cutoff_mult: float = CLEAR_INNER_CUTOFF):
-        """surf: influence.Surfaces. solve(pu (3,np) float32 - the finalized panel-centre velocities of the state) must return
-        (ts (3,np), sss (np,) or None): the panels' total vortex strengths and source strengths - the BEM solve, host code as in
-        the reference. None: strengths stay what set_body_strengths last set."""
+        """surf: influence.Surfaces. solve(pu (3,np) float32 - the raw panel-centre sums of the state: zeroed, then
+        points_affect_panels) is the rest of solve_bem (finalize_vels, right-hand side, solve, set_str - host code as in the
+        reference) and must return (ts (3,np), sss (np,) or None): the panels' total vortex and source strengths. None:
+        strengths stay what set_body_strengths last set."""
         self._cb_error = None
         cb = None
         if solve is not None:
@@ -152,11 +153,11 @@ class DeviceParticles:
         sss = None if sss is None else np.ascontiguousarray(sss, f32)
         self.ctx.check(self.lib.o3d_cuda_particles_set_body_strengths(self.ctx.h, self.h, _ptr(ts[0]), _ptr(ts[1]), _ptr(ts[2]), _ptr(sss)))
 
-    def body_vels(self, fs=(0.0, 0.0, 0.0)):
-        """Finalized panel-centre velocities induced by the resident particles (+ freestream): the BEM right-hand side before
-        projection (src/BEMHelper.h:83-103). Returns (3,np) float32."""
+    def body_vels(self):
+        """Raw panel-centre sums induced by the resident particles: what solve_bem holds after zero_vels + points_affect_panels
+        (src/BEMHelper.h:83-94), before finalize_vels. Returns (3,np) float32."""
         pu = np.zeros((3, self._body.np_), f32)
-        self.ctx.check(self.lib.o3d_cuda_particles_body_vels(self.ctx.h, self.h, _fs(fs), _ptr(pu[0]), _ptr(pu[1]), _ptr(pu[2])))
+        self.ctx.check(self.lib.o3d_cuda_particles_body_vels(self.ctx.h, self.h, _ptr(pu[0]), _ptr(pu[1]), _ptr(pu[2])))
         return pu
 
     def clear_inner(self) -> int:
@@ -239,6 +240,7 @@ class Convection:
 
             def solve(pu):
                 surf.pu[:] = pu
+                surf.finalize_vels(fs)
                 solve_bem_for(surf, bem)
                 return surf.ts, surf.ps[2]
             d.set_body(surf, ips, solve)

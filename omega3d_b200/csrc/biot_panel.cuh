@@ -572,6 +572,118 @@ __global__ void __launch_bounds__(BLOCK) pts_pan_kernel(const PtsPanArgs p) {
   for (int k = 0; k < 3; ++k) slab[(size_t)k * p.np + i] = sum[k];
 }
 
+// particles -> panels with the warp-level work queue of pan_pts_queue_kernel, roles swapped: a lane owns a target PANEL, the
+// deferred items are (panel, particle) pairs of one 64-particle chunk; whichever lane takes an item fetches the owner's
+// triangle by shuffles, subdivides it against the particle (read from the warp's tile) and returns three partial sums.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pts_pan_queue_kernel(const PtsPanArgs p) {
+  constexpr int NW = BLOCK / 32;
+  constexpr int RET = 5;                                         // row stride of the return buffer (3 sums, odd padding)
+  __shared__ alignas(128) float4 tiles[NW][kTile * 2];
+  __shared__ unsigned short lists[NW][32 * 64];                  // owner << 6 | particle within the chunk
+  __shared__ float rets[NW][32 * RET];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4* tile = tiles[warp];
+  unsigned short* list = lists[warp];
+  float* ret = rets[warp];
+  const int per = (p.ntiles + p.nsplit - 1) / p.nsplit;
+  const int k0 = blockIdx.y * per;
+  const int k1 = min(p.ntiles, k0 + per);
+
+  const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+  const int64_t ic = min(i, p.np - 1);
+  const bool live = i < p.np;
+  const float4* r = p.pan + (size_t)ic * kPanRec;
+  const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4];
+  const Tri t{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
+  const float cx = r3.y, cy = r3.z, cz = r3.w, thr0 = r4.z;   // the squared level-0 threshold (sq_threshold)
+
+  float acc[3] = {0.f, 0.f, 0.f};
+  double sum[3] = {0.0, 0.0, 0.0};
+  unsigned counts[2] = {0u, 0u};
+
+  for (int k = k0; k < k1; ++k) {
+    __syncwarp();
+    const float4* g = p.src + (size_t)k * (kTile * 2);
+#pragma unroll 4
+    for (int e = lane; e < kTile * 2; e += 32) tile[e] = g[e];
+    __syncwarp();
+    const int cnt = (int)min((int64_t)kTile, p.ns - (int64_t)k * kTile);
+#pragma unroll 1
+    for (int c0 = 0; c0 < cnt; c0 += 64) {
+      const int cn = min(64, cnt - c0);
+      unsigned long long near = 0ull;
+      unsigned leaves0 = 0u;
+#pragma unroll 1
+      for (int jj = 0; jj < cn; jj += 2) {
+        const int pr = (c0 + jj) >> 1;
+        const float4 q0 = tile[4 * pr], q1 = tile[4 * pr + 1], q2 = tile[4 * pr + 2], q3 = tile[4 * pr + 3];
+        if (pan_node<false>(cx, cy, cz, thr0, false, -q0.x, -q0.z, -q1.x, q2.x, q2.z, q3.x, 0.0f, acc)) leaves0 += 1;
+        else near |= 1ull << jj;
+        if (jj + 1 < cn) {
+          if (pan_node<false>(cx, cy, cz, thr0, false, -q0.y, -q0.w, -q1.y, q2.y, q2.w, q3.y, 0.0f, acc)) leaves0 += 1;
+          else near |= 1ull << (jj + 1);
+        }
+      }
+      if (live) counts[0] += leaves0;
+      else near = 0ull;
+      const int mine = __popcll(near);
+      int first = mine;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, first, off);
+        if (lane >= off) first += v;
+      }
+      const int total = __shfl_sync(0xffffffffu, first, 31);
+      first -= mine;
+      if (total == 0) continue;
+      {
+        unsigned long long m = near;
+        int at = first;
+        while (m) {
+          const int jj = __ffsll((long long)m) - 1;
+          m &= m - 1ull;
+          list[at++] = (unsigned short)((lane << 6) | jj);
+        }
+      }
+      __syncwarp();
+      for (int base = 0; base < total; base += 32) {
+        const int gi = base + lane;
+        const bool have = gi < total;
+        const unsigned e = have ? list[gi] : (unsigned)(lane << 6);
+        const int owner = (int)(e >> 6), jj = (int)(e & 63u);
+        Tri o;
+        o.x0 = __shfl_sync(0xffffffffu, t.x0, owner); o.y0 = __shfl_sync(0xffffffffu, t.y0, owner); o.z0 = __shfl_sync(0xffffffffu, t.z0, owner);
+        o.x1 = __shfl_sync(0xffffffffu, t.x1, owner); o.y1 = __shfl_sync(0xffffffffu, t.y1, owner); o.z1 = __shfl_sync(0xffffffffu, t.z1, owner);
+        o.x2 = __shfl_sync(0xffffffffu, t.x2, owner); o.y2 = __shfl_sync(0xffffffffu, t.y2, owner); o.z2 = __shfl_sync(0xffffffffu, t.z2, owner);
+        const float othr = __shfl_sync(0xffffffffu, thr0, owner);
+        float part[3] = {0.f, 0.f, 0.f};
+        if (have) {
+          const int j = c0 + jj, pr = j >> 1, h = j & 1;
+          const float4 q0 = tile[4 * pr], q1 = tile[4 * pr + 1], q2 = tile[4 * pr + 2], q3 = tile[4 * pr + 3];
+          const float px = -(h ? q0.y : q0.x), py = -(h ? q0.w : q0.z), pz = -(h ? q1.y : q1.x);
+          const float wx = h ? q2.y : q2.x, wy = h ? q2.w : q2.z, wz = h ? q3.y : q3.x;
+          pan_subdivide<false>(o, othr, wx, wy, wz, 0.0f, px, py, pz, part, counts);
+        }
+        __syncwarp();
+        ret[lane * RET + 0] = part[0]; ret[lane * RET + 1] = part[1]; ret[lane * RET + 2] = part[2];
+        __syncwarp();
+        const int a = max(first, base) - base, b = min(first + mine, base + 32) - base;
+        for (int sl = a; sl < b; ++sl) {
+          acc[0] += ret[sl * RET + 0]; acc[1] += ret[sl * RET + 1]; acc[2] += ret[sl * RET + 2];
+        }
+      }
+    }
+    sum[0] += (double)acc[0]; sum[1] += (double)acc[1]; sum[2] += (double)acc[2];
+    acc[0] = acc[1] = acc[2] = 0.f;
+  }
+  add_counts(p.counts, counts);
+  if (!live) return;
+  double* slab = p.partial + (size_t)blockIdx.y * 3 * p.np;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) slab[(size_t)k * p.np + i] = sum[k];
+}
+
 // ---- panel -> panel BEM coefficient block -------------------------------------------------------------
 // rkernel_2vs_2p (src/Kernels.h:1217-1315): both triangles subdivide, 16 children per level, the
 // strength falls by 1/16, size = sqrt(sa) + sqrt(ta). The reference runs it three times per pair with

@@ -69,6 +69,10 @@
 #define O3D_PP_STAGE 0    // how a source tile reaches shared memory. 0 (product): one cp.async.bulk (TMA) per tile by one elected
 #endif                    // thread + mbarrier; 1: cp.async 16 B x 8 per thread; 2: LDG.128 -> STS.128 through registers. 1 and 2 exist
                           // for microbench/kbench only (make kbench_stage): DESIGN.md section 7 "staging" rows
+#ifndef O3D_PP_TWOBUF
+#define O3D_PP_TWOBUF 1   // 1 (product): the walk alternates two copies of the tile body, one per ring buffer, each with static
+#endif                    // shared-memory addresses; 0: one copy, the buffer's shared address handed to ptxas through a warp
+                          // reduction once per tile (microbench/kbench only: DESIGN.md section 7)
 #ifndef O3D_PP_UNROLL_VEL
 #define O3D_PP_UNROLL_VEL 2    // ... velocity-only kernel
 #endif
@@ -504,10 +508,25 @@ __device__ __forceinline__ void pp2_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
     }
   }
   pp_ring_wait(full, w.kring);
+#if O3D_PP_TWOBUF
   const float4* __restrict__ src = tile[BUF];
+#else
+  // one copy of the body for both buffers: the buffer's shared-memory address, formed once per tile and passed through a warp
+  // reduction (REDUX writes a uniform register) so that ptxas holds it instead of re-deriving it on every trip of the loop
+  const uint32_t sbase = __reduce_max_sync(0xffffffffu, smem_u32(tile[w.kring & 1]));
+#endif
 #pragma unroll(U)
   for (int j = 0; j < kTile / 2; ++j) {
+#if O3D_PP_TWOBUF
     const float4 q0 = src[4 * j], q1 = src[4 * j + 1], q2 = src[4 * j + 2], q3 = src[4 * j + 3];
+#else
+    float4 q0, q1, q2, q3;
+    const uint32_t sa = sbase + (uint32_t)j * 64u;
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(sa));
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(sa));
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+32];" : "=f"(q2.x), "=f"(q2.y), "=f"(q2.z), "=f"(q2.w) : "r"(sa));
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+48];" : "=f"(q3.x), "=f"(q3.y), "=f"(q3.z), "=f"(q3.w) : "r"(sa));
+#endif
 #if O3D_PP_JOINT
     if constexpr (GRAD && UNI && T == 2) {
       const float2 tk = f2(k15, k15), tk5 = f2(k75, k75);          // 32-bit broadcast operands, as in pp_interact2
@@ -529,7 +548,11 @@ __device__ __forceinline__ void pp2_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
 #endif
     pp_promote<GRAD>(h, sum[t]);
   }
+#if O3D_PP_TWOBUF
   pp_ring_refill<BLOCK>(p, w, tile[BUF], &full[BUF]);         // ++w.kring
+#else
+  pp_ring_refill<BLOCK>(p, w, tile[w.kring & 1], &full[w.kring & 1]);
+#endif
   ++s.kt;
   s.fresh = s.kt == p.ntiles || w.kring == w.nk;              // the segment ends with this tile
   if (s.fresh) {
@@ -565,7 +588,9 @@ __device__ __forceinline__ void pp2_walk(const PPArgs& p, PPWalk& w, float4 (&ti
   PPBlock s{w.b0, w.kt0, true, true};
   while (w.kring < w.nk) {
     pp2_tile<0, T, GRAD, UNI, BLOCK>(p, w, s, tile, full, r2u, k15, k75, tx, ty, tz, tr2, acc, sum);
+#if O3D_PP_TWOBUF
     if (w.kring < w.nk) pp2_tile<1, T, GRAD, UNI, BLOCK>(p, w, s, tile, full, r2u, k15, k75, tx, ty, tz, tr2, acc, sum);
+#endif
   }
 }
 

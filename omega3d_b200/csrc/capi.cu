@@ -841,12 +841,13 @@ bool body_clear_inner(o3d_ctx* c, o3d_particles* p, int sel) {
   return true;
 }
 
-// Right-hand side of the BEM solve for one state (solve_bem, src/BEMHelper.h:83-103): zero the panel-centre velocities,
-// particles -> panels (subtracting, src/Influence.h:1210-1212), finalize_vels(fs) (src/Surfaces.h:877-887) on device 0, whose
-// packed stream holds every particle of the state; then the host callback solves for the strengths (the reference's BEM
-// stays host code) and every device repacks its panel records with them. Needs the state's packed stream: call after
-// part_pack_exchange.
+// Right-hand side of the BEM solve for one state (solve_bem, src/BEMHelper.h:83-94): zero the panel-centre velocities,
+// particles -> panels (subtracting, src/Influence.h:1210-1212) on device 0, whose packed stream holds every particle of the
+// state; then the host callback - the rest of solve_bem: finalize_vels(fs), right-hand side, solve, set_str; the reference's
+// BEM stays host code - returns the strengths and every device repacks its panel records with them. Needs the state's packed
+// stream in place (part_find_vels steps 1-2).
 bool body_solve(o3d_ctx* c, o3d_particles* p, const double* fs) {
+  (void)fs;   // the freestream enters in the host's finalize_vels
   const int nd = (int)c->dev.size();
   const int64_t np = p->b_np, nn = p->b_nn;
   Device& d = c->dev[0];
@@ -873,15 +874,13 @@ bool body_solve(o3d_ctx* c, o3d_particles* p, const double* fs) {
     a.nsplit = pan_nsplit(d, gx, a.ntiles);
     O3D_TRY(d, b.work.ensure((size_t)a.nsplit * 3 * np * sizeof(double)));
     a.partial = b.work.as<double>();
-    pts_pan_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
+    if (d.pan_queue) pts_pan_queue_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
+    else             pts_pan_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
     O3D_TRY(d, cudaGetLastError());
     pp_finish_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(3, a.nsplit, np, a.partial, pu, pu + np, pu + 2 * np, nullptr, np, -1.0f);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 2;
   }
-  pts_finalize_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(np, pu, pu + np, pu + 2 * np, nullptr, np, fs[0], fs[1], fs[2]);
-  O3D_TRY(d, cudaGetLastError());
-  d.launches += 1;
   p->h_pu.resize((size_t)3 * np);
   p->h_str.assign((size_t)4 * np, 0.0f);
   O3D_TRY(d, cudaMemcpyAsync(p->h_pu.data(), pu, (size_t)3 * np * 4, cudaMemcpyDeviceToHost, st));
@@ -1450,7 +1449,8 @@ int o3d_cuda_pts_on_pan(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
     a.nsplit = pan_nsplit(d, gx, a.ntiles);
     O3D_TRY(d, d.work.ensure((size_t)a.nsplit * 3 * n * sizeof(double)));
     a.partial = d.work.as<double>();
-    pts_pan_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
+    if (d.pan_queue) pts_pan_queue_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
+    else             pts_pan_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
     pp_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(3, a.nsplit, n, a.partial, dout, dout + n, dout + 2 * n, nullptr, n, -1.0f);
@@ -2035,9 +2035,10 @@ int o3d_cuda_particles_set_body_strengths(o3d_ctx* c, o3d_particles* p, const fl
   return collect(c);
 }
 
-// The BEM right-hand-side velocities of the CURRENT state without solving: zero, particles -> panels, finalize_vels(fs)
-int o3d_cuda_particles_body_vels(o3d_ctx* c, o3d_particles* p, const double* fs, float* pu, float* pv, float* pw) {
-  if (!c || !p || !fs || !pu || !pv || !pw || p->dev.size() != c->dev.size() || !p->has_body)
+// The raw panel-centre sums of the CURRENT state without solving: zero, particles -> panels (what solve_bem holds before finalize_vels)
+int o3d_cuda_particles_body_vels(o3d_ctx* c, o3d_particles* p, float* pu, float* pv, float* pw) {
+  const double fs[3] = {0.0, 0.0, 0.0};
+  if (!c || !p || !pu || !pv || !pw || p->dev.size() != c->dev.size() || !p->has_body)
     return fail(c, O3D_ERR_INVALID, "particles_body_vels: bad argument or no body attached");
   for (Device& d : c->dev) d.kernel_ms = d.h2d_ms = d.d2h_ms = 0, d.launches = 0;
   if (p->n == 0) return collect(c);

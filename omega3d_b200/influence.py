@@ -213,6 +213,12 @@ class Surfaces:
     def get_src_str(self): return self.ps[2]
     def zero_vels(self): self.pu[:] = 0
 
+    def finalize_vels(self, fs=(0.0, 0.0, 0.0)):
+        """src/Surfaces.h:877-887: panel-centre velocities = fs + pu / 4pi, formed in double."""
+        factor = 0.25 / math.pi
+        for d in range(3):
+            self.pu[d] = (float(fs[d]) + self.pu[d].astype(np.float64) * factor).astype(f32)
+
     def compute_bases(self):
         """src/Surfaces.h:766-815: x1 along node0->node1, x2 toward node2, normal x1 x x2, area = base*height/2.
         (float vectors; the two normalisations multiply by a double reciprocal, as the reference does)."""

@@ -207,6 +207,10 @@ class Reference:
             L.o3d_ref_reflect.restype = c_long
             L.o3d_ref_clear_inner.argtypes = [c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_float]
             L.o3d_ref_clear_inner.restype = c_long
+        if hasattr(L, "o3d_ref_advect_body"):
+            L.o3d_ref_advect_body.argtypes = ([c_int, c_double, c_void_p, c_float, c_int] + [c_void_p] * 4 + [c_int, c_void_p, c_int, c_void_p,
+                                               c_void_p, c_void_p])
+            L.o3d_ref_advect_body.restype = c_long
         if hasattr(L, "o3d_ref_totals"):
             L.o3d_ref_totals.argtypes = [c_int] + [c_void_p] * 4
             L.o3d_ref_status_lines.argtypes = [ctypes.c_char_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
@@ -245,6 +249,24 @@ class Reference:
         a, b = c_float(), c_float()
         self.lib.o3d_ref_stats(s.shape[1], _p(s), _p(elong), ctypes.byref(a), ctypes.byref(b))
         return a.value, b.value
+
+    DENSE_SOLVE_FN = ctypes.CFUNCTYPE(None, ctypes.POINTER(c_float), c_int, ctypes.POINTER(c_float))
+
+    def advect_body(self, order, dt, fs, ips, x, s, r, elong, nodes_i, idx, solve):
+        """One Convection::advect step (order 1 or 2) of a particle collection around one static body through the reference's own
+        routines; solve(rhs float32[3 np]) -> strengths float32[3 np] stands in for BEM::solve (Eigen). x, s, elong updated in
+        place. Returns (BEM solves made, ts (3,np))."""
+        fs = np.asarray(fs, np.float64)
+        np_ = idx.shape[0]
+
+        def _cb(rhs, n, out):
+            sol = np.ascontiguousarray(solve(np.ctypeslib.as_array(rhs, shape=(n,)).copy()), np.float32)
+            np.ctypeslib.as_array(out, shape=(n,))[:] = sol
+        cb = self.DENSE_SOLVE_FN(_cb)
+        ts = np.zeros((3, np_), np.float32)
+        k = self.lib.o3d_ref_advect_body(order, float(dt), _p(fs), float(ips), x.shape[1], _p(x), _p(s), _p(r), _p(elong),
+                                         nodes_i.shape[0], _p(nodes_i), np_, _p(idx), ctypes.cast(cb, c_void_p), _p(ts))
+        return int(k), ts
 
     def totals(self, x, s):
         """(ElementBase::get_total_circ, Points::get_total_impulse) through the reference's Points<float>: two float32[3]."""

@@ -24,6 +24,7 @@
 #include <chrono>
 #include "Reflect.h"
 #include "StatusFile.h"          // src/StatusFile.cpp is compiled where it lies (oracle/Makefile)
+#include "RHS.h"                 // vels_to_rhs_panels: the projection solve_bem applies (src/BEMHelper.h:103)
 #ifdef USE_CUDA
 #include "O3DCudaConvection.h"   // what the patched Convection.h includes (integration/omega3d_use_cuda.patch)
 #endif
@@ -41,6 +42,7 @@
 // that abort if anything ever reaches them.
 void Body::transform(const double) { std::abort(); }
 Trans Body::get_transform_mat() { std::abort(); }
+std::string Body::get_name() { std::abort(); }      // (Surfaces::to_string, only with a Body attached)
 
 namespace {
 
@@ -383,6 +385,68 @@ void o3d_ref_advect(int order, int nsteps, double dt, const double* fs, int n, f
   for (int k = 0; k < nsteps; ++k) { advect_once(vort, order, time, dt, f, env); time += dt; }
   store_state(vort, n, x, s, elong);
   store_results(vort, n, u, ug);
+}
+
+// One Convection::advect step of a particle collection around ONE static body, the way the patched Convection.h dispatches it
+// (integration/omega3d_use_cuda.patch): with the drop-in build and accel 4, o3d::cuda_advect_particles_body keeps the particles
+// on the device and calls `rest` once per derivative evaluation. `rest` here is solve_bem (src/BEMHelper.h:44-262) line for
+// line for one surface - zero_vels, points_affect_panels through the reference's own dispatch (whose gpu_cuda arm delivers the
+// device's sums), finalize_vels, vels_to_rhs_panels, set_str - EXCEPT the linear solve, for which BEM.h needs Eigen: the caller's
+// `solve(rhs, n, strengths)` stands in for BEM::solve. Without CUDA (accel 1) the same `rest` runs inside the reference's own
+// host sequencing: find_derivs, move, clear_inner_layer (src/Convection.h:232-425), orders 1 and 2.
+typedef void (*o3d_ref_dense_solve_fn)(const float* rhs, int n, float* strengths);
+long o3d_ref_advect_body(int order, double dt, const double* fs, float ips, int n, float* x, float* s, const float* r, float* elong,
+                         int nn, const float* nodes, int np, const uint32_t* idx, o3d_ref_dense_solve_fn solve, float* ts_out) {
+  Mute m(g_mute);
+  Points<float> vort = make_points(n, x, x + n, x + 2*(size_t)n, s, r, active, lagrangian);
+  load_state(vort, n, x, s, elong);
+  std::vector<float> bc(3 * (size_t)np, 0.0f);
+  Surfaces<float> surf = make_surfaces(nn, nodes, np, idx, bc.data(), reactive);
+  ExecEnv env(true, true, direct, (accel_t)g_accel);
+  const std::array<double,3> f = {fs[0], fs[1], fs[2]};
+  const float cut = 0.5/std::sqrt(2.0*M_PI);
+  long solves = 0;
+  auto rest_for = [&](Points<float>& state) {
+    surf.zero_vels();
+    points_affect_panels<float, double>(state, surf, ResultsType(velonly), env);
+    surf.finalize_vels(f);
+    std::vector<float> rhs = vels_to_rhs_panels<float>(surf);
+    Vector<float> sol(rhs.size());
+    solve(rhs.data(), (int)rhs.size(), sol.data());
+    surf.set_str(0, sol.size(), sol);
+    ++solves;
+  };
+  bool on_device = false;
+#ifdef USE_CUDA
+  if (g_device_convect && env.get_instrs() == gpu_cuda) {
+    auto rest = [&]() { rest_for(vort); };     // (vort's host arrays are stale here: the gpu_cuda arm never reads them)
+    (void) o3d::cuda_advect_particles_body(vort, surf, order, 0.0, dt, f, ips, rest);
+    on_device = true;
+  }
+#endif
+  if (!on_device) {
+    auto derivs = [&](Points<float>& state) {
+      rest_for(state);
+      state.zero_vels();
+      points_affect_points<float, double>(state, state, ResultsType(velandgrad), env);
+      panels_affect_points<float, double>(surf, state, ResultsType(velandgrad), env);
+      state.finalize_vels(f);
+    };
+    derivs(vort);
+    if (order == 1) {
+      vort.move(0.0, dt, 1.0, vort);
+    } else {
+      Points<float> interim = vort;
+      interim.move(0.0, (2.0/3.0)*dt, 1.0, interim);
+      (void) clear_inner_panp2<float>(1, surf, interim, cut, ips);
+      derivs(interim);
+      vort.move(0.0, dt, 0.25, vort, 0.75, interim);
+    }
+    (void) clear_inner_panp2<float>(1, surf, vort, cut, ips);
+  }
+  store_state(vort, n, x, s, elong);
+  if (ts_out) for (int d = 0; d < 3; ++d) for (int i = 0; i < np; ++i) ts_out[(size_t)d*np + i] = surf.get_str()[d][i];
+  return solves;
 }
 
 // ElementBase::get_max_str and Points::get_max_elong

@@ -61,7 +61,7 @@ def main():
         o = p.download()
         ref = np.concatenate([o["x"], o["s"], o["elong"][None, :], o["u"], o["ug"]], axis=0)
         print(json.dumps({"check": "ShardedConvection over NCCL == single-GPU resident step", "ranks": world, "particles": n,
-                          "order": order, "steps": steps, "bit_identical": bool(np.array_equal(got, ref)),
+                          "order": order, "steps": steps, "bit_identical": bool(np.array_equal(got, ref)), "values": int(got.size), "values_differing": int(np.sum(got != ref)),
                           "max_abs_diff": float(np.max(np.abs(got - ref))), "ms_per_step_max_over_ranks": float(ms.item()) / steps}), flush=True)
     dist.barrier()
     dist.destroy_process_group()

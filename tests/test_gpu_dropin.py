@@ -116,6 +116,40 @@ def test_convection_through_reference_points(dropin, order):
         assert rel_err(a, b) <= tol[name], name
 
 
+@pytest.mark.parametrize("order", [1, 2])
+def test_body_step_through_the_patched_dispatch(dropin, order):
+    """Convection::advect around one static body (configs[3]'s sphere) as the patched Convection.h dispatches it: with gpu_cuda
+    the particles stay resident (o3d::cuda_advect_particles_body) and the reference's solve_bem runs unchanged on the sums
+    the device delivers through its own points_affect_panels dispatch; with cpu_x86 the same driver runs the reference's host
+    sequencing (find_derivs / move / clear_inner_layer). Only BEM::solve (Eigen) is replaced, by one dense numpy solve on both
+    sides, with the reference's own coefficient matrix."""
+    import math
+    nodes, idx = W.icosphere(2, 0.5)
+    np_ = idx.shape[0]
+    rng = np.random.Generator(np.random.MT19937(17))
+    n = 6000
+    d = rng.standard_normal((3, n // 2)); d /= np.linalg.norm(d, axis=0)
+    x = np.concatenate([d * (0.5 + 0.12 * rng.random(n // 2) - 0.01),
+                        np.stack([0.4 + 1.5 * rng.random(n - n // 2), 0.7 * (rng.random(n - n // 2) - 0.5), 0.7 * (rng.random(n - n // 2) - 0.5)])], axis=1).astype(f32)
+    x = np.ascontiguousarray(x)
+    s = ((rng.random((3, n)) - 0.5) * (4.0 / n)).astype(f32)
+    ips = 0.0894
+    r = np.full(n, 1.5 * ips, f32)
+    A = np.asarray(dropin.pan_on_pan_coeff(nodes, idx, np.zeros((np_, 3), f32)), np.float64).reshape(3 * np_, 3 * np_).T
+    lu = np.linalg.inv(A)
+
+    def run():
+        px, ps, pe = x.copy(), s.copy(), np.ones(n, f32)
+        solves, ts = dropin.advect_body(order, 0.02, (1.0, 0.0, 0.0), ips, px, ps, r, pe, nodes, idx, lambda rhs: (lu @ rhs.astype(np.float64)).astype(f32))
+        return px, ps, pe, solves, ts
+    (cx, cs, ce, ck, cts), (gx, gs, ge, gk, gts) = both(dropin, run)
+    assert ck == order and gk == order
+    assert np.max(np.abs(cts)) > 0 and rel_err(gts, cts) <= 20 * VEL_TOL       # solved strengths (amplified by cond(A))
+    assert not np.array_equal(cx, x)
+    assert rel_err(gx, cx) <= 1e-6 and rel_err(gs, cs) <= 2e-5 and rel_err(ge, ce) <= 2e-5
+    assert np.min(np.linalg.norm(gx, axis=0)) > 0.49                           # the inner layer was cleared on the device
+
+
 def test_reflect_and_clear_inner_through_reference_functions(dropin):
     """The patched reflect_panp2 / clear_inner_panp2 (src/Reflect.h + integration hunk) take no ExecEnv: in a -DUSE_CUDA
     build the default back end decides, so calling the reference's own functions here runs the CUDA arm. The fixtures

@@ -106,22 +106,24 @@ def test_flow_over_sphere_step_vs_reference_templates(cuda_ctx, reference_lib, s
     seen = {}
 
     def solve(pu):
+        seen.setdefault("raw", pu.copy())
         surf.pu[:] = pu
+        surf.finalize_vels(FS)
         B.solve_bem_for(surf, bem)
-        seen.setdefault("pu", pu.copy()); seen.setdefault("sol", bem.getStrengths().copy())
+        seen.setdefault("pu", surf.pu.copy()); seen.setdefault("sol", bem.getStrengths().copy())
         return surf.ts, surf.ps[2]
 
     d = C.DeviceParticles(cuda_ctx).upload(x, s, r)
     d.set_body(surf, IPS, solve)
     # the right-hand-side velocities alone, then the step
-    pu_only = d.body_vels(FS)
+    pu_only = d.body_vels()
     d.advect(order, 0.0, DT, FS, 1)
     moved, solves = d.body_counters()
     out = d.download()
     d.close()
     assert solves == order
     # BEM right-hand side and solution of the first evaluation
-    assert np.array_equal(pu_only, seen["pu"])
+    assert np.array_equal(pu_only, seen["raw"])
     assert rel_err(seen["pu"], keep["pu"]) <= VEL_TOL
     assert rel_err(seen["sol"], keep["sol"]) <= 20 * VEL_TOL          # the solve amplifies the rhs difference (cond(A) below)
     # the state after the step
