@@ -59,9 +59,12 @@
 #ifndef O3D_PP_JOINT_FILE
 #define O3D_PP_JOINT_FILE "pp_body_velgrad_uni_joint.inc"
 #endif
-#ifndef O3D_PP_MINB
-#define O3D_PP_MINB 3     // __launch_bounds__ min CTAs per SM for pp2_kernel (caps registers at 168)
-#endif
+#ifndef O3D_PP_BLOCK
+#define O3D_PP_BLOCK 384  // threads per CTA. The kernels need 12 warps per SM (168 registers each: the whole register file) and run them as
+#endif                    // ONE persistent CTA per SM. 128 (three CTAs per SM; microbench/kbench only) loses 2-3 %: the warp schedulers serve
+                          // co-resident CTAs in strict age order - the oldest CTA of an SM finishes its static share at 39 % of the
+                          // kernel's duration, the second at 70 %, and the youngest then runs alone, one warp per scheduler
+                          // (profiles/r02_cta_end_times.txt). Inside one CTA the per-tile barrier keeps the twelve warps together.
 #ifndef O3D_PP_UNROLL_GRAD
 #define O3D_PP_UNROLL_GRAD 4   // source pairs per trip of the packed inner loop, velocity+gradient kernel
 #endif
@@ -73,16 +76,30 @@
 #define O3D_PP_TWOBUF 1   // 1 (product): the walk alternates two copies of the tile body, one per ring buffer, each with static
 #endif                    // shared-memory addresses; 0: one copy, the buffer's shared address handed to ptxas through a warp
                           // reduction once per tile (microbench/kbench only: DESIGN.md section 7)
+#ifndef O3D_PP_STAGGER
+#define O3D_PP_STAGGER 0  // > 0 (microbench/kbench only): the k-th CTA to arrive on an SM starts (k mod 3) * O3D_PP_STAGGER clocks late, so
+#endif                    // that the co-resident CTAs do not reach their tile boundaries together
 #ifndef O3D_PP_UNROLL_VEL
 #define O3D_PP_UNROLL_VEL 2    // ... velocity-only kernel
 #endif
 
 namespace o3d {
 
+#if O3D_PP_STAGGER
+__device__ unsigned pp_stagger_arrivals[1024];
+#endif
+#ifdef O3D_PP_ENDTIME
+__device__ unsigned long long pp_end_time[2048];   // microbench only: globaltimer at the end of every CTA
+__device__ unsigned pp_end_smid[2048];
+#endif
+
 // Product launch configuration of pp2_kernel (capi.cu launches these two instantiations; pp_tuned.cu compiles the same
-// two into the cubin that tools/sass_patch.py post-processes): 128-thread CTAs, 2 register-blocked targets per thread
-// with gradients, 4 without.
-constexpr int kPPBlock = 128;
+// two into the cubin that tools/sass_patch.py post-processes): one 384-thread CTA per SM, 2 register-blocked targets per
+// thread with gradients, 4 without.
+constexpr int kPPBlock = O3D_PP_BLOCK;
+constexpr int kPPWarpsPerSM = 12;                       // 65536 registers / (168 x 32)
+constexpr int kPPResident = kPPWarpsPerSM * 32 / kPPBlock;   // persistent CTAs per SM
+static_assert(kPPResident * kPPBlock == kPPWarpsPerSM * 32, "CTA size must divide 384 threads");
 constexpr int kPPTgrad = 2;
 constexpr int kPPTvel = 4;
 
@@ -168,17 +185,19 @@ __device__ __forceinline__ int pp_wrap(int t, int ntiles) { return t + 1 == ntil
 // microbench-only staging variants: every thread moves its 128-byte share of the tile (8 x 16 B, coalesced per 16-byte column)
 template <int BLOCK>
 __device__ __forceinline__ void pp_stage_copy(float4* dst, const float4* __restrict__ src) {
+  constexpr int NQ = (kTile * 2 + BLOCK - 1) / BLOCK;
 #if O3D_PP_STAGE == 1
 #pragma unroll
-  for (int q = 0; q < kTile * 2 / BLOCK; ++q)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + q * BLOCK + threadIdx.x)), "l"(src + q * BLOCK + threadIdx.x) : "memory");
+  for (int q = 0; q < NQ; ++q)
+    if (q * BLOCK + (int)threadIdx.x < kTile * 2)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst + q * BLOCK + threadIdx.x)), "l"(src + q * BLOCK + threadIdx.x) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 #else
-  float4 v[kTile * 2 / BLOCK];
+  float4 v[NQ];
 #pragma unroll
-  for (int q = 0; q < kTile * 2 / BLOCK; ++q) v[q] = __ldg(src + q * BLOCK + threadIdx.x);
+  for (int q = 0; q < NQ; ++q) if (q * BLOCK + (int)threadIdx.x < kTile * 2) v[q] = __ldg(src + q * BLOCK + threadIdx.x);
 #pragma unroll
-  for (int q = 0; q < kTile * 2 / BLOCK; ++q) dst[q * BLOCK + threadIdx.x] = v[q];
+  for (int q = 0; q < NQ; ++q) if (q * BLOCK + (int)threadIdx.x < kTile * 2) dst[q * BLOCK + threadIdx.x] = v[q];
 #endif
 }
 #endif
@@ -295,8 +314,8 @@ __device__ __forceinline__ void pp_store(const PPArgs& p, const int b, const boo
 // One CTA per range boundary j = blockIdx.x + 1 of the launch that just ran with P CTAs: if that boundary is the first one
 // inside its target block, add the block's pieces in unit order - the last segment of CTA j-1, then the first segments of
 // CTAs j, j+1, ... that start inside the block - and finish the block: out = float(double(out) + sign * sum).
-// blockDim.x = targets per block (BLOCK * T of the main kernel).
-__global__ void pp_fixup_kernel(const int nrows, const PPPlan plan, const int64_t nt, const double* __restrict__ partial,
+// per = targets per block (BLOCK * T of the main kernel).
+__global__ void pp_fixup_kernel(const int nrows, const int per, const PPPlan plan, const int64_t nt, const double* __restrict__ partial,
                                 float* tu, float* tv, float* tw, float* tug, const int64_t tug_stride, const float sign,
                                 double* acc64, const int64_t acc_stride) {
   const int j = blockIdx.x + 1;
@@ -305,20 +324,21 @@ __global__ void pp_fixup_kernel(const int nrows, const PPPlan plan, const int64_
   if (cut == start) return;                 // the boundary coincides with a block edge: nothing is shared here
   const int64_t prev = plan.begin(j - 1);
   if (prev > start) return;                 // an earlier boundary inside this block owns it
-  const int per = blockDim.x;
-  const int64_t i = b * per + threadIdx.x;
-  if (i >= nt) return;
   const size_t slot_elems = (size_t)nrows * per;
-  for (int k = 0; k < nrows; ++k) {
-    double acc = partial[((size_t)(j - 1) * kPPSlots + (prev == start ? 0 : 1)) * slot_elems + (size_t)k * per + threadIdx.x];
-    for (int c = j; c < plan.P && plan.begin(c) < end; ++c)
-      acc += partial[((size_t)c * kPPSlots) * slot_elems + (size_t)k * per + threadIdx.x];
-    if (acc64) {
-      acc64[(size_t)k * acc_stride + i] = acc;
-      continue;
+  for (int l = threadIdx.x; l < per; l += blockDim.x) {
+    const int64_t i = b * per + l;
+    if (i >= nt) return;
+    for (int k = 0; k < nrows; ++k) {
+      double acc = partial[((size_t)(j - 1) * kPPSlots + (prev == start ? 0 : 1)) * slot_elems + (size_t)k * per + l];
+      for (int c = j; c < plan.P && plan.begin(c) < end; ++c)
+        acc += partial[((size_t)c * kPPSlots) * slot_elems + (size_t)k * per + l];
+      if (acc64) {
+        acc64[(size_t)k * acc_stride + i] = acc;
+        continue;
+      }
+      float* o = k == 0 ? tu + i : k == 1 ? tv + i : k == 2 ? tw + i : tug + (size_t)(k - 3) * tug_stride + i;
+      *o = (float)((double)*o + (double)sign * acc);
     }
-    float* o = k == 0 ? tu + i : k == 1 ? tv + i : k == 2 ? tw + i : tug + (size_t)(k - 3) * tug_stride + i;
-    *o = (float)((double)*o + (double)sign * acc);
   }
 }
 
@@ -595,10 +615,23 @@ __device__ __forceinline__ void pp2_walk(const PPArgs& p, PPWalk& w, float4 (&ti
 }
 
 template <int T, bool GRAD, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) pp2_kernel(const PPArgs p) {
+__global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) pp2_kernel(const PPArgs p) {
   __shared__ alignas(128) float4 tile[2][kTile * 2];
   __shared__ alignas(8) uint64_t full[2];
 
+#if O3D_PP_STAGGER
+  {
+    __shared__ unsigned slot;
+    if (threadIdx.x == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      slot = atomicAdd(&pp_stagger_arrivals[smid], 1u) % 3u;
+    }
+    __syncthreads();
+    const long long until = clock64() + (long long)slot * O3D_PP_STAGGER;
+    while (clock64() < until) {}
+  }
+#endif
   PPWalk w = pp_ring_start<BLOCK>(p, tile, full);
 
   // radius scan (pp_scan_kernel): [0] ~min, [1] max of sr^2 bit patterns over sources that carry strength,
@@ -613,6 +646,14 @@ __global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) pp2_kernel(const PPArgs p)
   }
   if (uni) pp2_walk<T, GRAD, true, BLOCK>(p, w, tile, full, r2u);
   else     pp2_walk<T, GRAD, false, BLOCK>(p, w, tile, full, r2u);
+#ifdef O3D_PP_ENDTIME
+  if (threadIdx.x == 0 && blockIdx.x < 2048) {
+    unsigned long long t; unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    pp_end_time[blockIdx.x] = t; pp_end_smid[blockIdx.x] = smid;
+  }
+#endif
 }
 
 // Radius ranges for the uniform-radius fast path of pp2_kernel. range[0..1]: min/max of the sr^2 bit patterns

@@ -201,7 +201,7 @@ __device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
 }
 
 template <int CORE, int T, bool GRAD, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, O3D_PP_MINB) ppc_kernel(const PPArgs p) {
+__global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) ppc_kernel(const PPArgs p) {
   constexpr int NS = GRAD ? 12 : 3;
   constexpr int NA = PPAcc<GRAD>::N;
   __shared__ alignas(128) float4 tile[2][kTile * 2];

@@ -341,7 +341,7 @@ bool d2h(Device& d, cudaStream_t st, void* dst, const void* src, size_t bytes) {
 // only lengthens the operand-reuse chains of adjacent packed FP32 instructions: identical instructions and results,
 // about 2 % fewer FMA-pipe cycles. Loaded once per process; a load failure is an error of o3d_cuda_create, not a
 // silent switch to the linked copies (those stay reachable through o3d_cuda_set_tuned_kernels(ctx, 0) for A/B tests).
-static_assert(kPPTgrad == 2 && kPPTvel == 4 && kPPBlock == 128, "kernel names below spell these template arguments");
+static_assert(kPPTgrad == 2 && kPPTvel == 4 && kPPBlock == 384, "kernel names below spell these template arguments");
 struct TunedKernels {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t grad = nullptr, vel = nullptr;
@@ -355,19 +355,19 @@ const TunedKernels& tuned_kernels() {
     k.status = cudaLibraryLoadData(&k.lib, o3d_pp2_tuned_cubin, nullptr, nullptr, 0, nullptr, nullptr, 0);
     k.where = "cudaLibraryLoadData(pp2_tuned.cubin)";
     if (k.status == cudaSuccess) {
-      k.status = cudaLibraryGetKernel(&k.grad, k.lib, "_ZN3o3d10pp2_kernelILi2ELb1ELi128EEEvNS_6PPArgsE");
-      k.where = "cudaLibraryGetKernel(pp2_kernel<2,true,128>)";
+      k.status = cudaLibraryGetKernel(&k.grad, k.lib, "_ZN3o3d10pp2_kernelILi2ELb1ELi384EEEvNS_6PPArgsE");
+      k.where = "cudaLibraryGetKernel(pp2_kernel<2,true,384>)";
     }
     if (k.status == cudaSuccess) {
-      k.status = cudaLibraryGetKernel(&k.vel, k.lib, "_ZN3o3d10pp2_kernelILi4ELb0ELi128EEEvNS_6PPArgsE");
-      k.where = "cudaLibraryGetKernel(pp2_kernel<4,false,128>)";
+      k.status = cudaLibraryGetKernel(&k.vel, k.lib, "_ZN3o3d10pp2_kernelILi4ELb0ELi384EEEvNS_6PPArgsE");
+      k.where = "cudaLibraryGetKernel(pp2_kernel<4,false,384>)";
     }
     for (int core = O3D_CORE_RM; core <= O3D_CORE_V2 && k.status == cudaSuccess; ++core)
       for (int g = 0; g < 2 && k.status == cudaSuccess; ++g) {
         char name[96];
-        snprintf(name, sizeof name, "_ZN3o3d10ppc_kernelILi%dELi%dELb%dELi128EEEvNS_6PPArgsE", core, g ? kPPTgrad : kPPTvel, g);
+        snprintf(name, sizeof name, "_ZN3o3d10ppc_kernelILi%dELi%dELb%dELi384EEEvNS_6PPArgsE", core, g ? kPPTgrad : kPPTvel, g);
         k.status = cudaLibraryGetKernel(&k.core[core][g], k.lib, name);
-        k.where = "cudaLibraryGetKernel(ppc_kernel<core,T,grad,128>)";
+        k.where = "cudaLibraryGetKernel(ppc_kernel<core,T,grad,384>)";
       }
     if (k.status != cudaSuccess) cudaGetLastError();
     return k;
@@ -376,18 +376,17 @@ const TunedKernels& tuned_kernels() {
 }
 
 // ---- launch shape for particles -> points ---------------------------------------------------------
-// Product configuration: packed FFMA2 kernels, 128-thread CTAs, 2 targets per thread with gradients, 4 without, as
-// PERSISTENT CTAs over a static stream-K partition of the (target block, source tile) units (csrc/biot_pp.cuh: PPPlan):
-// one CTA per resident slot of the GPU, every CTA the same number of tiles (+-1) whatever the target count.
+// Product configuration: packed FFMA2 kernels, one PERSISTENT 384-thread CTA per SM, 2 targets per thread with gradients,
+// 4 without, over a static stream-K partition of the (target block, source tile) units (csrc/biot_pp.cuh: PPPlan):
+// every CTA the same number of tiles (+-1) whatever the target count.
 struct PPShape {
-  int nblocks;        // target blocks of 128 * T targets
+  int nblocks;        // target blocks of 384 * T targets
   int grid;           // CTAs = min(units, resident slots)
   int64_t units;      // nblocks * ntiles
   int split_blocks;   // target blocks shared by more than one CTA (finished by pp_fixup_kernel)
 };
-// CTAs resident per SM (register-limited: <= 168 registers x 128 threads, lib/ptxas.log) for every product kernel
-constexpr int kPPResident = 3;
-// workspace of one launch: 2 slots per CTA x (12 rows x 256 targets | 3 rows x 512 targets) FP64 - a constant of the device
+// (kPPResident = 1 CTA of 384 threads per SM, register-limited: <= 168 registers per thread, lib/ptxas.log; csrc/biot_pp.cuh)
+// workspace of one launch: 2 slots per CTA x (12 rows x 768 targets | 3 rows x 1536 targets) FP64 - a constant of the device
 constexpr size_t pp_workspace_bytes(int sm_count) {
   return (size_t)sm_count * kPPResident * kPPSlots * 12 * (kPPBlock * kPPTgrad) * sizeof(double);
 }
@@ -484,7 +483,7 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   if (s.grid > 1) {
     // the target blocks cut by a CTA-range boundary: add their pieces in unit order (one CTA per boundary)
     const PPPlan plan{s.units, s.grid, (int)ntiles};
-    pp_fixup_kernel<<<(unsigned)(s.grid - 1), kPPBlock * (grad ? kPPTgrad : kPPTvel), 0, st>>>(grad ? 12 : 3, plan, nt, a.partial, tu, tv, tw,
+    pp_fixup_kernel<<<(unsigned)(s.grid - 1), 256, 0, st>>>(grad ? 12 : 3, kPPBlock * (grad ? kPPTgrad : kPPTvel), plan, nt, a.partial, tu, tv, tw,
                                                                                               tug, tug_stride, 1.0f, a.acc64, a.acc_stride);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;

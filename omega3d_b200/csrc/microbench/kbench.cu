@@ -6,12 +6,15 @@
 #include <cstdlib>
 #include <random>
 #include <vector>
+#include <algorithm>
 #include <string>
 #include <cstring>
 #include <cuda.h>
 #include "pp_scalar.cuh"   // the scalar-FFMA kernel with its gridDim.y split (not a product kernel) + ../biot_pp.cuh
 
 using namespace o3d;
+#define O3D_STR2(x) #x
+#define O3D_STR(x) O3D_STR2(x)
 #define CHECK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 static void host_ref(int ns, const float* sx, const float* sy, const float* sz, const float* sr, const float* wx,
@@ -124,7 +127,7 @@ int main(int argc, char** argv) {
     a.radius_range = no_uniform ? nullptr : range;
     const int64_t units = (int64_t)a.nblocks * a.ntiles;
     const int grid = (int)std::min<int64_t>(units, (int64_t)prop.multiProcessorCount * per_sm);
-    if (grid > resident || BLOCK * T * (grad ? 12 : 3) > 12 * 256) { printf("%s: workspace too small for this shape\n", name); return; }
+    if ((int64_t)grid * BLOCK * T * (grad ? 12 : 3) > (int64_t)resident * 12 * 256) { printf("%s: workspace too small for this shape\n", name); return; }
     const PPPlan plan{units, grid, a.ntiles};
     float best = 1e30f;
     for (int r = 0; r < reps + 1; ++r) {
@@ -136,18 +139,29 @@ int main(int argc, char** argv) {
       } else {
         kern<<<grid, BLOCK>>>(a);
       }
-      if (grid > 1) pp_fixup_kernel<<<grid - 1, BLOCK * T>>>(grad ? 12 : 3, plan, n, ppwork, a.tu, a.tv, a.tw, a.tug, n, 1.0f, nullptr, 0);
+      if (grid > 1) pp_fixup_kernel<<<grid - 1, 256>>>(grad ? 12 : 3, BLOCK * T, plan, n, ppwork, a.tu, a.tv, a.tw, a.tug, n, 1.0f, nullptr, 0);
       cudaEventRecord(e1);
       CHECK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       if (r > 0 && ms < best) best = ms;
     }
     report(name, T, BLOCK, grad, 1, grid, best, true);
+#ifdef O3D_PP_ENDTIME
+    if (!fn) {   // when did each CTA of the last launch end, and on which SM: do co-resident CTAs progress equally?
+      std::vector<unsigned long long> te(2048); std::vector<unsigned> sm(2048);
+      CHECK(cudaMemcpyFromSymbol(te.data(), pp_end_time, 2048 * 8)); CHECK(cudaMemcpyFromSymbol(sm.data(), pp_end_smid, 2048 * 4));
+      unsigned long long tmax = 0; for (int c = 0; c < grid; ++c) tmax = std::max(tmax, te[c]);
+      std::vector<double> lag(grid); for (int c = 0; c < grid; ++c) lag[c] = (double)(tmax - te[c]) * 1e-6;   // ms before the last CTA
+      std::vector<double> s2 = lag; std::sort(s2.begin(), s2.end());
+      printf("   CTA end times, ms before the last one: min %.3f  p25 %.3f  median %.3f  p75 %.3f  max %.3f\n", s2[0], s2[grid / 4], s2[grid / 2], s2[3 * grid / 4], s2[grid - 1]);
+      printf("   SM 0..3 CTAs (lag ms):");
+      for (unsigned q = 0; q < 4; ++q) { printf(" ["); for (int c = 0; c < grid; ++c) if (sm[c] == q) printf(" %.2f", lag[c]); printf(" ]"); }
+      printf("\n");
+    }
+#endif
   };
 #define RUN_S(T, B, G, SPLIT) run_scalar("scalar" #G, pp_kernel<T, G, B>, T, B, G, SPLIT)
 #define RUN_P(T, B, G, PER_SM) run_packed("packed" #G " stage" O3D_STR(O3D_PP_STAGE), pp2_kernel<T, G, B>, nullptr, T, B, G, PER_SM)
-#define O3D_STR2(x) #x
-#define O3D_STR(x) O3D_STR2(x)
   // KBENCH_CUBIN=a.cubin[:b.cubin...]: time the two product instantiations of pp2_kernel loaded from cubin files
   // (tools/sass_patch.py output) through the driver API, next to the copies linked into this binary.
   if (const char* list = getenv("KBENCH_CUBIN")) {
@@ -161,19 +175,23 @@ int main(int argc, char** argv) {
       if (path.empty()) continue;
       CUmodule mod; CUfunction fn;
       if (cuModuleLoad(&mod, path.c_str()) != CUDA_SUCCESS) { printf("cannot load %s\n", path.c_str()); continue; }
-      struct { const char* sym; int T; bool grad; } kinds[] = {{"_ZN3o3d10pp2_kernelILi2ELb1ELi128EEEvNS_6PPArgsE", 2, true},
-                                                             {"_ZN3o3d10pp2_kernelILi4ELb0ELi128EEEvNS_6PPArgsE", 4, false}};
+      struct { const char* sym; int T; bool grad; } kinds[] = {{"_ZN3o3d10pp2_kernelILi2ELb1ELi" O3D_STR(O3D_PP_BLOCK) "EEEvNS_6PPArgsE", 2, true},
+                                                             {"_ZN3o3d10pp2_kernelILi4ELb0ELi" O3D_STR(O3D_PP_BLOCK) "EEEvNS_6PPArgsE", 4, false}};
       for (auto& kd : kinds) {
         if (cuModuleGetFunction(&fn, mod, kd.sym) != CUDA_SUCCESS) continue;
         const std::string label = "cubin " + path + (kd.grad ? " velgrad" : " vel");
-        run_packed(label.c_str(), pp2_kernel<2, true, 128>, fn, kd.T, 128, kd.grad, 3);
+        run_packed(label.c_str(), pp2_kernel<2, true, kPPBlock>, fn, kd.T, kPPBlock, kd.grad, kPPResident);
       }
     }
     if (getenv("KBENCH_CUBIN_ONLY")) return 0;
   }
   if (getenv("KBENCH_PRODUCT_ONLY")) {     // the two product shapes only (staging-variant builds: make kbench_stage)
-    RUN_P(2, 128, true, 3);
+    RUN_P(2, kPPBlock, true, kPPResident);
+    RUN_P(4, kPPBlock, false, kPPResident);
+#ifdef O3D_PP_ENDTIME
+    RUN_P(2, 128, true, 3);     // three CTAs per SM: the oldest finishes first (strict age priority between co-resident CTAs)
     RUN_P(4, 128, false, 3);
+#endif
     return 0;
   }
   RUN_S(1, 256, true, 1);
@@ -184,11 +202,11 @@ int main(int argc, char** argv) {
   RUN_S(3, 128, true, 1);
   RUN_S(3, 256, true, 1);
   RUN_S(2, 256, true, 4);
-  RUN_P(1, 256, true, 2);
-  RUN_P(1, 128, true, 4);
   RUN_P(2, 128, true, 3);
+  RUN_P(2, 384, true, 1);
   RUN_S(4, 256, false, 1);
   RUN_S(8, 128, false, 1);
   RUN_P(4, 128, false, 3);
+  RUN_P(4, 384, false, 1);
   return 0;
 }

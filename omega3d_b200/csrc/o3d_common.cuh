@@ -14,7 +14,10 @@ namespace o3d {
 //     rec[2*j+1] = { wx, wy, wz, 0 }       src/CoreFunc.h:267)
 // The stream is padded to a whole number of tiles with zero-strength records (they add exactly 0).
 // ---------------------------------------------------------------------------------------------
-constexpr int kTile = 512;                       // sources per shared-memory tile (16 KB)
+#ifndef O3D_TILE
+#define O3D_TILE 512
+#endif
+constexpr int kTile = O3D_TILE;                  // sources per shared-memory tile (512: 16 KB)
 constexpr int kTileBytes = kTile * 32;
 
 __host__ __device__ inline int64_t padded_sources(int64_t ns) { return ((ns + kTile - 1) / kTile) * kTile; }

@@ -158,13 +158,13 @@ def test_launch_plan_fills_the_gpu_at_the_benchmark_sizes():
             nt = n // gpus
             grid, sp, bal, ws = c_int64(), c_int(), c_double(), c_int64()
             assert lib.o3d_cuda_plan_pts_on_pts(148, n, nt, 1, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
-            assert grid.value == 444 and 0 <= sp.value <= 443
+            assert grid.value == 148 and 0 <= sp.value <= 147   # one persistent 384-thread CTA per SM
             assert bal.value >= (0.9995 if n >= 1 << 21 else 0.993), (n, gpus, bal.value)   # one tile of granularity
-            assert ws.value == 444 * 2 * 12 * 256 * 8
+            assert ws.value == 148 * 2 * 12 * 768 * 8
     # tiny target counts: the source tiles of the one target block are dealt out over the CTAs
     grid, sp, bal, ws = c_int64(), c_int(), c_double(), c_int64()
     assert lib.o3d_cuda_plan_pts_on_pts(148, 100000, 320, 0, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
-    assert grid.value == 196 and sp.value == 1            # 196 tiles of 512 sources, one block of 512 targets
+    assert grid.value == 148 and sp.value == 1            # 196 tiles of 512 sources, one block of 1536 targets, 148 CTAs
     assert lib.o3d_cuda_plan_pts_on_pts(148, 700, 5, 1, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
     assert grid.value == 2 and sp.value == 1              # 700 sources are two 512-record tiles
     assert lib.o3d_cuda_plan_pts_on_pts(148, 100, 100, 1, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
@@ -180,7 +180,8 @@ def test_stream_k_bookkeeping_replayed_on_the_host():
     lib = _lib.load()
     rng = np.random.Generator(np.random.MT19937(5))
     shapes = [(1, 1), (512, 256), (513, 257), (700, 5), (100000, 320), (1 << 20, 1 << 20), (1 << 20, 1 << 17), (1 << 22, 1 << 22),
-              (1 << 24, 1 << 21), (444 * 512, 256), (443 * 512, 512), (445 * 512, 256 * 3), (512 * 37, 256 * 444), (512 * 37, 256 * 12)]
+              (1 << 24, 1 << 21), (444 * 512, 256), (443 * 512, 512), (445 * 512, 256 * 3), (512 * 37, 256 * 444), (512 * 37, 256 * 12),
+              (148 * 512, 768), (147 * 512, 1536), (149 * 512, 768 * 3), (512 * 37, 768 * 148), (512 * 37, 768 * 5)]
     shapes += [(int(rng.integers(1, 300000)), int(rng.integers(1, 300000))) for _ in range(60)]
     for ns, nt in shapes:
         for grad in (0, 1):

@@ -14,9 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "omega3d_b200", "lib")
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-KERNELS = ["_ZN3o3d10pp2_kernelILi2ELb1ELi128EEEvNS_6PPArgsE", "_ZN3o3d10pp2_kernelILi4ELb0ELi128EEEvNS_6PPArgsE"]
+KERNELS = ["_ZN3o3d10pp2_kernelILi2ELb1ELi384EEEvNS_6PPArgsE", "_ZN3o3d10pp2_kernelILi4ELb0ELi384EEEvNS_6PPArgsE"]
 # ... and the alternate-core kernels (csrc/biot_pp_cores.cuh): ppc_kernel<core 1..3, T, grad, 128>
-KERNELS += [f"_ZN3o3d10ppc_kernelILi{c}ELi{t}ELb{g}ELi128EEEvNS_6PPArgsE" for c in (1, 2, 3) for t, g in ((2, 1), (4, 0))]
+KERNELS += [f"_ZN3o3d10ppc_kernelILi{c}ELi{t}ELb{g}ELi384EEEvNS_6PPArgsE" for c in (1, 2, 3) for t, g in ((2, 1), (4, 0))]
 
 
 @pytest.fixture(scope="module")
@@ -87,7 +87,7 @@ def test_model_counts_fewer_third_reads_after_the_patch(cubins):
     _, _, base, tuned = cubins
     res = []
     for path in (base, tuned):
-        ins = M.kernel_sass(path, "pp2_kernelILi2ELb1ELi128")
+        ins = M.kernel_sass(path, "pp2_kernelILi2ELb1ELi384")
         j, i = M.hot_loop(ins)
         res.append(M.model([t for _, t in ins[j:i + 1]]))
     assert res[0][0] == res[1][0]            # same packed instructions per trip
