@@ -76,6 +76,11 @@
 #define O3D_PP_TWOBUF 1   // 1 (product): the walk alternates two copies of the tile body, one per ring buffer, each with static
 #endif                    // shared-memory addresses; 0: one copy, the buffer's shared address handed to ptxas through a warp
                           // reduction once per tile (microbench/kbench only: DESIGN.md section 7)
+#ifndef O3D_PP_NOBAR
+#define O3D_PP_NOBAR 1    // no CTA-wide barrier per tile: every warp counts itself out of a ring buffer (shared-memory counter) and the last
+#endif                    // one out refills it, so the warps of a CTA may drift one tile apart. 0: barrier in every kernel; 1 (product): the
+                          // velocity+gradient pp2_kernel goes without (-0.8 %; the velocity-only kernel measures 1.1 % SLOWER without its
+                          // barrier: profiles/r02_kbench_nobar.txt); 2: every kernel without (microbench/kbench only)
 #ifndef O3D_PP_STAGGER
 #define O3D_PP_STAGGER 0  // > 0 (microbench/kbench only): the k-th CTA to arrive on an SM starts (k mod 3) * O3D_PP_STAGGER clocks late, so
 #endif                    // that the co-resident CTAs do not reach their tile boundaries together
@@ -91,6 +96,7 @@ __device__ unsigned pp_stagger_arrivals[1024];
 #ifdef O3D_PP_ENDTIME
 __device__ unsigned long long pp_end_time[2048];   // microbench only: globaltimer at the end of every CTA
 __device__ unsigned pp_end_smid[2048];
+__device__ long long pp_tile_clock[12][64];        // ... and clock64 of every warp of CTA 0 when it has finished the arithmetic of its k-th tile
 #endif
 
 // Product launch configuration of pp2_kernel (capi.cu launches these two instantiations; pp_tuned.cu compiles the same
@@ -135,24 +141,50 @@ __device__ __forceinline__ void pp_promote(float (&acc)[PPAcc<GRAD>::N], double 
 }
 
 
-// ---- the static stream-K partition -----------------------------------------------------------------------------
-// Units are (target block b, source tile k), numbered u = b * ntiles + k. CTA c owns [begin(c), begin(c+1)).
-// Host and device use the same arithmetic (capi.cu: launch shape, o3d_cuda_plan_pts_on_pts; the kernels; pp_fixup_kernel).
+// ---- the static partition: whole blocks first, a stream-K tail -------------------------------------------------------
+// Units are (target block b, source tile k). With P persistent CTAs and nblocks target blocks:
+//   phase A  CTA c owns the `full` = nblocks / P WHOLE blocks [c full, (c+1) full): every CTA starts every block at tile 0 at
+//            (nearly) the same time, so the P CTAs walk the source stream together and a tile fetched from HBM by one of them
+//            is an L2 hit for the others - one pass over the sources per sweep of P blocks, whatever their size (with a pure
+//            stream-K partition the CTAs sit at P different places of the stream, and a source set larger than L2 is re-read
+//            from HBM by each of them: 368 GB per launch measured at 4 M particles, profiles/r02_pp2_dram_traffic.txt);
+//   phase B  the remaining nblocks - P full < P blocks are dealt out stream-K: their Wt = (nblocks - P full) ntiles units in
+//            block-major order, CTA c < Pt owns [Wt c / Pt, Wt (c+1) / Pt), Pt = min(P, Wt). Every CTA streams the same number
+//            of tiles (+-1) whatever the target count - no last-wave quantisation - and the TMA ring runs straight through
+//            block and phase boundaries.
+// Host and device use the same arithmetic (capi.cu: launch shape, o3d_cuda_plan_pts_on_pts, o3d_cuda_plan_check; the kernels;
+// pp_fixup_kernel).
 struct PPPlan {
-  int64_t W;      // units = nblocks * ntiles
-  int P;          // CTAs (<= W: no CTA is empty)
-  int ntiles;
-  __host__ __device__ int64_t begin(int c) const { return W * (int64_t)c / P; }
+  int nblocks, ntiles;
+  int P;          // CTAs
+  int full;       // whole blocks per CTA (phase A)
+  int Pt;         // CTAs that take part in the tail (phase B); 0: no tail
+  int64_t Wt;     // tail units
+  __host__ __device__ int tail_block0() const { return P * full; }
+  __host__ __device__ int64_t begin(int c) const { return Pt ? Wt * (int64_t)(c < Pt ? c : Pt) / Pt : 0; }   // first tail unit of CTA c
+  __host__ __device__ int64_t tiles_of(int c) const { return (int64_t)full * ntiles + begin(c + 1) - begin(c); }
 };
-// A CTA's range is cut into segments at target-block boundaries. Only its FIRST and its LAST segment can cover a block
-// partially; a partial first segment leaves its sums in slot 0 of the CTA's workspace pair, a partial last segment that is
-// not also the first in slot 1.
+// slots = resident CTA slots of the device (SMs x kPPResident)
+__host__ __device__ inline PPPlan pp_make_plan(int slots, int nblocks, int ntiles) {
+  PPPlan q;
+  q.nblocks = nblocks; q.ntiles = ntiles;
+  const int64_t W = (int64_t)nblocks * ntiles;
+  q.P = (int)(W < slots ? W : slots);
+  q.full = nblocks / q.P;
+  q.Wt = (int64_t)(nblocks - q.P * q.full) * ntiles;
+  q.Pt = (int)(q.Wt < q.P ? q.Wt : q.P);
+  return q;
+}
+// A CTA's tail range is cut into segments at target-block boundaries. Only its FIRST and its LAST tail segment can cover a
+// block partially; a partial first segment leaves its sums in slot 0 of the CTA's workspace pair, a partial last segment that
+// is not also the first in slot 1.
 constexpr int kPPSlots = 2;
 
 struct PPArgs {
   const float4* src;      // packed source stream, 2 float4 per source, padded to whole tiles
   int ntiles;             // tiles in the whole stream
   int nblocks;            // target blocks of BLOCK * T targets
+  int slots;              // resident CTA slots the launch was planned for (gridDim.x = pp_make_plan(slots, ..).P)
   int64_t nt;             // targets
   const float* tx; const float* ty; const float* tz;
   const float* tr;        // nullptr => singular targets (tr = 0)
@@ -173,9 +205,14 @@ struct PPArgs {
 // only, so ptxas keeps it in UNIFORM registers: the inner loops address shared memory as [UR + imm] and branch on uniform
 // predicates exactly as a one-block-per-CTA kernel would (values re-read from shared memory would count as divergent and move
 // the loop counters and LDS addresses into the vector register file, whose read bandwidth is what bounds the hot loop).
+// mbarriers of the two ring buffers, and (O3D_PP_NOBAR) how many of the CTA's warps have left each
+struct PPSync { uint64_t full[2]; unsigned released[2]; };
+
 struct PPWalk {
-  int nk;           // tiles in the CTA's share
-  int b0, kt0;      // target block and source tile of its first unit
+  int nk;           // tiles in the CTA's share: nA + its tail units
+  int nA;           // ... of which phase A (whole blocks)
+  int bA0;          // first whole block
+  int bB0, ktB0;    // target block and source tile of its first tail unit
   int kring;        // tiles consumed so far; tile kring lives in ring buffer kring & 1
   int tnext;        // source tile the next refill fetches (wraps from the last tile of a block to tile 0 of the next)
 };
@@ -213,33 +250,40 @@ __device__ __forceinline__ void pp_ring_fetch(const PPArgs& p, PPWalk& w, float4
 #else
   pp_stage_copy<BLOCK>(buf, p.src + (size_t)w.tnext * (kTile * 2));
 #endif
-  w.tnext = pp_wrap(w.tnext, p.ntiles);
+}
+// the source tile of ring position `pos` has been requested: which one does position pos + 1 hold? (the walk jumps from the last
+// tile of phase A to the CTA's first tail unit)
+__device__ __forceinline__ void pp_ring_advance(const PPArgs& p, PPWalk& w, const int pos) {
+  w.tnext = pos + 1 == w.nA ? w.ktB0 : pp_wrap(w.tnext, p.ntiles);
 }
 
 template <int BLOCK>
-__device__ __forceinline__ PPWalk pp_ring_start(const PPArgs& p, float4 (&tile)[2][kTile * 2], uint64_t (&full)[2]) {
-  const PPPlan plan{(int64_t)p.nblocks * p.ntiles, (int)gridDim.x, p.ntiles};
+__device__ __forceinline__ PPWalk pp_ring_start(const PPArgs& p, float4 (&tile)[2][kTile * 2], PPSync& sy) {
+  const PPPlan plan = pp_make_plan(p.slots, p.nblocks, p.ntiles);
   const int64_t u0 = plan.begin(blockIdx.x), u1 = plan.begin(blockIdx.x + 1);
   // (the 64-bit divisions run as a subroutine on the vector datapath, after which ptxas no longer knows the quotients to be
   // warp-uniform; a warp reduction - REDUX writes a uniform register - hands them back as provably uniform values)
-  const int b0 = (int)(u0 / p.ntiles);
+  const int bt = (int)(u0 / p.ntiles);
   PPWalk w;
-  w.nk = __reduce_max_sync(0xffffffffu, (int)(u1 - u0));
-  w.b0 = __reduce_max_sync(0xffffffffu, b0);
-  w.kt0 = __reduce_max_sync(0xffffffffu, (int)(u0 - (int64_t)b0 * p.ntiles));
+  w.nA = __reduce_max_sync(0xffffffffu, plan.full * p.ntiles);
+  w.nk = __reduce_max_sync(0xffffffffu, plan.full * p.ntiles + (int)(u1 - u0));
+  w.bA0 = __reduce_max_sync(0xffffffffu, (int)blockIdx.x * plan.full);
+  w.bB0 = __reduce_max_sync(0xffffffffu, plan.tail_block0() + bt);
+  w.ktB0 = __reduce_max_sync(0xffffffffu, (int)(u0 - (int64_t)bt * p.ntiles));
   w.kring = 0;
-  w.tnext = w.kt0;
+  w.tnext = w.nA > 0 ? 0 : w.ktB0;
 #if O3D_PP_STAGE == 0
   if (threadIdx.x == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    mbar_init(&sy.full[0], 1);
+    mbar_init(&sy.full[1], 1);
     mbar_fence_init();
+    sy.released[0] = sy.released[1] = 0u;
   }
   __syncthreads();
 #endif
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    if (s < w.nk) pp_ring_fetch<BLOCK>(p, w, tile[s], &full[s]);
+    if (s < w.nk) { pp_ring_fetch<BLOCK>(p, w, tile[s], &sy.full[s]); pp_ring_advance(p, w, s); }
 #if O3D_PP_STAGE == 1
     else asm volatile("cp.async.commit_group;" ::: "memory");   // keep the group count in step with the tile count
 #endif
@@ -247,9 +291,9 @@ __device__ __forceinline__ PPWalk pp_ring_start(const PPArgs& p, float4 (&tile)[
   return w;
 }
 // tile w.kring of the CTA's share has landed in its ring buffer
-__device__ __forceinline__ void pp_ring_wait(uint64_t (&full)[2], const int kring) {
+__device__ __forceinline__ void pp_ring_wait(PPSync& sy, const int kring) {
 #if O3D_PP_STAGE == 0
-  mbar_wait(&full[kring & 1], (kring >> 1) & 1);
+  mbar_wait(&sy.full[kring & 1], (kring >> 1) & 1);
 #else
 #if O3D_PP_STAGE == 1
   asm volatile("cp.async.wait_group 1;" ::: "memory");   // all but the newest group
@@ -258,10 +302,31 @@ __device__ __forceinline__ void pp_ring_wait(uint64_t (&full)[2], const int krin
 #endif
 }
 // every warp is done with the buffer of tile w.kring: refill it with the tile two ahead, step to the next tile
-template <int BLOCK>
-__device__ __forceinline__ void pp_ring_refill(const PPArgs& p, PPWalk& w, float4* buf, uint64_t* bar) {
+template <int BLOCK, bool NOBAR>
+__device__ __forceinline__ void pp_ring_refill(const PPArgs& p, PPWalk& w, float4* buf, uint64_t* bar, unsigned* released) {
+#if O3D_PP_STAGE == 0
+  if constexpr (NOBAR) {
+  // each warp counts itself out of the buffer; the last of the CTA's warps to leave it issues the refill
+  __syncwarp();
+  const bool more = w.kring + 2 < w.nk;
+  if ((threadIdx.x & 31) == 0) {
+    if (atomicAdd(released, 1u) == BLOCK / 32 - 1) {
+      *released = 0u;
+      if (more) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, kTileBytes);
+        bulk_g2s(buf, p.src + (size_t)w.tnext * (kTile * 2), kTileBytes, bar);
+      }
+    }
+  }
+  if (more) pp_ring_advance(p, w, w.kring + 2);
+  ++w.kring;
+  return;
+  }
+#endif
+  (void)released;
   __syncthreads();
-  if (w.kring + 2 < w.nk) pp_ring_fetch<BLOCK>(p, w, buf, bar);
+  if (w.kring + 2 < w.nk) { pp_ring_fetch<BLOCK>(p, w, buf, bar); pp_ring_advance(p, w, w.kring + 2); }
 #if O3D_PP_STAGE == 1
   else asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
@@ -311,8 +376,34 @@ __device__ __forceinline__ void pp_store(const PPArgs& p, const int b, const boo
   }
 }
 
-// One CTA per range boundary j = blockIdx.x + 1 of the launch that just ran with P CTAs: if that boundary is the first one
-// inside its target block, add the block's pieces in unit order - the last segment of CTA j-1, then the first segments of
+// Per-target-block state of a persistent CTA's walk (pp2_walk / ppc_kernel)
+struct PPBlock {
+  int b, kt;        // target block and source tile of the current unit
+  bool seg_first;   // the current segment is the first of the CTA's tail (the only one of its FIRST segments that may be partial)
+  bool fresh;       // the current tile starts a segment: (re)load the targets, clear the FP64 sums
+};
+
+// The tile just consumed may end a segment: store it, move on to the next block - or from the last whole block to the CTA's tail.
+template <int T, bool GRAD, int BLOCK>
+__device__ __forceinline__ void pp_segment_end(const PPArgs& p, const PPWalk& w, PPBlock& s, const double (&sum)[T][GRAD ? 12 : 3]) {
+  ++s.kt;
+  s.fresh = s.kt == p.ntiles || w.kring == w.nk;
+  if (s.fresh) {
+    // whole block <=> the segment ran from tile 0 to the last tile: kt == ntiles and (not a first tail segment, or one that began at tile 0)
+    const bool whole = s.kt == p.ntiles && (!s.seg_first || w.ktB0 == 0);
+    pp_store<T, GRAD, BLOCK>(p, s.b, whole, s.seg_first ? 0 : 1, sum);
+    s.seg_first = false;
+    s.kt = 0;
+    ++s.b;
+    if (w.kring == w.nA) { s.b = w.bB0; s.kt = w.ktB0; s.seg_first = true; }   // phase A is done (nA > 0 here: kring >= 1)
+  }
+}
+__device__ __forceinline__ PPBlock pp_first_block(const PPWalk& w) {
+  return w.nA > 0 ? PPBlock{w.bA0, 0, false, true} : PPBlock{w.bB0, w.ktB0, true, true};
+}
+
+// One CTA per TAIL-range boundary j = blockIdx.x + 1 (1 .. Pt-1) of the launch that just ran: if that boundary is the first one
+// inside its target block, add the block's pieces in unit order - the last segment of CTA j-1, then the first tail segments of
 // CTAs j, j+1, ... that start inside the block - and finish the block: out = float(double(out) + sign * sum).
 // per = targets per block (BLOCK * T of the main kernel).
 __global__ void pp_fixup_kernel(const int nrows, const int per, const PPPlan plan, const int64_t nt, const double* __restrict__ partial,
@@ -320,17 +411,18 @@ __global__ void pp_fixup_kernel(const int nrows, const int per, const PPPlan pla
                                 double* acc64, const int64_t acc_stride) {
   const int j = blockIdx.x + 1;
   const int64_t cut = plan.begin(j);
-  const int64_t b = cut / plan.ntiles, start = b * plan.ntiles, end = start + plan.ntiles;
+  const int64_t bt = cut / plan.ntiles, start = bt * plan.ntiles, end = start + plan.ntiles;   // tail block, its unit range
   if (cut == start) return;                 // the boundary coincides with a block edge: nothing is shared here
   const int64_t prev = plan.begin(j - 1);
   if (prev > start) return;                 // an earlier boundary inside this block owns it
+  const int64_t b = plan.tail_block0() + bt;
   const size_t slot_elems = (size_t)nrows * per;
   for (int l = threadIdx.x; l < per; l += blockDim.x) {
     const int64_t i = b * per + l;
     if (i >= nt) return;
     for (int k = 0; k < nrows; ++k) {
       double acc = partial[((size_t)(j - 1) * kPPSlots + (prev == start ? 0 : 1)) * slot_elems + (size_t)k * per + l];
-      for (int c = j; c < plan.P && plan.begin(c) < end; ++c)
+      for (int c = j; c < plan.Pt && plan.begin(c) < end; ++c)
         acc += partial[((size_t)c * kPPSlots) * slot_elems + (size_t)k * per + l];
       if (acc64) {
         acc64[(size_t)k * acc_stride + i] = acc;
@@ -496,19 +588,12 @@ __device__ __forceinline__ void pp_interact2(const float4 q0, const float4 q1, c
   }
 }
 
-// Per-target-block state of a persistent CTA's walk (pp2_walk / ppc_kernel)
-struct PPBlock {
-  int b, kt;        // target block and source tile of the current unit
-  bool seg_first;   // the current segment is the CTA's first
-  bool fresh;       // the current tile starts a segment: (re)load the targets, clear the FP64 sums
-};
-
 // One tile of the walk, out of ring buffer BUF. BUF is a template argument - the walk alternates two copies of this body - so
 // that every shared-memory address of the inner loop is [uniform base + immediate] with a base that does not depend on the tile:
 // with a run-time buffer index ptxas re-derives the buffer's address (a chain of five uniform-datapath instructions) at the
 // top of every trip of the inner loop, ahead of its first LDS, and at three warps per scheduler that latency is exposed (+3 %).
 template <int BUF, int T, bool GRAD, bool UNI, int BLOCK>
-__device__ __forceinline__ void pp2_tile(const PPArgs& p, PPWalk& w, PPBlock& s, float4 (&tile)[2][kTile * 2], uint64_t (&full)[2],
+__device__ __forceinline__ void pp2_tile(const PPArgs& p, PPWalk& w, PPBlock& s, float4 (&tile)[2][kTile * 2], PPSync& sy,
                                          const float r2u, const float k15, const float k75, float2 (&tx)[T], float2 (&ty)[T],
                                          float2 (&tz)[T], float2 (&tr2)[T],
                                          float2 (&acc)[T][PPAcc<GRAD>::N], double (&sum)[T][GRAD ? 12 : 3]) {
@@ -527,7 +612,7 @@ __device__ __forceinline__ void pp2_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
       for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
     }
   }
-  pp_ring_wait(full, w.kring);
+  pp_ring_wait(sy, w.kring);
 #if O3D_PP_TWOBUF
   const float4* __restrict__ src = tile[BUF];
 #else
@@ -568,21 +653,16 @@ __device__ __forceinline__ void pp2_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
 #endif
     pp_promote<GRAD>(h, sum[t]);
   }
-#if O3D_PP_TWOBUF
-  pp_ring_refill<BLOCK>(p, w, tile[BUF], &full[BUF]);         // ++w.kring
-#else
-  pp_ring_refill<BLOCK>(p, w, tile[w.kring & 1], &full[w.kring & 1]);
+#ifdef O3D_PP_ENDTIME
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && w.kring < 64 && (threadIdx.x >> 5) < 12) pp_tile_clock[threadIdx.x >> 5][w.kring] = clock64();
 #endif
-  ++s.kt;
-  s.fresh = s.kt == p.ntiles || w.kring == w.nk;              // the segment ends with this tile
-  if (s.fresh) {
-    // whole block <=> the segment ran from tile 0 to the last tile: kt == ntiles and (not the first segment or kt0 == 0)
-    const bool whole = s.kt == p.ntiles && (!s.seg_first || w.kt0 == 0);
-    pp_store<T, GRAD, BLOCK>(p, s.b, whole, s.seg_first ? 0 : 1, sum);
-    s.seg_first = false;
-    s.kt = 0;
-    ++s.b;
-  }
+  constexpr bool NOBAR = (O3D_PP_NOBAR == 1 && GRAD) || O3D_PP_NOBAR == 2;
+#if O3D_PP_TWOBUF
+  pp_ring_refill<BLOCK, NOBAR>(p, w, tile[BUF], &sy.full[BUF], &sy.released[BUF]);         // ++w.kring
+#else
+  pp_ring_refill<BLOCK, NOBAR>(p, w, tile[w.kring & 1], &sy.full[w.kring & 1], &sy.released[w.kring & 1]);
+#endif
+  pp_segment_end<T, GRAD, BLOCK>(p, w, s, sum);
 }
 
 // The whole share of one persistent CTA: ONE loop over its tiles, two per trip (ring buffer 0, ring buffer 1), so that the nest
@@ -590,7 +670,7 @@ __device__ __forceinline__ void pp2_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
 // and LDS addresses in uniform registers for; the target block changes inside that loop, at the tiles where a segment starts /
 // ends. The UNI flag is warp-uniform: the two instantiations are two straight-line copies selected once per kernel.
 template <int T, bool GRAD, bool UNI, int BLOCK>
-__device__ __forceinline__ void pp2_walk(const PPArgs& p, PPWalk& w, float4 (&tile)[2][kTile * 2], uint64_t (&full)[2], const float r2u) {
+__device__ __forceinline__ void pp2_walk(const PPArgs& p, PPWalk& w, float4 (&tile)[2][kTile * 2], PPSync& sy, const float r2u) {
   constexpr int NA = PPAcc<GRAD>::N;
   constexpr int NS = GRAD ? 12 : 3;
   float2 tx[T], ty[T], tz[T], tr2[T];
@@ -605,11 +685,11 @@ __device__ __forceinline__ void pp2_walk(const PPArgs& p, PPWalk& w, float4 (&ti
   // register) hands them to ptxas as values it neither has to keep in the vector register file nor can re-derive in the loop
   const float k15 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(1.5f * r2u)));
   const float k75 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(-7.5f * r2u)));
-  PPBlock s{w.b0, w.kt0, true, true};
+  PPBlock s = pp_first_block(w);
   while (w.kring < w.nk) {
-    pp2_tile<0, T, GRAD, UNI, BLOCK>(p, w, s, tile, full, r2u, k15, k75, tx, ty, tz, tr2, acc, sum);
+    pp2_tile<0, T, GRAD, UNI, BLOCK>(p, w, s, tile, sy, r2u, k15, k75, tx, ty, tz, tr2, acc, sum);
 #if O3D_PP_TWOBUF
-    if (w.kring < w.nk) pp2_tile<1, T, GRAD, UNI, BLOCK>(p, w, s, tile, full, r2u, k15, k75, tx, ty, tz, tr2, acc, sum);
+    if (w.kring < w.nk) pp2_tile<1, T, GRAD, UNI, BLOCK>(p, w, s, tile, sy, r2u, k15, k75, tx, ty, tz, tr2, acc, sum);
 #endif
   }
 }
@@ -617,7 +697,7 @@ __device__ __forceinline__ void pp2_walk(const PPArgs& p, PPWalk& w, float4 (&ti
 template <int T, bool GRAD, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) pp2_kernel(const PPArgs p) {
   __shared__ alignas(128) float4 tile[2][kTile * 2];
-  __shared__ alignas(8) uint64_t full[2];
+  __shared__ alignas(8) PPSync sy;
 
 #if O3D_PP_STAGGER
   {
@@ -632,7 +712,7 @@ __global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) pp2_kernel(
     while (clock64() < until) {}
   }
 #endif
-  PPWalk w = pp_ring_start<BLOCK>(p, tile, full);
+  PPWalk w = pp_ring_start<BLOCK>(p, tile, sy);
 
   // radius scan (pp_scan_kernel): [0] ~min, [1] max of sr^2 bit patterns over sources that carry strength,
   // [2] ~min, [3] max of tr bit patterns. Uniform <=> both ranges collapse and the constant r2 is positive.
@@ -644,8 +724,8 @@ __global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) pp2_kernel(
     r2u = __fadd_rn(__uint_as_float(s0), __fmul_rn(tr, tr));   // sr*sr + tr*tr, the reference's r2 (src/CoreFunc.h:267)
     uni = s0 == s1 && (!p.tr || t0 == t1) && r2u > 0.0f && s0 != 0xffffffffu;
   }
-  if (uni) pp2_walk<T, GRAD, true, BLOCK>(p, w, tile, full, r2u);
-  else     pp2_walk<T, GRAD, false, BLOCK>(p, w, tile, full, r2u);
+  if (uni) pp2_walk<T, GRAD, true, BLOCK>(p, w, tile, sy, r2u);
+  else     pp2_walk<T, GRAD, false, BLOCK>(p, w, tile, sy, r2u);
 #ifdef O3D_PP_ENDTIME
   if (threadIdx.x == 0 && blockIdx.x < 2048) {
     unsigned long long t; unsigned smid;

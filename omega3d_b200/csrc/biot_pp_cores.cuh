@@ -155,7 +155,7 @@ __device__ __forceinline__ void ppc_interact2(const float4 q0, const float4 q1, 
 
 // One tile of a persistent CTA's walk out of ring buffer BUF: pp2_tile (biot_pp.cuh) with this file's interaction.
 template <int BUF, int CORE, int T, bool GRAD, int BLOCK>
-__device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s, float4 (&tile)[2][kTile * 2], uint64_t (&full)[2],
+__device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s, float4 (&tile)[2][kTile * 2], PPSync& sy,
                                          float2 (&tx)[T], float2 (&ty)[T], float2 (&tz)[T], float2 (&tt)[T],
                                          float2 (&acc)[T][PPAcc<GRAD>::N], double (&sum)[T][GRAD ? 12 : 3]) {
   constexpr int NS = GRAD ? 12 : 3;
@@ -172,7 +172,7 @@ __device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
       for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
     }
   }
-  pp_ring_wait(full, w.kring);
+  pp_ring_wait(sy, w.kring);
   const float4* __restrict__ src = tile[BUF];
 #pragma unroll(CORE == kCoreEXP ? 2 : GRAD ? kPPUnrollGrad : kPPUnrollVel)
   for (int j = 0; j < kTile / 2; ++j) {
@@ -188,16 +188,8 @@ __device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
     if constexpr (GRAD) h[11] = -(h[3] + h[7]);
     pp_promote<GRAD>(h, sum[t]);
   }
-  pp_ring_refill<BLOCK>(p, w, tile[BUF], &full[BUF]);         // ++w.kring
-  ++s.kt;
-  s.fresh = s.kt == p.ntiles || w.kring == w.nk;
-  if (s.fresh) {
-    const bool whole = s.kt == p.ntiles && (!s.seg_first || w.kt0 == 0);
-    pp_store<T, GRAD, BLOCK>(p, s.b, whole, s.seg_first ? 0 : 1, sum);
-    s.seg_first = false;
-    s.kt = 0;
-    ++s.b;
-  }
+  pp_ring_refill<BLOCK, O3D_PP_NOBAR == 2>(p, w, tile[BUF], &sy.full[BUF], &sy.released[BUF]);         // ++w.kring
+  pp_segment_end<T, GRAD, BLOCK>(p, w, s, sum);
 }
 
 template <int CORE, int T, bool GRAD, int BLOCK>
@@ -205,11 +197,11 @@ __global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) ppc_kernel(
   constexpr int NS = GRAD ? 12 : 3;
   constexpr int NA = PPAcc<GRAD>::N;
   __shared__ alignas(128) float4 tile[2][kTile * 2];
-  __shared__ alignas(8) uint64_t full[2];
+  __shared__ alignas(8) PPSync sy;
 
   // persistent CTA: one loop over the tiles of its share, two per trip (ring buffer 0, 1), the target block changing at
   // segment boundaries (pp2_walk, biot_pp.cuh)
-  PPWalk w = pp_ring_start<BLOCK>(p, tile, full);
+  PPWalk w = pp_ring_start<BLOCK>(p, tile, sy);
   float2 tx[T], ty[T], tz[T], tt[T];
   double sum[T][NS];
   float2 acc[T][NA];
@@ -218,10 +210,10 @@ __global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) ppc_kernel(
 #pragma unroll
     for (int k = 0; k < NA; ++k) acc[t][k] = f2(0.f, 0.f);
   }
-  PPBlock s{w.b0, w.kt0, true, true};
+  PPBlock s = pp_first_block(w);
   while (w.kring < w.nk) {
-    ppc_tile<0, CORE, T, GRAD, BLOCK>(p, w, s, tile, full, tx, ty, tz, tt, acc, sum);
-    if (w.kring < w.nk) ppc_tile<1, CORE, T, GRAD, BLOCK>(p, w, s, tile, full, tx, ty, tz, tt, acc, sum);
+    ppc_tile<0, CORE, T, GRAD, BLOCK>(p, w, s, tile, sy, tx, ty, tz, tt, acc, sum);
+    if (w.kring < w.nk) ppc_tile<1, CORE, T, GRAD, BLOCK>(p, w, s, tile, sy, tx, ty, tz, tt, acc, sum);
   }
 }
 

@@ -383,7 +383,8 @@ struct PPShape {
   int nblocks;        // target blocks of 384 * T targets
   int grid;           // CTAs = min(units, resident slots)
   int64_t units;      // nblocks * ntiles
-  int split_blocks;   // target blocks shared by more than one CTA (finished by pp_fixup_kernel)
+  int split_blocks;   // tail blocks shared by more than one CTA (finished by pp_fixup_kernel)
+  PPPlan plan;
 };
 // (kPPResident = 1 CTA of 384 threads per SM, register-limited: <= 168 registers per thread, lib/ptxas.log; csrc/biot_pp.cuh)
 // workspace of one launch: 2 slots per CTA x (12 rows x 768 targets | 3 rows x 1536 targets) FP64 - a constant of the device
@@ -409,12 +410,12 @@ PPShape pp_shape(int sm_count, int64_t ntiles, int64_t nt, bool grad) {
   PPShape s;
   s.nblocks = (int)((nt + per_cta - 1) / per_cta);
   s.units = (int64_t)s.nblocks * ntiles;
-  s.grid = (int)std::min<int64_t>(s.units, (int64_t)sm_count * kPPResident);
-  const PPPlan plan{s.units, s.grid, (int)ntiles};
+  s.plan = pp_make_plan(sm_count * kPPResident, s.nblocks, (int)ntiles);
+  s.grid = s.plan.P;
   s.split_blocks = 0;
-  for (int j = 1; j < s.grid; ++j) {      // pp_fixup_kernel's own test: a boundary inside a block, the first one there
-    const int64_t cut = plan.begin(j), start = cut / ntiles * ntiles;
-    if (cut != start && plan.begin(j - 1) <= start) ++s.split_blocks;
+  for (int j = 1; j < s.plan.Pt; ++j) {   // pp_fixup_kernel's own test: a boundary inside a block, the first one there
+    const int64_t cut = s.plan.begin(j), start = cut / ntiles * ntiles;
+    if (cut != start && s.plan.begin(j - 1) <= start) ++s.split_blocks;
   }
   return s;
 }
@@ -431,6 +432,7 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   a.src = packed;
   a.ntiles = (int)ntiles;
   a.nblocks = s.nblocks;
+  a.slots = d.sm_count * kPPResident;
   a.nt = nt;
   a.tx = tx; a.ty = ty; a.tz = tz; a.tr = tr;
   a.tu = tu; a.tv = tv; a.tw = tw;
@@ -480,11 +482,10 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   O3D_TRY(d, cudaGetLastError());
   if (d.profile) O3D_TRY(d, cudaEventRecord(d.evk[1], st));
   d.launches += 1;
-  if (s.grid > 1) {
-    // the target blocks cut by a CTA-range boundary: add their pieces in unit order (one CTA per boundary)
-    const PPPlan plan{s.units, s.grid, (int)ntiles};
-    pp_fixup_kernel<<<(unsigned)(s.grid - 1), 256, 0, st>>>(grad ? 12 : 3, kPPBlock * (grad ? kPPTgrad : kPPTvel), plan, nt, a.partial, tu, tv, tw,
-                                                                                              tug, tug_stride, 1.0f, a.acc64, a.acc_stride);
+  if (s.plan.Pt > 1) {
+    // the tail blocks cut by a CTA-range boundary: add their pieces in unit order (one CTA per boundary)
+    pp_fixup_kernel<<<(unsigned)(s.plan.Pt - 1), 256, 0, st>>>(grad ? 12 : 3, kPPBlock * (grad ? kPPTgrad : kPPTvel), s.plan, nt, a.partial, tu, tv, tw,
+                                                             tug, tug_stride, 1.0f, a.acc64, a.acc_stride);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
   }
@@ -1556,9 +1557,8 @@ int o3d_cuda_plan_pts_on_pts(int sm_count, int64_t ns, int64_t nt, int want_grad
   if (grid) *grid = s.grid;
   if (split_blocks) *split_blocks = s.split_blocks;
   if (balance) {   // mean / max tiles per CTA: what fraction of the launch's duration the average CTA is busy
-    const PPPlan plan{s.units, s.grid, (int)ntiles};
     int64_t most = 0;
-    for (int c = 0; c < s.grid; ++c) most = std::max(most, plan.begin(c + 1) - plan.begin(c));
+    for (int c = 0; c < s.grid; ++c) most = std::max(most, s.plan.tiles_of(c));
     *balance = (double)s.units / ((double)most * s.grid);
   }
   if (workspace_bytes) *workspace_bytes = (int64_t)pp_workspace_bytes(sm_count);
@@ -1574,22 +1574,31 @@ int o3d_cuda_plan_check(int sm_count, int64_t ns, int64_t nt, int want_grad) {
   const bool grad = want_grad != 0;
   const int ntiles = (int)(padded_sources(ns) / kTile);
   const PPShape s = pp_shape(sm_count, ntiles, nt, grad);
-  const PPPlan plan{s.units, s.grid, ntiles};
-  if (s.grid < 1 || s.grid > sm_count * kPPResident || plan.begin(0) != 0 || plan.begin(s.grid) != s.units) return 1;
+  const PPPlan plan = s.plan;
+  if (s.grid < 1 || s.grid > sm_count * kPPResident || plan.begin(0) != 0 || plan.begin(s.grid) != plan.Wt || plan.Pt > plan.P) return 1;
+  if ((int64_t)plan.P * plan.full * ntiles + plan.Wt != s.units) return 1;
   std::vector<int> tiles_done(s.nblocks, 0), whole(s.nblocks, 0), fixed(s.nblocks, 0);
   std::vector<int> slot_block((size_t)s.grid * kPPSlots, -1), slot_tiles((size_t)s.grid * kPPSlots, 0), slot_read((size_t)s.grid * kPPSlots, 0);
   for (int c = 0; c < s.grid; ++c) {
     const int64_t u0 = plan.begin(c), u1 = plan.begin(c + 1);
-    const int nk = (int)(u1 - u0), b0 = (int)(u0 / ntiles), kt0 = (int)(u0 % ntiles);      // pp_ring_start
-    if (nk < 1) return 2;
-    int b = b0, kt = kt0, kring = 0, seg_tiles = 0;                                          // pp2_walk / ppc_kernel
-    bool seg_first = true;
-    while (kring < nk) {
+    const int nA = plan.full * ntiles, nk = nA + (int)(u1 - u0);                              // pp_ring_start
+    const int bA0 = c * plan.full, bB0 = plan.tail_block0() + (int)(u0 / ntiles), ktB0 = (int)(u0 % ntiles);
+    if (nk < 1 || nk != plan.tiles_of(c)) return 2;
+    int b = nA > 0 ? bA0 : bB0, kt = nA > 0 ? 0 : ktB0, kring = 0, seg_tiles = 0;             // pp_first_block
+    bool seg_first = nA == 0;
+    int tnext = nA > 0 ? 0 : ktB0, fetched = 0;                                               // the ring's prefetch order
+    auto fetch = [&]() { const int t = tnext; tnext = fetched + 1 == nA ? ktB0 : (tnext + 1 == ntiles ? 0 : tnext + 1); ++fetched; return t; };
+    int ring[2] = {-1, -1};
+    for (int q = 0; q < 2 && q < nk; ++q) ring[q] = fetch();
+    while (kring < nk) {                                                                      // pp2_walk / pp_segment_end
       if (b >= s.nblocks) return 3;
-      if ((int64_t)b * ntiles + kt != u0 + kring) return 4;
+      if (ring[kring & 1] != kt) return 4;                                                    // the tile in the buffer is the unit's
+      if (kring >= nA && (int64_t)(b - plan.tail_block0()) * ntiles + kt != u0 + (kring - nA)) return 4;
+      if (kring < nA && (b != bA0 + kring / ntiles || kt != kring % ntiles)) return 4;
+      if (kring + 2 < nk) ring[kring & 1] = fetch();
       ++kring; ++kt; ++seg_tiles;
       if (kt == ntiles || kring == nk) {
-        const bool is_whole = kt == ntiles && (!seg_first || kt0 == 0);
+        const bool is_whole = kt == ntiles && (!seg_first || ktB0 == 0);
         if (is_whole != (seg_tiles == ntiles)) return 5;
         tiles_done[b] += seg_tiles;
         if (is_whole) whole[b] += 1;
@@ -1603,15 +1612,17 @@ int o3d_cuda_plan_check(int sm_count, int64_t ns, int64_t nt, int want_grad) {
         kt = 0;
         seg_tiles = 0;
         ++b;
+        if (kring == nA) { b = bB0; kt = ktB0; seg_first = true; }
       }
     }
   }
-  for (int j = 1; j < s.grid; ++j) {                                      // pp_fixup_kernel
+  for (int j = 1; j < plan.Pt; ++j) {                                     // pp_fixup_kernel
     const int64_t cut = plan.begin(j);
-    const int64_t b = cut / ntiles, start = b * ntiles, end = start + ntiles;
+    const int64_t bt = cut / ntiles, start = bt * ntiles, end = start + ntiles;
     if (cut == start) continue;
     const int64_t prev = plan.begin(j - 1);
     if (prev > start) continue;
+    const int64_t b = plan.tail_block0() + bt;
     int got = 0;
     auto take = [&](size_t slot) {
       if (slot_block[slot] != (int)b) return false;
@@ -1620,7 +1631,7 @@ int o3d_cuda_plan_check(int sm_count, int64_t ns, int64_t nt, int want_grad) {
       return true;
     };
     if (!take((size_t)(j - 1) * kPPSlots + (prev == start ? 0 : 1))) return 7;
-    for (int c = j; c < plan.P && plan.begin(c) < end; ++c)
+    for (int c = j; c < plan.Pt && plan.begin(c) < end; ++c)
       if (!take((size_t)c * kPPSlots)) return 8;
     if (got != ntiles) return 9;
     fixed[b] += 1;

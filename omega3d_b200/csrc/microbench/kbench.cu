@@ -125,10 +125,10 @@ int main(int argc, char** argv) {
     a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = grad ? out + 3 * (size_t)n : nullptr; a.tug_stride = n;
     a.partial = ppwork; a.sign = 1.0f;
     a.radius_range = no_uniform ? nullptr : range;
-    const int64_t units = (int64_t)a.nblocks * a.ntiles;
-    const int grid = (int)std::min<int64_t>(units, (int64_t)prop.multiProcessorCount * per_sm);
+    a.slots = prop.multiProcessorCount * per_sm;
+    const PPPlan plan = pp_make_plan(a.slots, a.nblocks, a.ntiles);
+    const int grid = plan.P;
     if ((int64_t)grid * BLOCK * T * (grad ? 12 : 3) > (int64_t)resident * 12 * 256) { printf("%s: workspace too small for this shape\n", name); return; }
-    const PPPlan plan{units, grid, a.ntiles};
     float best = 1e30f;
     for (int r = 0; r < reps + 1; ++r) {
       CHECK(cudaMemset(out, 0, (size_t)n * 12 * 4));
@@ -139,7 +139,7 @@ int main(int argc, char** argv) {
       } else {
         kern<<<grid, BLOCK>>>(a);
       }
-      if (grid > 1) pp_fixup_kernel<<<grid - 1, 256>>>(grad ? 12 : 3, BLOCK * T, plan, n, ppwork, a.tu, a.tv, a.tw, a.tug, n, 1.0f, nullptr, 0);
+      if (plan.Pt > 1) pp_fixup_kernel<<<plan.Pt - 1, 256>>>(grad ? 12 : 3, BLOCK * T, plan, n, ppwork, a.tu, a.tv, a.tw, a.tug, n, 1.0f, nullptr, 0);
       cudaEventRecord(e1);
       CHECK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -157,6 +157,16 @@ int main(int argc, char** argv) {
       printf("   SM 0..3 CTAs (lag ms):");
       for (unsigned q = 0; q < 4; ++q) { printf(" ["); for (int c = 0; c < grid; ++c) if (sm[c] == q) printf(" %.2f", lag[c]); printf(" ]"); }
       printf("\n");
+      if (BLOCK == 384) {   // per-tile skew of the 12 warps of CTA 0: when does each warp finish a tile's arithmetic, relative to the first
+        long long tc[12][64];
+        CHECK(cudaMemcpyFromSymbol(tc, pp_tile_clock, sizeof tc));
+        for (int k = 8; k < 14; ++k) {
+          long long t0 = tc[0][k]; for (int wp = 0; wp < 12; ++wp) t0 = std::min(t0, tc[wp][k]);
+          printf("   tile %2d: length %lld clk; warps done at (clk after the first, scheduler = warp %% 4):", k, tc[0][k] - tc[0][k - 1]);
+          for (int q = 0; q < 4; ++q) { printf("  [s%d", q); for (int wp = q; wp < 12; wp += 4) printf(" %lld", tc[wp][k] - t0); printf("]"); }
+          printf("\n");
+        }
+      }
     }
 #endif
   };

@@ -18,8 +18,8 @@ timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --ma
    bench.py --gpus $G --steps $STEPS --warmup 3 2>&1 | tail -1 | tee $OUT/r2_bench_g${G}_4m.json
 echo "== bench $G GPUs at 1 M"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29512 \
-   bench.py --gpus $G --steps 5 --warmup 3 --n 1048576 --extra-n 0 2>&1 | tail -1 | tee $OUT/r2_bench_g${G}_1m.json
+   bench.py --gpus $G --steps 5 --warmup 3 --particles 1048576 --extra-n 0 2>&1 | tail -1 | tee $OUT/r2_bench_g${G}_1m.json
 echo "== bench --inproc $G (one process, pageable host arrays)"
-timeout 900 python bench.py --inproc $G --steps 3 --warmup 1 --n 1048576 2>&1 | tail -1 | tee $OUT/r2_bench_inproc${G}_1m.json
+timeout 900 python bench.py --inproc $G --steps 3 --warmup 1 --particles 1048576 2>&1 | tail -1 | tee $OUT/r2_bench_inproc${G}_1m.json
 timeout 900 python bench.py --inproc $G --steps 2 --warmup 1 2>&1 | tail -1 | tee $OUT/r2_bench_inproc${G}_4m.json
-timeout 600 python bench.py --inproc 1 --steps 3 --warmup 1 --n 1048576 2>&1 | tail -1 | tee $OUT/r2_bench_inproc1_1m.json
+timeout 600 python bench.py --inproc 1 --steps 3 --warmup 1 --particles 1048576 2>&1 | tail -1 | tee $OUT/r2_bench_inproc1_1m.json

@@ -93,11 +93,11 @@ HEADER = "biot_pp_cores.cuh" if PPC else "biot_pp.cuh"
 SASS_NAME = "ppc_kernel" if PPC else "pp2_kernel"
 MUFU_PER_BODY = 4.0 if VARIANT in ("v2", "v2vel") else 2.0     # MUFU instructions per (target, source pair): two lanes x (rsqrt [+ sqrt])
 if PPC:
-    KERNEL = {"rm": "ppc_kernel<1, 2, true, 128>", "rmvel": "ppc_kernel<1, 4, false, 128>",
-              "v2": "ppc_kernel<3, 2, true, 128>", "v2vel": "ppc_kernel<3, 4, false, 128>"}[VARIANT]
+    KERNEL = {"rm": "ppc_kernel<1, 2, true, 384>", "rmvel": "ppc_kernel<1, 4, false, 384>",
+              "v2": "ppc_kernel<3, 2, true, 384>", "v2vel": "ppc_kernel<3, 4, false, 384>"}[VARIANT]
     BODY_MACRO = {"rm": "O3D_PPC_BODY_RM_GRAD", "rmvel": "O3D_PPC_BODY_RM_VEL", "v2": "O3D_PPC_BODY_V2_GRAD", "v2vel": "O3D_PPC_BODY_V2_VEL"}[VARIANT]
 else:
-    KERNEL = "pp2_kernel<2, true, 128>" if VARIANT in ("uni", "gen") else "pp2_kernel<4, false, 128>"
+    KERNEL = "pp2_kernel<2, true, 384>" if VARIANT in ("uni", "gen") else "pp2_kernel<4, false, 384>"
     BODY_MACRO = {"uni": "O3D_PP_BODY_FILE", "gen": "O3D_PP_BODY_FILE_GEN", "vel": "O3D_PP_BODY_FILE_VEL", "velgen": "O3D_PP_BODY_FILE_VELGEN"}[VARIANT]
 PER_BODY = len([st for st in STMTS if st[1] not in ("rsq", "sqrt")])        # packed instructions per (target, source pair): picks the loop
 
