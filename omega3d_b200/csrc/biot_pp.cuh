@@ -81,6 +81,12 @@
 #endif                    // one out refills it, so the warps of a CTA may drift one tile apart. 0: barrier in every kernel; 1 (product): the
                           // velocity+gradient pp2_kernel goes without (-0.8 %; the velocity-only kernel measures 1.1 % SLOWER without its
                           // barrier: profiles/r02_kbench_nobar.txt); 2: every kernel without (microbench/kbench only)
+#ifndef O3D_PP_PURE
+#define O3D_PP_PURE 0     // 1 (microbench/kbench only): no whole-block phase - the pure stream-K partition of every unit
+#endif
+#ifndef O3D_PP_SKEW
+#define O3D_PP_SKEW 0     // > 0 (microbench/kbench only): CTA c starts c * O3D_PP_SKEW nanoseconds late
+#endif
 #ifndef O3D_PP_STAGGER
 #define O3D_PP_STAGGER 0  // > 0 (microbench/kbench only): the k-th CTA to arrive on an SM starts (k mod 3) * O3D_PP_STAGGER clocks late, so
 #endif                    // that the co-resident CTAs do not reach their tile boundaries together
@@ -170,7 +176,7 @@ __host__ __device__ inline PPPlan pp_make_plan(int slots, int nblocks, int ntile
   q.nblocks = nblocks; q.ntiles = ntiles;
   const int64_t W = (int64_t)nblocks * ntiles;
   q.P = (int)(W < slots ? W : slots);
-  q.full = nblocks / q.P;
+  q.full = O3D_PP_PURE ? 0 : nblocks / q.P;
   q.Wt = (int64_t)(nblocks - q.P * q.full) * ntiles;
   q.Pt = (int)(q.Wt < q.P ? q.Wt : q.P);
   return q;
@@ -710,6 +716,13 @@ __global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) pp2_kernel(
     __syncthreads();
     const long long until = clock64() + (long long)slot * O3D_PP_STAGGER;
     while (clock64() < until) {}
+  }
+#endif
+#if O3D_PP_SKEW
+  {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); } while (t1 - t0 < (unsigned long long)blockIdx.x * O3D_PP_SKEW);
   }
 #endif
   PPWalk w = pp_ring_start<BLOCK>(p, tile, sy);

@@ -24,7 +24,7 @@ os.environ.setdefault("O3D_TUNE_PATCHED", "1")
 os.environ.setdefault("O3D_TUNE_WORK", "/tmp/kvgpu")
 import tune_order as T  # noqa: E402
 
-POP = os.path.join(ROOT, "kb_variants")
+POP = os.path.join(ROOT, os.environ.get("O3D_TUNE_POP", "kb_variants"))       # population directory (relative to the repo)
 
 
 def build(args):
@@ -69,8 +69,9 @@ def gen(base, count, seed, slack):
 def pick():
     index = json.load(open(os.path.join(POP, "index.json")))
     rows = []
-    for l in open(os.path.join(ROOT, "gpurun_out", "cubins.txt")):
-        m = re.match(r"cubin kb_variants/(cand_\d+)\.cubin\s+(\w+)\s+([\d.]+) ms.*fnv (\w+)", l)
+    tag = os.path.relpath(POP, ROOT)
+    for l in open(os.path.join(ROOT, "gpurun_out", os.environ.get("O3D_TUNE_TIMES", "cubins.txt"))):
+        m = re.match(r"cubin " + re.escape(tag) + r"/(cand_\d+)\.cubin\s+(\w+).*?([\d.]+) ms.*fnv (\w+)", l)
         if m:
             rows.append((float(m.group(3)), m.group(1), m.group(4)))
     rows.sort()
