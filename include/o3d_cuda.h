@@ -196,7 +196,9 @@ int o3d_cuda_particles_advect(o3d_ctx* ctx, o3d_particles* p, int order, double 
                               int nsteps, double* flops_out);
 /* panels -> points (o3d_cuda_pan_on_pts, bodies attached to resident collections) pools the (point, panel) pairs that need
  * subdivision per warp and lets all 32 lanes drain the pool (default); off = every lane walks only its own pairs, the
- * round-1 kernel, kept for A/B measurements. Same leaves, same counts; FP32 terms of a tile regrouped. */
+ * round-1 kernel, kept for A/B measurements. Same leaves, same counts; FP32 terms of a tile regrouped.
+ * on = 1 (default): panels -> points only; 2: particles -> panels as well (o3d_cuda_pts_on_pan, the BEM right-hand side of a
+ * resident body: measured no faster than the per-lane kernel, so not the default); 0: neither. */
 int o3d_cuda_set_panel_queue(o3d_ctx* ctx, int on);
 /* Host arrays of the entry points above may be pageable (the reference's std::vector storage) or pinned. Pageable arrays
  * travel through a ring of pinned slots the context owns (4 x 8 MB per device; helper threads fill the next slot while the

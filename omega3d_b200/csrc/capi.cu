@@ -194,7 +194,8 @@ struct Device {
   cudaEvent_t evk[2] = {nullptr, nullptr};                   // around the dominant kernel of a *_dev call
   bool profile = false;
   bool tuned = true;                                         // launch pp2_kernel from the post-processed cubin (TunedKernels)
-  bool pan_queue = true;                                     // panels -> points with the warp-level work queue (pan_pts_queue_kernel)
+  int pan_queue = 1;                                         // 1: panels -> points with the warp-level work pool (pan_pts_queue_kernel);
+                                                             // 2: particles -> panels too (pts_pan_queue_kernel: measured no faster); 0: neither
   int core = O3D_CORE_WL;                                    // core function of the particle kernels (o3d_cuda_set_core_func)
   DevBuf src, packed, targ, out, work, ppwork, geom, panels, tpanels, cnt, rng;
   unsigned long long counts[2] = {0, 0};  // leaves, splits of the last panel call on this device
@@ -874,7 +875,7 @@ bool body_solve(o3d_ctx* c, o3d_particles* p, const double* fs) {
     a.nsplit = pan_nsplit(d, gx, a.ntiles);
     O3D_TRY(d, b.work.ensure((size_t)a.nsplit * 3 * np * sizeof(double)));
     a.partial = b.work.as<double>();
-    if (d.pan_queue) pts_pan_queue_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
+    if (d.pan_queue >= 2) pts_pan_queue_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
     else             pts_pan_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
     O3D_TRY(d, cudaGetLastError());
     pp_finish_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(3, a.nsplit, np, a.partial, pu, pu + np, pu + 2 * np, nullptr, np, -1.0f);
@@ -1449,7 +1450,7 @@ int o3d_cuda_pts_on_pan(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
     a.nsplit = pan_nsplit(d, gx, a.ntiles);
     O3D_TRY(d, d.work.ensure((size_t)a.nsplit * 3 * n * sizeof(double)));
     a.partial = d.work.as<double>();
-    if (d.pan_queue) pts_pan_queue_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
+    if (d.pan_queue >= 2) pts_pan_queue_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
     else             pts_pan_kernel<B><<<dim3((unsigned)gx, (unsigned)a.nsplit), B, 0, st>>>(a);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
@@ -2481,7 +2482,7 @@ int o3d_cuda_set_graphs(o3d_ctx* c, int on) {
 
 int o3d_cuda_set_panel_queue(o3d_ctx* c, int on) {
   if (!c) return O3D_ERR_INVALID;
-  for (Device& d : c->dev) d.pan_queue = on != 0;
+  for (Device& d : c->dev) d.pan_queue = on < 0 ? 0 : on > 2 ? 2 : on;
   return O3D_OK;
 }
 

@@ -88,6 +88,33 @@ def test_panels_golden(cuda_ctx, restate):
     assert rel_err(tsurf.pu, g["pan_on_pan_pu"]) <= VEL_TOL
 
 
+def test_panel_work_pool_modes_agree(cuda_ctx):
+    """o3d_cuda_set_panel_queue: 0 = every lane walks its own deferred pairs, 1 (default) = panels -> points pools them per warp,
+    2 = particles -> panels as well. Same leaves and splits (the reference's flop count is an exact function of the traversal),
+    same sums up to the regrouping of FP32 terms inside a tile."""
+    g = golden("panels_80.npz")
+    surf = I.Surfaces(soa(g["nodes_i"]), g["idx"], g["val"], I.active, I.fixed)
+    src = I.Points(g["psx"], g["pss"], g["psr"], I.active, I.lagrangian)
+    out = {}
+    try:
+        for mode in (0, 1, 2):
+            cuda_ctx.set_panel_queue(mode)
+            fld = I.Points(g["tx"], e=I.inert, m=I.fixed)
+            I.panels_affect_points(surf, fld, I.ResultsType(I.velonly), I.ExecEnv(), cuda_ctx)
+            f1 = cuda_ctx.flops
+            surf.pu[:] = 0
+            I.points_affect_panels(src, surf, I.ResultsType(I.velonly), I.ExecEnv(), cuda_ctx)
+            out[mode] = (fld.u.copy(), fld.ug.copy(), surf.pu.copy(), f1, cuda_ctx.flops)
+    finally:
+        cuda_ctx.set_panel_queue(1)
+    for mode in (1, 2):
+        assert out[mode][3] == out[0][3] and out[mode][4] == out[0][4]
+        assert rel_err(out[mode][0], out[0][0]) <= 2e-6 and rel_err(out[mode][1], out[0][1]) <= 2e-6
+        assert rel_err(out[mode][2], out[0][2]) <= 2e-6
+    assert np.array_equal(out[1][2], out[0][2])      # mode 1 leaves particles -> panels on the per-lane kernel
+    assert rel_err(out[0][2], g["pu"] - g["pu0"]) <= VEL_TOL
+
+
 def test_coeff_golden(cuda_ctx):
     g = golden("coeff_20.npz")
     s0 = I.Surfaces(soa(g["n0"]), g["i0"], None, I.reactive, I.fixed)
