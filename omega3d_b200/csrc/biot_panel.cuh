@@ -63,6 +63,15 @@ __device__ __forceinline__ float sumsq_rn(float dx, float dy, float dz) {
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// sumsq_rn for two lanes at once. The products are packed; the sums are NOT: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
+// FFMA2 (it leaves the scalar .rn forms alone, and -fmad=false does not stop it), which would change the bits of the squared
+// distance and with them the reference's stop decision. Scalar adds on the halves of packed products stay unfused (checked in
+// the SASS: FMUL2, FMUL2, FADD, FADD, FMUL2, FADD, FADD; and by the leaf-for-leaf counts of tests/test_gpu_parity.py).
+__device__ __forceinline__ float2 sumsq2_rn(float2 dx, float2 dy, float2 dz) {
+  const float2 xx = __fmul2_rn(dx, dx), yy = __fmul2_rn(dy, dy), zz = __fmul2_rn(dz, dz);
+  return make_float2(__fadd_rn(__fadd_rn(xx.x, yy.x), zz.x), __fadd_rn(__fadd_rn(xx.y, yy.y), zz.y));
+}
+
 // The stop predicate without the square root. The reference tests  my_dist = sqrt(dx^2+dy^2+dz^2) > 4 sqrt(area)  with a
 // correctly rounded sqrt (src/Kernels.h:979-1002); that function is monotonic, so for every threshold thr there is one float
 // T = max { x : sqrt_rn(x) <= thr }  with  sqrt_rn(x) > thr  <=>  x > T  for all x >= 0: the SAME decision, bit for bit, from
@@ -138,6 +147,40 @@ __device__ __forceinline__ void pan_leaf(float dx, float dy, float dz, float dis
     acc[13] = fmaf(wy, r3, acc[13]);
     acc[14] = fmaf(wz, r3, acc[14]);
     acc[15] = fmaf(q, r3, acc[15]);
+  }
+}
+
+// Two leaves per instruction (packed FP32, as in biot_pp.cuh): lane halves .x / .y are two source panels against one point.
+// rs = 0 in a half switches that half off (its r3 and bbb vanish and every contribution is 0 * finite). Same operations per
+// half as pan_leaf; the two halves' sums meet once per tile.
+template <bool GRAD, bool SRC = true>
+__device__ __forceinline__ void pan_leaf2(float2 dx, float2 dy, float2 dz, float2 rs, float2 wx, float2 wy, float2 wz,
+                                          float2 q, float2 (&acc)[PanAcc<GRAD>::N]) {
+  const float2 rs2 = __fmul2_rn(rs, rs);
+  const float2 r3 = __fmul2_rn(rs2, rs);
+  float2 ex = __ffma2_rn(dz, wy, neg2(__fmul2_rn(dy, wz)));
+  float2 ey = __ffma2_rn(dx, wz, neg2(__fmul2_rn(dz, wx)));
+  float2 ez = __ffma2_rn(dy, wx, neg2(__fmul2_rn(dx, wy)));
+  if constexpr (SRC) { ex = __ffma2_rn(dx, q, ex); ey = __ffma2_rn(dy, q, ey); ez = __ffma2_rn(dz, q, ez); }   // source sheet
+  acc[0] = __ffma2_rn(r3, ex, acc[0]);
+  acc[1] = __ffma2_rn(r3, ey, acc[1]);
+  acc[2] = __ffma2_rn(r3, ez, acc[2]);
+  if constexpr (GRAD) {
+    const float2 bbb = __fmul2_rn(f2(-3.0f, -3.0f), __fmul2_rn(r3, rs2));
+    ex = __fmul2_rn(ex, bbb); ey = __fmul2_rn(ey, bbb); ez = __fmul2_rn(ez, bbb);
+    acc[3]  = __ffma2_rn(dx, ex, acc[3]);
+    acc[4]  = __ffma2_rn(dx, ey, acc[4]);
+    acc[5]  = __ffma2_rn(dx, ez, acc[5]);
+    acc[6]  = __ffma2_rn(dy, ex, acc[6]);
+    acc[7]  = __ffma2_rn(dy, ey, acc[7]);
+    acc[8]  = __ffma2_rn(dy, ez, acc[8]);
+    acc[9]  = __ffma2_rn(dz, ex, acc[9]);
+    acc[10] = __ffma2_rn(dz, ey, acc[10]);
+    acc[11] = __ffma2_rn(dz, ez, acc[11]);
+    acc[12] = __ffma2_rn(wx, r3, acc[12]);
+    acc[13] = __ffma2_rn(wy, r3, acc[13]);
+    acc[14] = __ffma2_rn(wz, r3, acc[14]);
+    acc[15] = __ffma2_rn(q, r3, acc[15]);
   }
 }
 
@@ -375,11 +418,16 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_queue_kernel(const PanPtsArgs p
   constexpr int NS = GRAD ? 12 : 3;
   constexpr int NW = BLOCK / 32;
   constexpr int RET = NA + 1;                                   // row stride of the return buffer: odd, conflict-free columns
-  __shared__ alignas(16) float4 tiles[NW][kPanTile * kPanRec];  // per-warp panel tile (5 KB)
+  // per-warp tile of phase A, pair-interleaved so that one packed instruction carries two panels (built while staging):
+  //   pair[4 m] = { -cx0 -cx1 -cy0 -cy1 }  [4 m + 1] = { -cz0 -cz1 T0 T1 }  [4 m + 2] = { wx0 wx1 wy0 wy1 }  [4 m + 3] = { wz0 wz1 q0 q1 }
+  // for panels 2 m, 2 m + 1 of the tile (T = squared level-0 threshold). The vertices are not staged: only the few pairs that
+  // subdivide need them, and read them from the record array (L1 / L2).
+  __shared__ alignas(16) float4 pairs[NW][(kPanTile / 2) * 4];  // 2 KB per warp
   __shared__ unsigned short lists[NW][32 * kPanTile];           // per-warp item list: owner << 6 | panel (4 KB)
   __shared__ float rets[NW][32 * RET];                          // per-warp partial sums of the 32 items in flight
+  static_assert(kPanTile == 64, "one lane stages one panel pair");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float4* tile = tiles[warp];
+  float4* pair = pairs[warp];
   unsigned short* list = lists[warp];
   float* ret = rets[warp];
 
@@ -390,31 +438,48 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_queue_kernel(const PanPtsArgs p
   const int64_t i = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
   const int64_t ic = min(i, p.nt - 1);
   const float tx = p.tx[ic], ty = p.ty[ic], tz = p.tz[ic];
+  const float2 tx2 = f2(tx, tx), ty2 = f2(ty, ty), tz2 = f2(tz, tz);
   const bool live = i < p.nt;                                   // clamped duplicate threads defer nothing and count nothing
 
+  float2 acc2[NA];
   float acc[NA];
   double sum[NS];
   unsigned counts[2] = {0u, 0u};
 #pragma unroll
-  for (int k = 0; k < NA; ++k) acc[k] = 0.0f;
+  for (int k = 0; k < NA; ++k) { acc2[k] = f2(0.f, 0.f); acc[k] = 0.0f; }
 #pragma unroll
   for (int k = 0; k < NS; ++k) sum[k] = 0.0;
 
   for (int k = k0; k < k1; ++k) {
     __syncwarp();
     const float4* g = p.pan + (size_t)k * (kPanTile * kPanRec);
-#pragma unroll
-    for (int e = lane; e < kPanTile * kPanRec; e += 32) tile[e] = g[e];
+    {
+      const float4* ra = g + (size_t)(2 * lane) * kPanRec;      // this lane stages panels 2 lane, 2 lane + 1
+      const float4* rb = ra + kPanRec;
+      const float4 a2 = ra[2], a3 = ra[3], a4 = ra[4], b2 = rb[2], b3 = rb[3], b4 = rb[4];
+      pair[4 * lane + 0] = make_float4(-a3.y, -b3.y, -a3.z, -b3.z);
+      pair[4 * lane + 1] = make_float4(-a3.w, -b3.w, a4.z, b4.z);
+      pair[4 * lane + 2] = make_float4(a2.y, b2.y, a2.z, b2.z);
+      pair[4 * lane + 3] = make_float4(a2.w, b2.w, a3.x, b3.x);
+    }
     __syncwarp();
-    // (A) every panel's level-0 test and, where the pair is well separated, its single leaf
+    // (A) every panel's level-0 test and, where the pair is well separated, its single leaf - two panels per instruction.
+    //     The decision is the reference's, bit for bit: t + (-c) is t - c, the squared distance is formed unfused in its order.
     unsigned long long near = 0ull;
     unsigned leaves0 = 0u;
 #pragma unroll 2
-    for (int j = 0; j < kPanTile; ++j) {
-      const float4 r2 = tile[j * kPanRec + 2], r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
-      if (pan_node<GRAD>(r3.y, r3.z, r3.w, r4.z, false, tx, ty, tz, r2.y, r2.z, r2.w, r3.x, acc)) leaves0 += 1;
-      else near |= 1ull << j;
+    for (int m = 0; m < kPanTile / 2; ++m) {
+      const float4 q0 = pair[4 * m], q1 = pair[4 * m + 1], q2 = pair[4 * m + 2], q3 = pair[4 * m + 3];
+      const float2 dx = __fadd2_rn(tx2, f2(q0.x, q0.y)), dy = __fadd2_rn(ty2, f2(q0.z, q0.w)), dz = __fadd2_rn(tz2, f2(q1.x, q1.y));
+      const float2 d2 = sumsq2_rn(dx, dy, dz);
+      const bool far0 = d2.x > q1.z, far1 = d2.y > q1.w;
+      leaves0 += (far0 ? 1u : 0u) + (far1 ? 1u : 0u);
+      near |= (unsigned long long)((far0 ? 0u : 1u) | (far1 ? 0u : 2u)) << (2 * m);
+      const float2 rs = f2(far0 ? rsqrt_approx(d2.x) : 0.0f, far1 ? rsqrt_approx(d2.y) : 0.0f);
+      pan_leaf2<GRAD>(dx, dy, dz, rs, f2(q2.x, q2.y), f2(q2.z, q2.w), f2(q3.x, q3.y), f2(q3.z, q3.w), acc2);
     }
+#pragma unroll
+    for (int q = 0; q < NA; ++q) { acc[q] = acc2[q].x + acc2[q].y; acc2[q] = f2(0.f, 0.f); }
     if (live) counts[0] += leaves0;
     else near = 0ull;
     // (B) pool the deferred pairs of the warp
@@ -451,8 +516,8 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_queue_kernel(const PanPtsArgs p
 #pragma unroll
       for (int q = 0; q < NA; ++q) part[q] = 0.0f;
       if (have) {
-        const float4 r0 = tile[j * kPanRec], r1 = tile[j * kPanRec + 1], r2 = tile[j * kPanRec + 2],
-                     r3 = tile[j * kPanRec + 3], r4 = tile[j * kPanRec + 4];
+        const float4* r = g + (size_t)j * kPanRec;
+        const float4 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4];
         const Tri t{r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
         pan_subdivide<GRAD>(t, r4.z, r2.y, r2.z, r2.w, r3.x, ox, oy, oz, part, counts);
       }
@@ -483,8 +548,8 @@ __global__ void __launch_bounds__(BLOCK) pan_pts_queue_kernel(const PanPtsArgs p
     if constexpr (GRAD) {
 #pragma unroll
       for (int k = 0; k < 9; ++k) {
-        float* g = p.tug + (size_t)k * p.tug_stride + i;
-        *g = (float)((double)*g + sum[3 + k]);
+        float* g2 = p.tug + (size_t)k * p.tug_stride + i;
+        *g2 = (float)((double)*g2 + sum[3 + k]);
       }
     }
   }
@@ -540,17 +605,27 @@ __global__ void __launch_bounds__(BLOCK) pts_pan_kernel(const PtsPanArgs p) {
       unsigned long long near = 0ull;
       // c0 is even and a record pair holds particles 2 pr, 2 pr + 1: one set of four LDS.128 serves both (the stream is
       // padded to whole tiles, so the second half of the last pair is readable; it is skipped when jj + 1 == cn)
-#pragma unroll 1
+      // two particles per packed instruction: the record pair holds (-x0 -x1 | -y0 -y1 | -z0 -z1), so nd = (-x) + c is -(x - c)
+      // exactly, the squared distance - and with it the reference's decision - has the same bits, and the sign goes into rs
+      // (the velocity sums are linear in r3 = rs^3)
+      const float2 cx2 = f2(cx, cx), cy2 = f2(cy, cy), cz2 = f2(cz, cz);
+      float2 acc2[3] = {f2(0.f, 0.f), f2(0.f, 0.f), f2(0.f, 0.f)};
+      unsigned leaves0 = 0u;
+#pragma unroll 2
       for (int jj = 0; jj < cn; jj += 2) {
         const int pr = (c0 + jj) >> 1;
         const float4 q0 = tile[4 * pr], q1 = tile[4 * pr + 1], q2 = tile[4 * pr + 2], q3 = tile[4 * pr + 3];
-        if (pan_node<false>(cx, cy, cz, thr0, false, -q0.x, -q0.z, -q1.x, q2.x, q2.z, q3.x, 0.0f, acc)) counts[0] += 1;
-        else near |= 1ull << jj;
-        if (jj + 1 < cn) {
-          if (pan_node<false>(cx, cy, cz, thr0, false, -q0.y, -q0.w, -q1.y, q2.y, q2.w, q3.y, 0.0f, acc)) counts[0] += 1;
-          else near |= 1ull << (jj + 1);
-        }
+        const float2 dx = __fadd2_rn(f2(q0.x, q0.y), cx2), dy = __fadd2_rn(f2(q0.z, q0.w), cy2), dz = __fadd2_rn(f2(q1.x, q1.y), cz2);
+        const float2 d2 = sumsq2_rn(dx, dy, dz);
+        const bool two = jj + 1 < cn;                            // the stream is padded to whole tiles: an odd count ends on half a pair
+        const bool far0 = d2.x > thr0, far1 = d2.y > thr0;
+        leaves0 += (far0 ? 1u : 0u) + (two && far1 ? 1u : 0u);
+        near |= (unsigned long long)((far0 ? 0u : 1u) | (two && !far1 ? 2u : 0u)) << jj;
+        const float2 rs = f2(far0 ? -rsqrt_approx(d2.x) : 0.0f, two && far1 ? -rsqrt_approx(d2.y) : 0.0f);
+        pan_leaf2<false, false>(dx, dy, dz, rs, f2(q2.x, q2.y), f2(q2.z, q2.w), f2(q3.x, q3.y), f2(0.f, 0.f), acc2);
       }
+      counts[0] += leaves0;
+      acc[0] += acc2[0].x + acc2[0].y; acc[1] += acc2[1].x + acc2[1].y; acc[2] += acc2[2].x + acc2[2].y;
       while (near) {
         const int jj = __ffsll((long long)near) - 1;
         near &= near - 1ull;

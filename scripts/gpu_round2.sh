@@ -1,6 +1,8 @@
 #!/bin/bash
-# round 2, eleventh GPU call: the kernels with the measured statement orders: GPU suite, product cubin vs the round-1 kernel,
-# the three staging variants (TMA bulk / cp.async / LDG->STS) on the final structure, bench at 1 M and 4 M.
+# gpurun --timeout 2400 -- bash scripts/gpu_round2.sh    - the recipe behind the round-2 one-GPU numbers of DESIGN.md: GPU suite,
+# product cubin against the round-1 kernel (kb_variants/r1: `git show cb1791d` sources built with its own kbench), the three
+# staging variants (TMA bulk / cp.async / LDG->STS; make -C omega3d_b200/csrc kbench kbench_stage), bench at 1 M and 4 M.
+# -> profiles/r02_pytest_gpu.txt, r02_kbench_product_vs_r1.txt, r02_bench_1gpu_{1m,4m}.json
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > gpurun_out/r2l_pytest.txt
