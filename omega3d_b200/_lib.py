@@ -12,7 +12,8 @@ import subprocess
 from ctypes import POINTER, c_char_p, c_double, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libo3d_cuda.so")
+# O3D_CUDA_LIB: an alternative build of the SAME library (make OUT=... EXTRA=-D..., A/B measurements); never a fallback
+LIB_PATH = os.environ.get("O3D_CUDA_LIB") or os.path.join(HERE, "lib", "libo3d_cuda.so")
 CSRC = os.path.join(HERE, "csrc")
 
 # every symbol include/o3d_cuda.h declares: (restype, argtypes)

@@ -199,12 +199,37 @@ __device__ __forceinline__ bool pan_node(float cx, float cy, float cz, float thr
   return false;
 }
 
+// s / 3 for two lanes: div3_rn on FMUL2 / FFMA2 (nothing here is a mul feeding an add, so nothing can be contracted)
+__device__ __forceinline__ float2 div3_rn2(float2 s) {
+  const float2 y = f2(0.3333333432674407958984375f, 0.3333333432674407958984375f);
+  const float2 q = __fmul2_rn(s, y);
+  const float2 r = __ffma2_rn(f2(-3.0f, -3.0f), q, s);
+  return __ffma2_rn(r, y, q);
+}
+// Two deepest-level children at once: vertex k of the two children in (ak, bk, ck).x/.y per coordinate. Always leaves.
+template <bool GRAD>
+__device__ __forceinline__ void pan_deepest2(float2 x0, float2 y0, float2 z0, float2 x1, float2 y1, float2 z1, float2 x2, float2 y2,
+                                             float2 z2, float tx, float ty, float tz, float wx, float wy, float wz, float q,
+                                             float2 (&acc)[PanAcc<GRAD>::N]) {
+  const float2 cx = div3_rn2(__fadd2_rn(__fadd2_rn(x0, x1), x2));     // (a + b + c) / 3 in the reference's order
+  const float2 cy = div3_rn2(__fadd2_rn(__fadd2_rn(y0, y1), y2));
+  const float2 cz = div3_rn2(__fadd2_rn(__fadd2_rn(z0, z1), z2));
+  const float2 m1 = f2(-1.0f, -1.0f);
+  const float2 dx = __ffma2_rn(cx, m1, f2(tx, tx)), dy = __ffma2_rn(cy, m1, f2(ty, ty)), dz = __ffma2_rn(cz, m1, f2(tz, tz));   // t - c, exactly
+  const float2 d2 = sumsq2_rn(dx, dy, dz);
+  const float2 rs = f2(rsqrt_approx(d2.x), rsqrt_approx(d2.y));
+  pan_leaf2<GRAD>(dx, dy, dz, rs, f2(wx, wx), f2(wy, wy), f2(wz, wz), f2(q, q), acc);
+}
+
 // Levels 1..3 of a (panel, point) pair whose level-0 node was NOT well separated. (wx,wy,wz,q) = total panel
 // strengths; thr0 = sq_threshold(4 sqrt(area)), the level-0 squared threshold. counts[0] += leaves, counts[1] += splits (the level-0 split included).
 template <bool GRAD>
 __device__ __forceinline__ void pan_subdivide(const Tri& p0, float thr0, float wx, float wy, float wz, float q, float tx,
                                               float ty, float tz, float (&acc)[PanAcc<GRAD>::N], unsigned (&counts)[2]) {
   counts[1] += 1;
+  float2 acc2[PanAcc<GRAD>::N];                     // the deepest level's leaves, two per instruction
+#pragma unroll
+  for (int k = 0; k < PanAcc<GRAD>::N; ++k) acc2[k] = f2(0.f, 0.f);
   const Mids m0 = tri_mids(p0);
   const float w1x = wx * 0.25f, w1y = wy * 0.25f, w1z = wz * 0.25f, q1 = q * 0.25f, thr1 = thr0 * 0.25f;
 #pragma unroll 1   // (unrolling this level too costs registers: 255 + spills in pts_pan_kernel)
@@ -229,14 +254,29 @@ __device__ __forceinline__ void pan_subdivide(const Tri& p0, float thr0, float w
       counts[1] += 1;
       const Mids m2 = tri_mids(p2);
       const float w3x = w2x * 0.25f, w3y = w2y * 0.25f, w3z = w2z * 0.25f, q3 = q2 * 0.25f;
-#pragma unroll   // deepest level, most of the visited nodes: unrolled so that each child is a static choice of registers, not selects
-      for (int k3 = 0; k3 < 4; ++k3) {
-        const Tri p3 = tri_child(p2, m2, k3);
-        pan_node<GRAD>(third_sum(p3.x0, p3.x1, p3.x2), third_sum(p3.y0, p3.y1, p3.y2), third_sum(p3.z0, p3.z1, p3.z2),
-                       0.0f, true, tx, ty, tz, w3x, w3y, w3z, q3, acc);
-        counts[0] += 1;
+      // deepest level, most of the visited nodes, and every one of them a leaf
+      if constexpr (!GRAD) {
+        // velocity only: children {0,1} and {2,3} go through the packed arithmetic two at a time (centroids by the exact packed /3,
+        // d = t - c as fma(c, -1, t), unfused squared distance). With gradients the 16 extra packed accumulators cost a resident
+        // CTA per SM (192 registers) or spills, and the gain is gone (measured: 3.19 -> 3.57 / 3.28 ms at 5 120 x 262 144).
+        pan_deepest2<GRAD>(f2(p2.x0, m2.ax), f2(p2.y0, m2.ay), f2(p2.z0, m2.az), f2(m2.ax, p2.x1), f2(m2.ay, p2.y1), f2(m2.az, p2.z1),
+                           f2(m2.bx, m2.cx), f2(m2.by, m2.cy), f2(m2.bz, m2.cz), tx, ty, tz, w3x, w3y, w3z, q3, acc2);
+        pan_deepest2<GRAD>(f2(m2.ax, m2.bx), f2(m2.ay, m2.by), f2(m2.az, m2.bz), f2(m2.cx, m2.cx), f2(m2.cy, m2.cy), f2(m2.cz, m2.cz),
+                           f2(m2.bx, p2.x2), f2(m2.by, p2.y2), f2(m2.bz, p2.z2), tx, ty, tz, w3x, w3y, w3z, q3, acc2);
+      } else {
+#pragma unroll   // unrolled so that each child is a static choice of registers, not selects
+        for (int k3 = 0; k3 < 4; ++k3) {
+          const Tri p3 = tri_child(p2, m2, k3);
+          pan_node<GRAD>(third_sum(p3.x0, p3.x1, p3.x2), third_sum(p3.y0, p3.y1, p3.y2), third_sum(p3.z0, p3.z1, p3.z2),
+                         0.0f, true, tx, ty, tz, w3x, w3y, w3z, q3, acc);
+        }
       }
+      counts[0] += 4;
     }
+  }
+  if constexpr (!GRAD) {
+#pragma unroll
+    for (int k = 0; k < PanAcc<GRAD>::N; ++k) acc[k] += acc2[k].x + acc2[k].y;
   }
 }
 

@@ -17,6 +17,10 @@
 #pragma once
 #include "biot_pp.cuh"
 
+#ifndef O3D_PPC_NOBAR
+#define O3D_PPC_NOBAR 0   // as O3D_PP_NOBAR (biot_pp.cuh) for the alternate-core kernels: 1 = the velocity+gradient ones run without the per-tile barrier
+#endif
+
 namespace o3d {
 
 constexpr int kCoreWL = 0, kCoreRM = 1, kCoreEXP = 2, kCoreV2 = 3;   // == O3D_CORE_* (include/o3d_cuda.h)
@@ -188,7 +192,8 @@ __device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
     if constexpr (GRAD) h[11] = -(h[3] + h[7]);
     pp_promote<GRAD>(h, sum[t]);
   }
-  pp_ring_refill<BLOCK, O3D_PP_NOBAR == 2>(p, w, tile[BUF], &sy.full[BUF], &sy.released[BUF]);         // ++w.kring
+  constexpr bool NOBAR = (O3D_PPC_NOBAR == 1 && GRAD) || O3D_PPC_NOBAR == 2 || O3D_PP_NOBAR == 2;
+  pp_ring_refill<BLOCK, NOBAR>(p, w, tile[BUF], &sy.full[BUF], &sy.released[BUF]);         // ++w.kring
   pp_segment_end<T, GRAD, BLOCK>(p, w, s, sum);
 }
 
