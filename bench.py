@@ -337,7 +337,7 @@ def run_ours(args, rank, world, local_rank):
             keep = [pinned(a) for a in (x_h, s_h, r_h, x_h[:, lo:hi], r_h[lo:hi], np.zeros((3, nloc), np.float32), np.zeros((9, nloc), np.float32))]
             hx, hs, hr, htx, htr, hu, hg = [k[1] for k in keep]
             long_steps = total_ms / steps > 5000.0              # (4 M on one GPU is 18.7 s a call: no separate warm-up call,
-            e2e_steps = max(1, min(steps, 2 if long_steps else args.e2e_steps))   # its allocations are ~ms of the first one)
+            e2e_steps = max(1, min(steps, 1 if long_steps else args.e2e_steps))   # its allocations are ~ms of the first one)
             if not (long_steps or args.e2e_no_warmup):
                 eng.ctx.pts_on_pts(hx, hr, hs, htx, htr, hu, hg)     # warm-up (allocations)
             barrier()
