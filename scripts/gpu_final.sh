@@ -1,20 +1,24 @@
 #!/bin/bash
-# Round-end evidence in one gpurun call: all GPU tests, smoke, both bench arms at the default size, a 4M bench point,
-# the ncu launch list of the default bench command and one full ncu capture of the dominant kernel (256K: 40 replays of
-# a 75 ms launch instead of a 1.2 s one). Usage: gpurun --timeout 1700 -- bash scripts/gpu_final.sh
+# Round-end rehearsal of what the driver runs on a fresh box: the GPU suite, smoke(), both bench arms with the driver's flags
+# (--steps 20 --warmup 5) at the default (north-star) size, with wall-clock times. Usage: gpurun --timeout 1800 -- bash scripts/gpu_final.sh
 set -u
+cd "$(dirname "$0")/.."
 OUT=gpurun_out; mkdir -p $OUT
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,power.limit --format=csv > $OUT/gpu.txt 2>&1
-echo "== pytest -m gpu"; timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -6 | tee $OUT/pytest_gpu.txt
-echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $OUT/smoke.txt
-echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>&1 | tail -1 | tee $OUT/bench_ref.json
-echo "== bench"; timeout 900 python bench.py 2>&1 | tail -1 | tee $OUT/bench.json
-echo "== bench 4M"; timeout 900 python bench.py --particles 4194304 --steps 2 --warmup 1 --e2e-steps 1 --no-cpu 2>&1 | tail -1 | tee $OUT/bench_4m.json
-echo "== ncu launch list (default bench command, 2 steps)"
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches_1m.csv \
-    python bench.py --steps 2 --warmup 1 --e2e-steps 1 > $OUT/bench_under_ncu.log 2>&1
-echo "== ncu full capture of the dominant kernel (N = 256K)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:pp2_kernel -s 1 -c 1 -f -o $OUT/pp2_full_256k \
-    python bench.py --steps 1 --warmup 1 --particles 262144 --no-cpu --e2e-steps 1 > $OUT/ncu_full.log 2>&1
-ncu -i $OUT/pp2_full_256k.ncu-rep --page raw --csv > $OUT/pp2_full_256k_raw.csv 2>/dev/null
-ls -la $OUT | tail -12
+t0=$(date +%s)
+timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4 | tee $OUT/final_pytest.txt
+t1=$(date +%s); echo "pytest -m gpu: $((t1-t0)) s"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $OUT/final_smoke.txt
+t2=$(date +%s); echo "smoke: $((t2-t1)) s"
+timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $OUT/final_bench_reference.json 2> $OUT/final_bench_reference.err
+t3=$(date +%s); echo "bench --impl reference: $((t3-t2)) s"
+timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $OUT/final_bench.json 2> $OUT/final_bench.err
+t4=$(date +%s); echo "bench: $((t4-t3)) s"
+python - <<'PY'
+import json
+for f in ("gpurun_out/final_bench_reference.json","gpurun_out/final_bench.json"):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, "%.4e"%d["value"], d["ms_per_step"], d.get("roofline",{}).get("frac"), d.get("roofline",{}).get("traffic"), d["e2e"]["value"], d.get("parity",{}).get("ok"), d["cpu_baseline"]["cores"])
+    except Exception as e: print(f, "failed", e)
+PY
+tail -2 $OUT/final_bench.err
