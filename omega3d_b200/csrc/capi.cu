@@ -342,10 +342,11 @@ bool d2h(Device& d, cudaStream_t st, void* dst, const void* src, size_t bytes) {
 // only lengthens the operand-reuse chains of adjacent packed FP32 instructions: identical instructions and results,
 // about 2 % fewer FMA-pipe cycles. Loaded once per process; a load failure is an error of o3d_cuda_create, not a
 // silent switch to the linked copies (those stay reachable through o3d_cuda_set_tuned_kernels(ctx, 0) for A/B tests).
-static_assert(kPPTgrad == 2 && kPPTvel == 4 && kPPBlock == 384, "kernel names below spell these template arguments");
+static_assert(kPPTgrad == 2 && kPPTvel == 4 && kPPBlock == 384 && kPPSmallBlock == 128, "kernel names below spell these template arguments");
 struct TunedKernels {
   cudaLibrary_t lib = nullptr;
   cudaKernel_t grad = nullptr, vel = nullptr;
+  cudaKernel_t grad_small = nullptr, vel_small = nullptr;   // the 128-thread instantiations (systems below one target block)
   cudaKernel_t core[4][2] = {};   // ppc_kernel<core, .., grad?>: [O3D_CORE_RM .. O3D_CORE_V2][0 = velocity only, 1 = with gradients]
   cudaError_t status = cudaSuccess;
   const char* where = "";
@@ -362,6 +363,14 @@ const TunedKernels& tuned_kernels() {
     if (k.status == cudaSuccess) {
       k.status = cudaLibraryGetKernel(&k.vel, k.lib, "_ZN3o3d10pp2_kernelILi4ELb0ELi384EEEvNS_6PPArgsE");
       k.where = "cudaLibraryGetKernel(pp2_kernel<4,false,384>)";
+    }
+    if (k.status == cudaSuccess) {
+      k.status = cudaLibraryGetKernel(&k.grad_small, k.lib, "_ZN3o3d10pp2_kernelILi2ELb1ELi128EEEvNS_6PPArgsE");
+      k.where = "cudaLibraryGetKernel(pp2_kernel<2,true,128>)";
+    }
+    if (k.status == cudaSuccess) {
+      k.status = cudaLibraryGetKernel(&k.vel_small, k.lib, "_ZN3o3d10pp2_kernelILi4ELb0ELi128EEEvNS_6PPArgsE");
+      k.where = "cudaLibraryGetKernel(pp2_kernel<4,false,128>)";
     }
     for (int core = O3D_CORE_RM; core <= O3D_CORE_V2 && k.status == cudaSuccess; ++core)
       for (int g = 0; g < 2 && k.status == cudaSuccess; ++g) {
@@ -381,7 +390,8 @@ const TunedKernels& tuned_kernels() {
 // 4 without, over a static stream-K partition of the (target block, source tile) units (csrc/biot_pp.cuh: PPPlan):
 // every CTA the same number of tiles (+-1) whatever the target count.
 struct PPShape {
-  int nblocks;        // target blocks of 384 * T targets
+  int block;          // threads per CTA: kPPBlock, or kPPSmallBlock for a system of at most one product-size target block
+  int nblocks;        // target blocks of block * T targets
   int grid;           // CTAs = min(units, resident slots)
   int64_t units;      // nblocks * ntiles
   int split_blocks;   // tail blocks shared by more than one CTA (finished by pp_fixup_kernel)
@@ -406,12 +416,14 @@ double pp_pair_flops(int core, bool grad, bool blob) { return (grad ? 54.0 : 23.
 // ... and of the panel leaves: flops_0vs_0pg = 79 + tp_grads, flops_0vs_0p = 29 + tp_nograds (src/Kernels.h:115,294); WL: 93 / 37
 double leaf_flops(int core, bool grad) { return (grad ? 79.0 : 29.0) + core_flops(core, grad, false); }
 
-PPShape pp_shape(int sm_count, int64_t ntiles, int64_t nt, bool grad) {
-  const int per_cta = kPPBlock * (grad ? kPPTgrad : kPPTvel);
+PPShape pp_shape(int sm_count, int64_t ntiles, int64_t nt, bool grad, bool wl_core = true) {
+  const int T = grad ? kPPTgrad : kPPTvel;
   PPShape s;
+  s.block = wl_core && nt <= (int64_t)kPPBlock * T ? kPPSmallBlock : kPPBlock;      // (the alternate cores ship as 384-thread kernels only)
+  const int per_cta = s.block * T;
   s.nblocks = (int)((nt + per_cta - 1) / per_cta);
   s.units = (int64_t)s.nblocks * ntiles;
-  s.plan = pp_make_plan(sm_count * kPPResident, s.nblocks, (int)ntiles);
+  s.plan = pp_make_plan(sm_count * (kPPWarpsPerSM * 32 / s.block), s.nblocks, (int)ntiles);
   s.grid = s.plan.P;
   s.split_blocks = 0;
   for (int j = 1; j < s.plan.Pt; ++j) {   // pp_fixup_kernel's own test: a boundary inside a block, the first one there
@@ -428,12 +440,12 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   // whether gradients are computed)
   const bool grad = want_grad < 0 ? tug != nullptr : want_grad != 0;
   const int64_t ntiles = nrec / kTile;
-  const PPShape s = pp_shape(d.sm_count, ntiles, nt, grad);
+  const PPShape s = pp_shape(d.sm_count, ntiles, nt, grad, d.core == O3D_CORE_WL);
   PPArgs a{};
   a.src = packed;
   a.ntiles = (int)ntiles;
   a.nblocks = s.nblocks;
-  a.slots = d.sm_count * kPPResident;
+  a.slots = d.sm_count * (kPPWarpsPerSM * 32 / s.block);
   a.nt = nt;
   a.tx = tx; a.ty = ty; a.tz = tz; a.tr = tr;
   a.tu = tu; a.tv = tv; a.tw = tw;
@@ -474,7 +486,11 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   } else if (d.tuned) {
     const TunedKernels& tk = tuned_kernels();
     void* params[] = {&a};
-    O3D_TRY(d, cudaLaunchKernel((const void*)(grad ? tk.grad : tk.vel), grid, dim3(kPPBlock), params, 0, st));
+    const bool small = s.block == kPPSmallBlock;
+    O3D_TRY(d, cudaLaunchKernel((const void*)(grad ? (small ? tk.grad_small : tk.grad) : (small ? tk.vel_small : tk.vel)), grid, dim3(s.block), params, 0, st));
+  } else if (s.block == kPPSmallBlock) {
+    if (grad) pp2_kernel<kPPTgrad, true, kPPSmallBlock><<<grid, kPPSmallBlock, 0, st>>>(a);
+    else      pp2_kernel<kPPTvel, false, kPPSmallBlock><<<grid, kPPSmallBlock, 0, st>>>(a);
   } else if (grad) {
     pp2_kernel<kPPTgrad, true, kPPBlock><<<grid, kPPBlock, 0, st>>>(a);
   } else {
@@ -485,7 +501,7 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   d.launches += 1;
   if (s.plan.Pt > 1) {
     // the tail blocks cut by a CTA-range boundary: add their pieces in unit order (one CTA per boundary)
-    pp_fixup_kernel<<<(unsigned)(s.plan.Pt - 1), 256, 0, st>>>(grad ? 12 : 3, kPPBlock * (grad ? kPPTgrad : kPPTvel), s.plan, nt, a.partial, tu, tv, tw,
+    pp_fixup_kernel<<<(unsigned)(s.plan.Pt - 1), 256, 0, st>>>(grad ? 12 : 3, s.block * (grad ? kPPTgrad : kPPTvel), s.plan, nt, a.partial, tu, tv, tw,
                                                              tug, tug_stride, 1.0f, a.acc64, a.acc_stride);
     O3D_TRY(d, cudaGetLastError());
     d.launches += 1;
@@ -1576,7 +1592,7 @@ int o3d_cuda_plan_check(int sm_count, int64_t ns, int64_t nt, int want_grad) {
   const int ntiles = (int)(padded_sources(ns) / kTile);
   const PPShape s = pp_shape(sm_count, ntiles, nt, grad);
   const PPPlan plan = s.plan;
-  if (s.grid < 1 || s.grid > sm_count * kPPResident || plan.begin(0) != 0 || plan.begin(s.grid) != plan.Wt || plan.Pt > plan.P) return 1;
+  if (s.grid < 1 || s.grid > sm_count * (kPPWarpsPerSM * 32 / s.block) || plan.begin(0) != 0 || plan.begin(s.grid) != plan.Wt || plan.Pt > plan.P) return 1;
   if ((int64_t)plan.P * plan.full * ntiles + plan.Wt != s.units) return 1;
   std::vector<int> tiles_done(s.nblocks, 0), whole(s.nblocks, 0), fixed(s.nblocks, 0);
   std::vector<int> slot_block((size_t)s.grid * kPPSlots, -1), slot_tiles((size_t)s.grid * kPPSlots, 0), slot_read((size_t)s.grid * kPPSlots, 0);

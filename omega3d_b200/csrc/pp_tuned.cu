@@ -10,6 +10,9 @@
 
 template __global__ void o3d::pp2_kernel<o3d::kPPTgrad, true, o3d::kPPBlock>(const o3d::PPArgs);
 template __global__ void o3d::pp2_kernel<o3d::kPPTvel, false, o3d::kPPBlock>(const o3d::PPArgs);
+// ... and as 128-thread CTAs for systems smaller than one product-size target block
+template __global__ void o3d::pp2_kernel<o3d::kPPTgrad, true, o3d::kPPSmallBlock>(const o3d::PPArgs);
+template __global__ void o3d::pp2_kernel<o3d::kPPTvel, false, o3d::kPPSmallBlock>(const o3d::PPArgs);
 
 // the alternate core functions (o3d_cuda_set_core_func): Rosenhead-Moore, exponential, Vatistas n=2
 template __global__ void o3d::ppc_kernel<o3d::kCoreRM, o3d::kPPTgrad, true, o3d::kPPBlock>(const o3d::PPArgs);

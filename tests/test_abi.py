@@ -164,7 +164,7 @@ def test_launch_plan_fills_the_gpu_at_the_benchmark_sizes():
     # tiny target counts: the source tiles of the one target block are dealt out over the CTAs
     grid, sp, bal, ws = c_int64(), c_int(), c_double(), c_int64()
     assert lib.o3d_cuda_plan_pts_on_pts(148, 100000, 320, 0, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
-    assert grid.value == 148 and sp.value == 1            # 196 tiles of 512 sources, one block of 1536 targets, 148 CTAs
+    assert grid.value == 196 and sp.value == 1            # a system below one 1536-target block runs as 128-thread CTAs: 196 tiles, one block of 512 targets
     assert lib.o3d_cuda_plan_pts_on_pts(148, 700, 5, 1, byref(grid), byref(sp), byref(bal), byref(ws)) == 0
     assert grid.value == 2 and sp.value == 1              # 700 sources are two 512-record tiles
     assert lib.o3d_cuda_plan_pts_on_pts(148, 100, 100, 1, byref(grid), byref(sp), byref(bal), byref(ws)) == 0

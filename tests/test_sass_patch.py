@@ -14,8 +14,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "omega3d_b200", "lib")
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
-KERNELS = ["_ZN3o3d10pp2_kernelILi2ELb1ELi384EEEvNS_6PPArgsE", "_ZN3o3d10pp2_kernelILi4ELb0ELi384EEEvNS_6PPArgsE"]
-# ... and the alternate-core kernels (csrc/biot_pp_cores.cuh): ppc_kernel<core 1..3, T, grad, 128>
+KERNELS = ["_ZN3o3d10pp2_kernelILi2ELb1ELi384EEEvNS_6PPArgsE", "_ZN3o3d10pp2_kernelILi4ELb0ELi384EEEvNS_6PPArgsE",
+           "_ZN3o3d10pp2_kernelILi2ELb1ELi128EEEvNS_6PPArgsE", "_ZN3o3d10pp2_kernelILi4ELb0ELi128EEEvNS_6PPArgsE"]   # + the small-system CTAs
+# ... and the alternate-core kernels (csrc/biot_pp_cores.cuh): ppc_kernel<core 1..3, T, grad, 384>
 KERNELS += [f"_ZN3o3d10ppc_kernelILi{c}ELi{t}ELb{g}ELi384EEEvNS_6PPArgsE" for c in (1, 2, 3) for t, g in ((2, 1), (4, 0))]
 
 
