@@ -11,6 +11,7 @@
 #include <cstring>
 #include <cuda.h>
 #include "pp_scalar.cuh"   // the scalar-FFMA kernel with its gridDim.y split (not a product kernel) + ../biot_pp.cuh
+#include "../biot_pp_cores.cuh"   // KBENCH_CORE: the alternate-core kernels from cubin files
 
 using namespace o3d;
 #define O3D_STR2(x) #x
@@ -50,7 +51,10 @@ int main(int argc, char** argv) {
   float4 *pk, *pk2;
   CHECK(cudaMalloc(&pk, npad * 32)); CHECK(cudaMalloc(&pk2, npad * 32));
   pp_pack_kernel<<<(npad + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk);
-  pp_pack2_kernel<<<(npad / 2 + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk2);
+  // KBENCH_CORE=1|2|3 (Rosenhead-Moore | exponential | Vatistas): the cubins hold ppc_kernel<core, ..>, the stream carries that core's radius lane
+  const int kcore = getenv("KBENCH_CORE") ? atoi(getenv("KBENCH_CORE")) : 0;
+  if (kcore) ppc_pack2_kernel<<<(npad / 2 + 255) / 256, 256>>>(kcore, n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk2);
+  else pp_pack2_kernel<<<(npad / 2 + 255) / 256, 256>>>(n, npad, d[0], d[1], d[2], d[3], d[4], d[5], d[6], pk2);
   float* out; CHECK(cudaMalloc(&out, (size_t)n * 12 * 4));
   double* partial; CHECK(cudaMalloc(&partial, (size_t)n * 12 * 8 * 4));  // scalar kernel: up to 4 source slices
   // packed kernel: persistent CTAs, 3 per SM (capi.cu: pp_shape), 2 workspace slots each
@@ -124,7 +128,7 @@ int main(int argc, char** argv) {
     a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
     a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = grad ? out + 3 * (size_t)n : nullptr; a.tug_stride = n;
     a.partial = ppwork; a.sign = 1.0f;
-    a.radius_range = no_uniform ? nullptr : range;
+    a.radius_range = no_uniform || kcore ? nullptr : range;
     a.slots = prop.multiProcessorCount * per_sm;
     const PPPlan plan = pp_make_plan(a.slots, a.nblocks, a.ntiles);
     const int grid = plan.P;
@@ -185,8 +189,15 @@ int main(int argc, char** argv) {
       if (path.empty()) continue;
       CUmodule mod; CUfunction fn;
       if (cuModuleLoad(&mod, path.c_str()) != CUDA_SUCCESS) { printf("cannot load %s\n", path.c_str()); continue; }
-      struct { const char* sym; int T; bool grad; } kinds[] = {{"_ZN3o3d10pp2_kernelILi2ELb1ELi" O3D_STR(O3D_PP_BLOCK) "EEEvNS_6PPArgsE", 2, true},
-                                                             {"_ZN3o3d10pp2_kernelILi4ELb0ELi" O3D_STR(O3D_PP_BLOCK) "EEEvNS_6PPArgsE", 4, false}};
+      char sg[96], sv[96];
+      if (kcore) {
+        snprintf(sg, sizeof sg, "_ZN3o3d10ppc_kernelILi%dELi2ELb1ELi" O3D_STR(O3D_PP_BLOCK) "EEEvNS_6PPArgsE", kcore);
+        snprintf(sv, sizeof sv, "_ZN3o3d10ppc_kernelILi%dELi4ELb0ELi" O3D_STR(O3D_PP_BLOCK) "EEEvNS_6PPArgsE", kcore);
+      } else {
+        snprintf(sg, sizeof sg, "_ZN3o3d10pp2_kernelILi2ELb1ELi" O3D_STR(O3D_PP_BLOCK) "EEEvNS_6PPArgsE");
+        snprintf(sv, sizeof sv, "_ZN3o3d10pp2_kernelILi4ELb0ELi" O3D_STR(O3D_PP_BLOCK) "EEEvNS_6PPArgsE");
+      }
+      struct { const char* sym; int T; bool grad; } kinds[] = {{sg, 2, true}, {sv, 4, false}};
       for (auto& kd : kinds) {
         if (cuModuleGetFunction(&fn, mod, kd.sym) != CUDA_SUCCESS) continue;
         const std::string label = "cubin " + path + (kd.grad ? " velgrad" : " vel");
