@@ -2,7 +2,7 @@
 # 1-GPU size sweep of the headline kernel (BASELINE configs[4]): gpurun --timeout 400 -- bash scripts/gpu_sweep.sh
 set -u
 OUT=gpurun_out; mkdir -p $OUT; : > $OUT/bench_sweep_1gpu.jsonl
-for N in 262144 524288 2097152; do
+for N in 262144 524288 1048576 2097152; do
   timeout 200 python bench.py --particles $N --steps 3 --warmup 3 --e2e-steps 1 --cpu-seconds 3 2>&1 | tail -1 >> $OUT/bench_sweep_1gpu.jsonl
 done
 python - <<'PY'
