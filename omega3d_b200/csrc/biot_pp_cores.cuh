@@ -56,11 +56,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // pick one per lane (FSEL). At |d| = 0 the unselected arms hold inf / NaN exactly as the reference's scalar code would
 // have produced had it evaluated them; selects do not propagate them (reld3 = 0 takes the "< 0.001" arm: r3 = corefac,
 // bbb = -1.5 * 0 * r3 * r3 = -0). Four MUFU per lane: SQRT, two RCP, EX2 (exp(-x) = 2^(-x log2 e)).
-template <bool GRAD>
+// UNI: one core radius in the system - st is a kernel-wide constant and arrives as its reciprocal cf already (one MUFU.RCP per
+// lane less, and no add).
+template <bool GRAD, bool UNI>
 __device__ __forceinline__ void exp_core2(const float2 dsq, const float2 st, float2& r3, float2& bbb) {
   const float2 dist = f2(sqrt_approx(dsq.x), sqrt_approx(dsq.y));
   const float2 d3 = __fmul2_rn(dsq, dist);
-  const float2 cf = f2(rcp_approx(st.x), rcp_approx(st.y));
+  const float2 cf = UNI ? st : f2(rcp_approx(st.x), rcp_approx(st.y));
   const float2 reld3 = __fmul2_rn(d3, cf);
   const float2 ood3 = f2(rcp_approx(d3.x), rcp_approx(d3.y));
   const float2 xe = __fmul2_rn(reld3, f2(-1.4426950408889634f, -1.4426950408889634f));
@@ -99,7 +101,9 @@ __device__ __forceinline__ void exp_core2(const float2 dsq, const float2 st, flo
 #ifndef O3D_PPC_BODY_V2_VEL
 #define O3D_PPC_BODY_V2_VEL "ppc_body_v2_vel.inc"
 #endif
-template <int CORE, bool GRAD>
+// UNI (every source and every target radius equal, found by pp_scan_kernel as in pp2_kernel): tt already holds the pair term
+// st = lane + tt (exponential core: its reciprocal), the same bits every pair would have formed.
+template <int CORE, bool GRAD, bool UNI>
 __device__ __forceinline__ void ppc_interact2(const float4 q0, const float4 q1, const float4 q2, const float4 q3,
                                               const float2 tx, const float2 ty, const float2 tz, const float2 tt,
                                               float2 (&acc)[PPAcc<GRAD>::N]) {
@@ -123,11 +127,11 @@ __device__ __forceinline__ void ppc_interact2(const float4 q0, const float4 q1, 
   const float2 dx = __fadd2_rn(tx, f2(q0.x, q0.y));
   const float2 dy = __fadd2_rn(ty, f2(q0.z, q0.w));
   const float2 dz = __fadd2_rn(tz, f2(q1.x, q1.y));
-  const float2 st = __fadd2_rn(tt, f2(q1.z, q1.w));
+  const float2 st = UNI ? tt : __fadd2_rn(tt, f2(q1.z, q1.w));
   const float2 wx = f2(q2.x, q2.y), wy = f2(q2.z, q2.w), wz = f2(q3.x, q3.y);
   float2 r3, bbb = f2(0.f, 0.f);
   const float2 dsq = __ffma2_rn(dx, dx, __ffma2_rn(dy, dy, __fmul2_rn(dz, dz)));
-  exp_core2<GRAD>(dsq, st, r3, bbb);
+  exp_core2<GRAD, UNI>(dsq, st, r3, bbb);
   const float2 t1 = __fmul2_rn(dy, wz);
   const float2 t2 = __fmul2_rn(dx, wz);
   const float2 t3 = __fmul2_rn(dx, wy);
@@ -158,8 +162,8 @@ __device__ __forceinline__ void ppc_interact2(const float4 q0, const float4 q1, 
 }
 
 // One tile of a persistent CTA's walk out of ring buffer BUF: pp2_tile (biot_pp.cuh) with this file's interaction.
-template <int BUF, int CORE, int T, bool GRAD, int BLOCK>
-__device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s, float4 (&tile)[2][kTile * 2], PPSync& sy,
+template <int BUF, int CORE, int T, bool GRAD, bool UNI, int BLOCK>
+__device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s, float4 (&tile)[2][kTile * 2], PPSync& sy, const float ttu,
                                          float2 (&tx)[T], float2 (&ty)[T], float2 (&tz)[T], float2 (&tt)[T],
                                          float2 (&acc)[T][PPAcc<GRAD>::N], double (&sum)[T][GRAD ? 12 : 3]) {
   constexpr int NS = GRAD ? 12 : 3;
@@ -170,7 +174,7 @@ __device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
     for (int t = 0; t < T; ++t) {
       const int64_t i = min(base + (int64_t)t * BLOCK, p.nt - 1);
       tx[t] = f2(p.tx[i], p.tx[i]); ty[t] = f2(p.ty[i], p.ty[i]); tz[t] = f2(p.tz[i], p.tz[i]);
-      const float term = core_radius_term(CORE, p.tr ? p.tr[i] : 0.0f);
+      const float term = UNI ? ttu : core_radius_term(CORE, p.tr ? p.tr[i] : 0.0f);
       tt[t] = f2(term, term);
 #pragma unroll
       for (int k = 0; k < NS; ++k) sum[t][k] = 0.0;
@@ -182,7 +186,7 @@ __device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
   for (int j = 0; j < kTile / 2; ++j) {
     const float4 q0 = src[4 * j], q1 = src[4 * j + 1], q2 = src[4 * j + 2], q3 = src[4 * j + 3];
 #pragma unroll
-    for (int t = 0; t < T; ++t) ppc_interact2<CORE, GRAD>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tt[t], acc[t]);
+    for (int t = 0; t < T; ++t) ppc_interact2<CORE, GRAD, UNI>(q0, q1, q2, q3, tx[t], ty[t], tz[t], tt[t], acc[t]);
   }
 #pragma unroll
   for (int t = 0; t < T; ++t) {
@@ -197,16 +201,12 @@ __device__ __forceinline__ void ppc_tile(const PPArgs& p, PPWalk& w, PPBlock& s,
   pp_segment_end<T, GRAD, BLOCK>(p, w, s, sum);
 }
 
-template <int CORE, int T, bool GRAD, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) ppc_kernel(const PPArgs p) {
+template <int CORE, int T, bool GRAD, bool UNI, int BLOCK>
+__device__ __forceinline__ void ppc_walk(const PPArgs& p, PPWalk& w, float4 (&tile)[2][kTile * 2], PPSync& sy, const float ttu_in) {
   constexpr int NS = GRAD ? 12 : 3;
   constexpr int NA = PPAcc<GRAD>::N;
-  __shared__ alignas(128) float4 tile[2][kTile * 2];
-  __shared__ alignas(8) PPSync sy;
-
-  // persistent CTA: one loop over the tiles of its share, two per trip (ring buffer 0, 1), the target block changing at
-  // segment boundaries (pp2_walk, biot_pp.cuh)
-  PPWalk w = pp_ring_start<BLOCK>(p, tile, sy);
+  // (the constant passes through a warp reduction so that ptxas holds it in a uniform register, as in pp2_walk)
+  const float ttu = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(ttu_in)));
   float2 tx[T], ty[T], tz[T], tt[T];
   double sum[T][NS];
   float2 acc[T][NA];
@@ -217,9 +217,31 @@ __global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) ppc_kernel(
   }
   PPBlock s = pp_first_block(w);
   while (w.kring < w.nk) {
-    ppc_tile<0, CORE, T, GRAD, BLOCK>(p, w, s, tile, sy, tx, ty, tz, tt, acc, sum);
-    if (w.kring < w.nk) ppc_tile<1, CORE, T, GRAD, BLOCK>(p, w, s, tile, sy, tx, ty, tz, tt, acc, sum);
+    ppc_tile<0, CORE, T, GRAD, UNI, BLOCK>(p, w, s, tile, sy, ttu, tx, ty, tz, tt, acc, sum);
+    if (w.kring < w.nk) ppc_tile<1, CORE, T, GRAD, UNI, BLOCK>(p, w, s, tile, sy, ttu, tx, ty, tz, tt, acc, sum);
   }
+}
+
+template <int CORE, int T, bool GRAD, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, kPPWarpsPerSM * 32 / BLOCK) ppc_kernel(const PPArgs p) {
+  __shared__ alignas(128) float4 tile[2][kTile * 2];
+  __shared__ alignas(8) PPSync sy;
+
+  // persistent CTA: one loop over the tiles of its share, two per trip (ring buffer 0, 1), the target block changing at
+  // segment boundaries (pp2_walk, biot_pp.cuh)
+  PPWalk w = pp_ring_start<BLOCK>(p, tile, sy);
+  // radius scan (pp_scan_kernel over this core's radius lane): uniform <=> one lane value among the sources that carry
+  // strength and one target radius. The pair term st = lane + core_radius_term(tr) is then a constant of the launch.
+  bool uni = false;
+  float ttu = 0.0f;
+  if (p.radius_range) {
+    const uint32_t s0 = ~p.radius_range[0], s1 = p.radius_range[1], t0 = ~p.radius_range[2], t1 = p.radius_range[3];
+    const float st = __fadd_rn(core_radius_term(CORE, p.tr ? __uint_as_float(t0) : 0.0f), __uint_as_float(s0));   // tt + lane, as every pair forms it
+    uni = s0 == s1 && (!p.tr || t0 == t1) && s0 != 0xffffffffu && st > 0.0f;
+    ttu = CORE == kCoreEXP ? rcp_approx(st) : st;
+  }
+  if (uni) ppc_walk<CORE, T, GRAD, true, BLOCK>(p, w, tile, sy, ttu);
+  else     ppc_walk<CORE, T, GRAD, false, BLOCK>(p, w, tile, sy, 0.0f);
 }
 
 // pp_pack2_kernel's record layout with the radius lane of the selected core (core_radius_term); padding records keep

@@ -457,8 +457,9 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   // fixed-size, allocated once per device and never moved: captured CUDA graphs may hold its address
   O3D_TRY(d, d.ppwork.ensure(pp_workspace_bytes(d.sm_count)));
   a.partial = d.ppwork.as<double>();
-  if (d.core == O3D_CORE_WL) {
-    // radius ranges for the uniform-radius fast path (one pass over the records' r^2 lane and the target radii)
+  {
+    // radius ranges for the uniform-radius fast path (one pass over the records' radius lane - r^2, r^3 or r^4 by core - and
+    // the target radii)
     O3D_TRY(d, d.rng.ensure(4 * sizeof(uint32_t)));
     O3D_TRY(d, cudaMemsetAsync(d.rng.p, 0, 4 * sizeof(uint32_t), st));
     pp_scan_kernel<<<d.sm_count * 4, 256, 0, st>>>(nrec, packed, nt, tr, d.rng.as<uint32_t>());
@@ -470,7 +471,6 @@ bool launch_pp(Device& d, cudaStream_t st, int64_t nrec, const float4* packed, i
   if (d.profile) O3D_TRY(d, cudaEventRecord(d.evk[0], st));
   if (d.core != O3D_CORE_WL) {
     // the alternate core functions of src/CoreFunc.h (csrc/biot_pp_cores.cuh); the stream was packed for d.core
-    a.radius_range = nullptr;
     if (d.tuned) {   // the post-processed copy (same instructions and results; tools/sass_patch.py)
       void* params[] = {&a};
       O3D_TRY(d, cudaLaunchKernel((const void*)tuned_kernels().core[d.core][grad ? 1 : 0], grid, dim3(kPPBlock), params, 0, st));

@@ -128,7 +128,7 @@ int main(int argc, char** argv) {
     a.tx = d[0]; a.ty = d[1]; a.tz = d[2]; a.tr = d[3];
     a.tu = out; a.tv = out + n; a.tw = out + 2 * (size_t)n; a.tug = grad ? out + 3 * (size_t)n : nullptr; a.tug_stride = n;
     a.partial = ppwork; a.sign = 1.0f;
-    a.radius_range = no_uniform || kcore ? nullptr : range;
+    a.radius_range = no_uniform ? nullptr : range;
     a.slots = prop.multiProcessorCount * per_sm;
     const PPPlan plan = pp_make_plan(a.slots, a.nblocks, a.ntiles);
     const int grid = plan.P;

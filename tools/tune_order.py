@@ -151,7 +151,9 @@ def emit(order, swaps):
         def v(x):
             return f"neg2({x[1:]})" if x.startswith("-") else x
         decl = "" if res.startswith("acc[") else "const float2 "
-        if op == "add":
+        if op == "add" and res == "st":   # alternate cores: with one radius in the system the pair term arrives precomputed in tt
+            out.append(f"    {decl}{res} = UNI ? tt : __fadd2_rn({v(a)}, {v(b)});\n")
+        elif op == "add":
             out.append(f"    {decl}{res} = __fadd2_rn({v(a)}, {v(b)});\n")
         elif op == "mul":
             out.append(f"    {decl}{res} = __fmul2_rn({v(a)}, {v(b)});\n")
@@ -319,7 +321,7 @@ def parse_body(path):
     """Recover (order, swaps) from a body file written by emit()."""
     order, swaps = [], set()
     for line in open(path):
-        m = re.match(r"\s+(?:const float2 )?([\w\[\]]+) = (__f\w+2_rn|f2)\((.*)\);", line)
+        m = re.match(r"\s+(?:const float2 )?([\w\[\]]+) = (?:UNI \? tt : )?(__f\w+2_rn|f2)\((.*)\);", line)
         if not m or line.lstrip().startswith(("const float2 sx =", "const float2 wx =", "const float2 r2 = tr2", "const float2 sr2 = f2(q1", "const float2 sl = f2(q1")):
             continue
         res = m.group(1)
