@@ -47,6 +47,8 @@ def gen(base, count, seed, slack):
     seen = {(tuple(order), swaps)}
     while len(cands) < count:
         m = T.mutate(rng, order, swaps)
+        for _ in range(int(os.environ.get("O3D_TUNE_WIDE", "1")) - 1):   # wider steps: several rounds of 1-3 edits per candidate
+            m = T.mutate(rng, *m)
         key = (tuple(m[0]), m[1])
         if key not in seen:
             seen.add(key)
