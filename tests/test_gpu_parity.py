@@ -150,6 +150,33 @@ def test_pts_on_pts_vs_oracle(cuda_ctx, restate, ns, nt, blob, grad):
         assert rel_err(a_g, b_g) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("ns,nt,grad", [(5003, 250001, True), (777, 130000, True), (1500, 400003, False), (513, 114000, True)])
+def test_whole_blocks_then_tail_shapes_vs_oracle(cuda_ctx, restate, ns, nt, grad):
+    """Target counts above one sweep of the persistent CTAs (148 x 768 with gradients, 148 x 1536 without): every CTA
+    finishes whole target blocks in place (phase A), then takes its share of the stream-K tail, with odd tile counts and a
+    ragged last block; the initial outputs are non-zero (+=). A strided sample of the targets against the oracle, and every
+    target's trace-free gradient."""
+    sx, ss, _ = W.random_cloud(ns, seed=100 + ns)
+    sr = W.varied_radii(ns, 200 + ns, 0.5 * ns ** (-1 / 3), 2.0 * ns ** (-1 / 3))
+    tx, _, _ = W.random_cloud(nt, seed=300 + nt)
+    tr = W.varied_radii(nt, 400 + nt, 0.5 * ns ** (-1 / 3), 2.0 * ns ** (-1 / 3))
+    rng = np.random.Generator(np.random.MT19937(nt))
+    u0 = (rng.standard_normal((3, nt)) * 1e-3).astype(f32)
+    g0 = (rng.standard_normal((9, nt)) * 1e-2).astype(f32) if grad else None
+    a_u, a_g = u0.copy(), (g0.copy() if grad else None)
+    cuda_ctx.pts_on_pts(sx, sr, ss, tx, tr, a_u, a_g)
+    sel = np.unique(np.concatenate([W.strided_subset(nt, 400), np.arange(nt - 40, nt), np.arange(0, 40)]))
+    b_u = np.ascontiguousarray(u0[:, sel])
+    b_g = np.ascontiguousarray(g0[:, sel]) if grad else None
+    restate.pts_on_pts(sx, sr, ss, np.ascontiguousarray(tx[:, sel]), np.ascontiguousarray(tr[sel]), b_u, b_g)
+    assert rel_err(a_u[:, sel] - u0[:, sel], b_u - u0[:, sel]) <= VEL_TOL
+    if grad:
+        assert rel_err(a_g[:, sel] - g0[:, sel], b_g - g0[:, sel]) <= GRAD_TOL
+        d = a_g - g0
+        assert np.max(np.abs(d[0] + d[4] + d[8])) <= 2e-4 * np.max(np.abs(d))
+    assert np.all(np.isfinite(a_u))
+
+
 def test_empty_inputs_are_noops(cuda_ctx):
     x0 = np.zeros((3, 0), f32); r0 = np.zeros(0, f32)
     x, s, r = W.random_cloud(10, seed=5)
