@@ -214,6 +214,9 @@ struct o3d_ctx {
   double kernel_ms = 0, h2d_ms = 0, d2h_ms = 0;
   int launches = 0;
   bool use_graphs = true;   // o3d_cuda_set_graphs
+  bool sources_pcie_all = false;   // O3D_CUDA_SOURCES_PCIE_ALL=1 (A/B measurement): every device of a multi-device context uploads and
+                                   // packs the sources itself (round 1) instead of device 0 uploading once and the peers pulling the
+                                   // packed records over NVLink
 };
 
 namespace {
@@ -1080,6 +1083,7 @@ int o3d_cuda_create(o3d_ctx** out, int ndev, const int* devices) {
   const int have = o3d_cuda_device_count();
   if (have < 1 || ndev > have) return O3D_ERR_NODEVICE;
   o3d_ctx* c = new o3d_ctx();
+  { const char* e = getenv("O3D_CUDA_SOURCES_PCIE_ALL"); c->sources_pcie_all = e && e[0] == '1'; }
   c->dev.resize(ndev);
   const char* env_tuned = getenv("O3D_CUDA_TUNED");          // "0": start with the linked copies of pp2_kernel
   const bool want_tuned = !(env_tuned && env_tuned[0] == '0');
@@ -1213,8 +1217,9 @@ int o3d_cuda_pts_on_pts(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
     if (n == 0 && k != 0) return true;       // device 0 always packs: its peers wait for it
     if (cudaSetDevice(d.id) != cudaSuccess) { d.status = cudaGetLastError(); d.where = "cudaSetDevice"; return bail(); }
     const int nout = grad ? 12 : 3;
+    const bool own_sources = k == 0 || c->sources_pcie_all;
     auto prep = [&]() {
-      if (k == 0) O3D_TRY(d, d.src.ensure((size_t)7 * ns * 4));
+      if (own_sources) O3D_TRY(d, d.src.ensure((size_t)7 * ns * 4));
       O3D_TRY(d, d.packed.ensure((size_t)nrec * 32));
       O3D_TRY(d, d.targ.ensure((size_t)4 * std::max<int64_t>(n, 1) * 4));
       O3D_TRY(d, d.out.ensure((size_t)nout * std::max<int64_t>(n, 1) * 4));
@@ -1228,13 +1233,13 @@ int o3d_cuda_pts_on_pts(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
     float* dout = d.out.as<float>();
     auto upload_sources = [&]() {
       O3D_TRY(d, cudaEventRecord(d.ev[0], st));
-      if (k == 0) {
+      if (own_sources) {
         const float* hs[7] = {sx, sy, sz, sr, ssx, ssy, ssz};
         for (int a = 0; a < 7; ++a)
           if (!h2d(d, st, ds + (size_t)a * ns, hs[a], (size_t)ns * 4)) return false;
         if (!launch_pack(d, st, ns, ds, ds + ns, ds + 2 * ns, ds + 3 * ns, ds + 4 * ns, ds + 5 * ns, ds + 6 * ns, d.packed.as<float4>()))
           return false;
-        if (ndev > 1) O3D_TRY(d, cudaEventRecord(d.evx[0], st));
+        if (ndev > 1 && k == 0) O3D_TRY(d, cudaEventRecord(d.evx[0], st));
       }
       return true;
     };
@@ -1245,7 +1250,7 @@ int o3d_cuda_pts_on_pts(o3d_ctx* c, int64_t ns, const float* sx, const float* sy
       O3D_TRY(d, cudaStreamSynchronize(st));
       return true;
     }
-    if (k != 0) {
+    if (!own_sources) {
       int state;
       while ((state = packed_posted.load()) == 0) std::this_thread::yield();
       if (state < 0) return true;            // device 0 reports the error
