@@ -203,7 +203,9 @@ int o3d_cuda_set_panel_queue(o3d_ctx* ctx, int on);
 /* Host arrays of the entry points above may be pageable (the reference's std::vector storage) or pinned. Pageable arrays
  * travel through a ring of pinned slots the context owns (4 x 8 MB per device; helper threads fill the next slot while the
  * DMA engine moves the previous one; O3D_CUDA_COPY_THREADS sets their number); pinned ones go to the DMA engine directly.
- * off = hand every pointer to cudaMemcpyAsync as it comes (the driver's own bounce buffers) - for A/B measurements. */
+ * off = hand every pointer to cudaMemcpyAsync as it comes (the driver's own bounce buffers) - for A/B measurements.
+ * With ndev > 1 the sources go to device 0 once and reach the other devices as packed records over NVLink; the environment
+ * variable O3D_CUDA_SOURCES_PCIE_ALL=1 (read by o3d_cuda_create) makes every device upload them itself instead (A/B only). */
 int o3d_cuda_set_host_staging(o3d_ctx* ctx, int on);
 /* CUDA-graph replay of repeated steps is on by default; off = launch every kernel individually (same results,
  * bit for bit - tests compare the two). o3d_cuda_particles_graph_active: 1 if the collection holds a captured step. */
