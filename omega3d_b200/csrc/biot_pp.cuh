@@ -19,14 +19,16 @@
 //     and applied in the epilogue instead of 6 FMA per interaction;
 //   * source tiles (512 records = 16 KB, contiguous) arrive by cp.async.bulk (TMA, SASS UBLKCP)
 //     into a 2-deep mbarrier ring - no thread spends registers or issue slots on the copy;
-//   * PERSISTENT CTAs over a static stream-K partition (PPPlan below): the work is the nblocks x ntiles
-//     grid of (target block, source tile) units in block-major order and CTA c of the P resident CTAs
-//     owns units [W c / P, W (c+1) / P). Every CTA streams the same number of tiles (+-1) whatever the
-//     target count - no last-wave quantisation, no source split - and the TMA ring runs straight
-//     through target-block boundaries. A target block that lies wholly inside one CTA's range is
-//     finished in place; the (at most P-1) blocks cut by a range boundary leave FP64 partial sums in a
-//     fixed-size workspace (2 slots per CTA) which pp_fixup_kernel adds in unit order: deterministic,
-//     no atomics, a few MB of traffic whatever the problem size;
+//   * ONE PERSISTENT 384-thread CTA per SM (the 12 warps x 168 registers the register file holds; co-resident CTAs are served
+//     in age order) over a static partition of the nblocks x ntiles grid of (target block, source tile) units
+//     (PPPlan below): every CTA first finishes nblocks / P WHOLE target blocks in place - all CTAs walk the source stream
+//     together, so a tile fetched from HBM by one is an L2 hit for the others - then takes an equal share of the units of the
+//     remaining < P blocks (stream-K). Every CTA streams the same number of tiles (+-1) whatever the target count - no
+//     last-wave quantisation, no source split - and the TMA ring runs straight through block and phase boundaries. The (at most
+//     P-1) tail blocks cut by a share boundary leave FP64 partial sums in a fixed-size workspace (2 slots per CTA) which
+//     pp_fixup_kernel adds in unit order: deterministic, no atomics, a few MB of traffic whatever the problem size;
+//   * in the velocity+gradient kernel no CTA-wide barrier per tile: every warp counts itself out of a ring buffer and the last
+//     one out issues the refill (O3D_PP_NOBAR);
 //   * sums are FP32 FMA chains inside one tile, promoted to FP64 once per tile (B200 keeps a full FP64
 //     pipe; 12 DADD per 512 interactions), mirroring the reference's float-kernel/double-accumulator
 //     scheme (src/Simulation.h:41-47) to ~1e-7 relative;
